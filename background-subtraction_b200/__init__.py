@@ -1,0 +1,12 @@
+"""background-subtraction_b200 -- B200-native (sm_100a) implementation of the inexact-ALM low-rank + structured-sparse
+decomposition of yakovdan/Background-Subtraction (the LSD / group-sparse RPCA hot path), behind the reference's own
+Python call surface.  All numerics run in libbsub_b200.so (hand-written CUDA) through the C ABI of
+include/bsub_b200.h; there is no CPU fallback."""
+from .api import (BLOCK_SIZE, Decomposition, LSD, block_shrinkage_operator, detect_flat_tiling, detect_window_graph,
+                  eig_topk, foreground_mask, getGraphSPAMS_all_groups, get_proximal_flat_groups_nonoverlap, gram,
+                  group_sparse_decomposition, inexact_alm_group_sparse_RPCA, inexact_alm_lsd, inexact_alm_rpca,
+                  labels_from_blocks, lsd_decomposition, make_config, normalizeImage, prox, prox_by_frame, prox_flat,
+                  resize_with_cv2, svd_k_largest, window_csc)
+from . import _cabi, build  # noqa: F401
+
+__all__ = [n for n in dir() if not n.startswith("_")]

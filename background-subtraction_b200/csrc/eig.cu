@@ -1,0 +1,489 @@
+// eig.cu -- device-resident top-K symmetric eigensolver for the frames x frames Gram matrix and the
+// data-dependent ALM control that follows it (no host round trip).
+//
+// Replaces the reference's svd_k_largest (/root/reference/utils.py:204-212: ARPACK svds or LAPACK gesdd on
+// the m x n matrix) plus the rank logic of /root/reference/inexact_alm_lsd.py:136-145: the right singular
+// vectors of W and sigma_i^2 are the eigenpairs of G = W^T W, so only the n x n problem is solved here.
+//
+// Algorithm (all fp64):
+//   1. Householder tridiagonalisation of G by ONE thread-block cluster: rows are dealt cyclically to the C
+//      CTAs of the cluster and kept in shared memory; per step the owner of row j builds the reflector, every
+//      CTA does its slice of the symmetric matrix-vector product and of the rank-2 update; the two exchanges
+//      per step go through L2 and are ordered by the hardware cluster barrier.
+//   2. The K largest eigenvalues of the tridiagonal matrix by parallel multisection on Sturm counts
+//      (every thread evaluates one shift per round; fixed number of rounds -> deterministic).
+//   3. Eigenvectors by inverse iteration (one thread per vector, pivoted tridiagonal LU), CGS2
+//      re-orthogonalisation, back-transformation through the stored reflectors (one warp per vector).
+//   4. Control: sigma = sqrt(lambda); svp = #{sigma_i > 1/mu, i < sv}; next sv (reference predictor);
+//      Vr and VC = Vr * diag(1 - 1/(mu sigma)) written in fp32 for the shrink pass.
+#include <cooperative_groups.h>
+#include <float.h>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace bsub {
+
+constexpr int EIG_THREADS = 512;
+constexpr int EIG_WARPS = EIG_THREADS / 32;
+constexpr int EIG_BT = 16;   // vectors back-transformed per batch (one warp each)
+
+struct EigArgs {
+    const double* G;           // [npad][npad]
+    const double* comm_max;    // [0] = max row-sum of |D| (init mode)
+    int n, npad, C, rows_per, in_smem, kcap, mode, k_override;
+    double* Aglob;             // [C][rows_per][n]  (only when !in_smem)
+    double* Vh;                // [n][n] reflectors
+    double* tau;               // [n]
+    double* dd;                // [n]
+    double* ee;                // [n]
+    double* pbuf;              // [2][n]
+    double* dotbuf;            // [2][16]
+    double* iw;                // inverse-iteration workspace [6][n][kcap]
+    double* lam;               // [n]
+    double* Z;                 // [n][n]
+    float* Vr; float* VC; int vstride;
+    DevState* st;
+};
+
+__device__ __forceinline__ double ldcg_d(const double* p) { return __ldcg(p); }
+
+// number of eigenvalues of the tridiagonal (d, e2 = e^2) that are < x   (LAPACK dlaebz-style pivmin guard)
+__device__ __forceinline__ int sturm_negcount(const double* d, const double* e2, int n, double x, double pivmin) {
+    double q = d[0] - x;
+    if (fabs(q) < pivmin) q = -pivmin;
+    int c = (q < 0.0);
+    for (int i = 1; i < n; ++i) {
+        q = d[i] - x - e2[i - 1] / q;
+        if (fabs(q) < pivmin) q = -pivmin;
+        c += (q < 0.0);
+    }
+    return c;
+}
+
+__device__ __forceinline__ double hash_unit(unsigned a, unsigned b) {
+    unsigned x = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u;
+    x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12; x *= 0x297A2D39u; x ^= x >> 15;
+    return ((double)(x & 0xFFFFFFu) / (double)0x1000000u) * 2.0 - 1.0;
+}
+
+__global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    DevState* st = a.st;
+    if (a.mode == 1 && st->done) return;          // uniform over the cluster
+    const int n = a.n, C = a.C, c = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int K = (a.mode == 0) ? 1 : ((a.mode == 1) ? st->sv : a.k_override);
+    if (K > n) K = n;
+    if (K < 1) K = 1;
+    const double mu = (a.mode == 1) ? st->mu : 0.0;
+
+    extern __shared__ __align__(16) double esm[];
+    double* v_s = esm;                 // [n]
+    double* w_s = esm + n;             // [n]
+    double* red = esm + 2 * n;         // [64]
+    double* Asm = esm + 2 * n + 64;    // matrix rows / later phases
+    __shared__ double bc[4];
+
+    auto Arow = [&](int li) -> double* {
+        return a.in_smem ? (Asm + (size_t)li * n) : (a.Aglob + ((size_t)c * a.rows_per + li) * n);
+    };
+
+    // ---- load my rows -------------------------------------------------------------------------------------
+    for (int li = warp; li < a.rows_per; li += EIG_WARPS) {
+        int i = c + li * C;
+        if (i < n) {
+            double* r = Arow(li);
+            const double* g = a.G + (size_t)i * a.npad;
+            for (int col = lane; col < n; col += 32) r[col] = g[col];
+        }
+    }
+    __syncthreads();
+
+    // ---- 1. Householder tridiagonalisation ------------------------------------------------------------------
+    for (int j = 0; j + 2 < n; ++j) {
+        const int par = j & 1;
+        if (c == (j % C)) {
+            const double* r = Arow(j / C);
+            double ss = 0.0;
+            for (int i = j + 2 + tid; i < n; i += EIG_THREADS) ss += r[i] * r[i];
+            ss = block_sum(ss, red);
+            if (tid == 0) {
+                double alpha = r[j + 1];
+                double beta, tau, scale;
+                if (ss == 0.0) { tau = 0.0; beta = alpha; scale = 0.0; }
+                else {
+                    beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+                    tau = (beta - alpha) / beta;
+                    scale = 1.0 / (alpha - beta);
+                }
+                bc[0] = scale;
+                a.tau[j] = tau; a.dd[j] = r[j]; a.ee[j] = beta;
+            }
+            __syncthreads();
+            const double scale = bc[0];
+            double* vh = a.Vh + (size_t)j * n;
+            for (int i = j + 1 + tid; i < n; i += EIG_THREADS) vh[i] = (i == j + 1) ? 1.0 : r[i] * scale;
+        }
+        cluster.sync();
+        const double tau = ldcg_d(a.tau + j);
+        if (tau != 0.0) {
+            const double* vh = a.Vh + (size_t)j * n;
+            for (int i = tid; i < n; i += EIG_THREADS) v_s[i] = (i > j) ? ldcg_d(vh + i) : 0.0;
+            __syncthreads();
+            double pv = 0.0;
+            for (int li = warp; li < a.rows_per; li += EIG_WARPS) {
+                int i = c + li * C;
+                if (i > j && i < n) {
+                    const double* r = Arow(li);
+                    double s = 0.0;
+                    for (int col = j + 1 + lane; col < n; col += 32) s += r[col] * v_s[col];
+                    s = warp_sum(s);
+                    double p = tau * s;
+                    if (lane == 0) { a.pbuf[par * n + i] = p; pv += p * v_s[i]; }
+                }
+            }
+            pv = block_sum(pv, red);
+            if (tid == 0) a.dotbuf[par * 16 + c] = pv;
+        }
+        cluster.sync();
+        if (tau != 0.0) {
+            double dot = 0.0;
+            for (int q = 0; q < C; ++q) dot += ldcg_d(a.dotbuf + par * 16 + q);
+            const double kc = -0.5 * tau * dot;
+            for (int i = tid; i < n; i += EIG_THREADS) w_s[i] = (i > j) ? (ldcg_d(a.pbuf + par * n + i) + kc * v_s[i]) : 0.0;
+            __syncthreads();
+            for (int li = warp; li < a.rows_per; li += EIG_WARPS) {
+                int i = c + li * C;
+                if (i > j && i < n) {
+                    double* r = Arow(li);
+                    const double vi = v_s[i], wi = w_s[i];
+                    for (int col = j + 1 + lane; col < n; col += 32) r[col] -= vi * w_s[col] + wi * v_s[col];
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // trailing 2x2 (or smaller)
+    if (tid == 0) {
+        if (n >= 2) {
+            if (c == ((n - 2) % C)) { const double* r = Arow((n - 2) / C); a.dd[n - 2] = r[n - 2]; a.ee[n - 2] = r[n - 1]; a.tau[n - 2] = 0.0; }
+            if (c == ((n - 1) % C)) { const double* r = Arow((n - 1) / C); a.dd[n - 1] = r[n - 1]; a.ee[n - 1] = 0.0; a.tau[n - 1] = 0.0; }
+        } else if (c == 0) { const double* r = Arow(0); a.dd[0] = r[0]; a.ee[0] = 0.0; a.tau[0] = 0.0; }
+    }
+    cluster.sync();
+    if (c != 0) return;
+
+    // ---- 2. top-K eigenvalues of the tridiagonal matrix: multisection on Sturm counts ------------------------
+    // shared-memory carve-up for the remaining phases (the matrix rows are dead now)
+    double* d_s = Asm;                 // [n]
+    double* e2_s = Asm + n;            // [n]
+    double* e_s = Asm + 2 * n;         // [n]
+    double* lo_s = Asm + 3 * n;        // [EIG_THREADS]
+    double* hi_s = lo_s + EIG_THREADS; // [EIG_THREADS]
+    double* nlo_s = hi_s + EIG_THREADS;
+    double* nhi_s = nlo_s + EIG_THREADS;
+    int* flag_s = reinterpret_cast<int*>(nhi_s + EIG_THREADS);   // [EIG_THREADS]
+    double* zs = nhi_s + EIG_THREADS + EIG_THREADS / 2;          // [EIG_BT][n]
+
+    double gl = 1e300, gu = -1e300, emax = 0.0;
+    for (int i = tid; i < n; i += EIG_THREADS) {
+        double di = ldcg_d(a.dd + i);
+        double ei = (i + 1 < n) ? ldcg_d(a.ee + i) : 0.0;
+        double em = (i > 0) ? fabs(ldcg_d(a.ee + i - 1)) : 0.0;
+        d_s[i] = di; e_s[i] = ei; e2_s[i] = ei * ei;
+        gl = fmin(gl, di - fabs(ei) - em);
+        gu = fmax(gu, di + fabs(ei) + em);
+        emax = fmax(emax, ei * ei);
+    }
+    gu = block_max(gu, red);
+    if (tid == 0) bc[0] = gu;
+    gl = -block_max(-gl, red);
+    if (tid == 0) bc[1] = gl;
+    emax = block_max(emax, red);
+    if (tid == 0) bc[2] = emax;
+    __syncthreads();
+    gu = bc[0]; gl = bc[1]; emax = bc[2];
+    const double tnorm = fmax(fabs(gl), fabs(gu));
+    const double pivmin = DBL_MIN * fmax(1.0, emax);
+    {
+        double widen = 2.1 * tnorm * DBL_EPSILON * n + 2.1 * pivmin;
+        gl -= widen; gu += widen;
+    }
+    for (int kb = 0; kb < K; kb += EIG_THREADS) {
+        const int Kb = min(K - kb, EIG_THREADS);
+        const int S = max(1, EIG_THREADS / Kb);
+        int rounds = (int)ceil(62.0 / log2((double)S + 1.0)) + 1;
+        for (int t = tid; t < Kb; t += EIG_THREADS) { lo_s[t] = gl; hi_s[t] = gu; }
+        __syncthreads();
+        const int kk = tid / S, s = tid - kk * S;
+        const bool active = kk < Kb;
+        for (int r = 0; r < rounds; ++r) {
+            double x = 0.0;
+            int f = 0;
+            if (active) {
+                const double lo = lo_s[kk], hi = hi_s[kk];
+                x = lo + (hi - lo) * ((double)(s + 1) / (double)(S + 1));
+                const int cnt_ge = n - sturm_negcount(d_s, e2_s, n, x, pivmin);   // # eigenvalues >= x
+                f = (cnt_ge >= kb + kk + 1);                                          // x <= lambda_k
+            }
+            flag_s[tid] = f;
+            nlo_s[tid] = x;
+            __syncthreads();
+            if (active) {
+                const int fn = (s + 1 < S) ? flag_s[tid + 1] : 0;
+                if (f && !fn) { lo_s[kk] = x; if (s + 1 < S) hi_s[kk] = nlo_s[tid + 1]; }
+                if (s == 0 && !f) hi_s[kk] = x;
+            }
+            __syncthreads();
+        }
+        for (int t = tid; t < Kb; t += EIG_THREADS) a.lam[kb + t] = 0.5 * (lo_s[t] + hi_s[t]);
+        __syncthreads();
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // ---- 3. eigenvectors of the tridiagonal matrix: inverse iteration, one thread per vector ---------------------
+    const int kcap = a.kcap;
+    for (int k = tid; k < K; k += EIG_THREADS) {
+        double lamk = a.lam[k];
+        double* Up = a.iw + (size_t)0 * n * kcap + k;
+        double* Uq = a.iw + (size_t)1 * n * kcap + k;
+        double* Ur = a.iw + (size_t)2 * n * kcap + k;
+        double* Mm = a.iw + (size_t)3 * n * kcap + k;
+        double* Sw = a.iw + (size_t)4 * n * kcap + k;
+        double* Bz = a.iw + (size_t)5 * n * kcap + k;
+        const double ptol = fmax(DBL_EPSILON * tnorm, pivmin);
+        // factor T - lam I = P L U  (partial pivoting; U has two super-diagonals)
+        double p = d_s[0] - lamk, q = (n > 1) ? e_s[0] : 0.0, rr = 0.0;
+        for (int i = 0; i + 1 < n; ++i) {
+            const double sub = e_s[i];
+            const double an = d_s[i + 1] - lamk;
+            const double en = (i + 2 < n) ? e_s[i + 1] : 0.0;
+            if (fabs(p) >= fabs(sub)) {
+                if (fabs(p) < ptol) p = copysign(ptol, p);
+                const double mlt = sub / p;
+                Up[(size_t)i * kcap] = p; Uq[(size_t)i * kcap] = q; Ur[(size_t)i * kcap] = rr;
+                Mm[(size_t)i * kcap] = mlt; Sw[(size_t)i * kcap] = 0.0;
+                p = an - mlt * q; q = en - mlt * rr; rr = 0.0;
+            } else {
+                const double mlt = p / sub;
+                Up[(size_t)i * kcap] = sub; Uq[(size_t)i * kcap] = an; Ur[(size_t)i * kcap] = en;
+                Mm[(size_t)i * kcap] = mlt; Sw[(size_t)i * kcap] = 1.0;
+                p = q - mlt * an; q = rr - mlt * en; rr = 0.0;
+            }
+        }
+        if (fabs(p) < ptol) p = copysign(ptol, p);
+        Up[(size_t)(n - 1) * kcap] = p; Uq[(size_t)(n - 1) * kcap] = 0.0; Ur[(size_t)(n - 1) * kcap] = 0.0;
+        for (int i = 0; i < n; ++i) Bz[(size_t)i * kcap] = hash_unit((unsigned)i, (unsigned)k);
+        for (int itn = 0; itn < 3; ++itn) {
+            // forward: apply P L^{-1}
+            for (int i = 0; i + 1 < n; ++i) {
+                double bi = Bz[(size_t)i * kcap], bn = Bz[(size_t)(i + 1) * kcap];
+                if (Sw[(size_t)i * kcap] != 0.0) { double t = bi; bi = bn; bn = t; }
+                bn -= Mm[(size_t)i * kcap] * bi;
+                Bz[(size_t)i * kcap] = bi; Bz[(size_t)(i + 1) * kcap] = bn;
+            }
+            // backward: solve U z = b
+            double z1 = 0.0, z2 = 0.0, zmax = 0.0;
+            for (int i = n - 1; i >= 0; --i) {
+                double z = (Bz[(size_t)i * kcap] - Uq[(size_t)i * kcap] * z1 - Ur[(size_t)i * kcap] * z2) / Up[(size_t)i * kcap];
+                Bz[(size_t)i * kcap] = z;
+                z2 = z1; z1 = z;
+                zmax = fmax(zmax, fabs(z));
+            }
+            const double sc = (zmax > 0.0) ? 1.0 / zmax : 1.0;
+            for (int i = 0; i < n; ++i) Bz[(size_t)i * kcap] *= sc;
+        }
+        double nn = 0.0;
+        for (int i = 0; i < n; ++i) { double z = Bz[(size_t)i * kcap]; nn += z * z; }
+        const double sc = 1.0 / sqrt(nn);
+        double* zrow = a.Z + (size_t)k * n;
+        for (int i = 0; i < n; ++i) zrow[i] = Bz[(size_t)i * kcap] * sc;
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // ---- 3b. CGS2 re-orthogonalisation among close eigenvalues (descending order) -------------------------------
+    {
+        const double ortol = 1e-3 * tnorm;
+        double* coef = lo_s;   // [<= EIG_THREADS] reuse
+        for (int k = 1; k < K; ++k) {
+            const double lamk = a.lam[k];
+            int j0 = k;
+            while (j0 > 0 && fabs(a.lam[j0 - 1] - lamk) <= ortol) --j0;
+            if (j0 == k) continue;                       // uniform across the block
+            double* zk = a.Z + (size_t)k * n;
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int jb = j0; jb < k; jb += EIG_THREADS) {
+                    const int je = min(k, jb + EIG_THREADS);
+                    for (int j = jb + warp; j < je; j += EIG_WARPS) {
+                        const double* zj = a.Z + (size_t)j * n;
+                        double s = 0.0;
+                        for (int i = lane; i < n; i += 32) s += zj[i] * zk[i];
+                        s = warp_sum(s);
+                        if (lane == 0) coef[j - jb] = s;
+                    }
+                    __syncthreads();
+                    for (int i = tid; i < n; i += EIG_THREADS) {
+                        double acc = zk[i];
+                        for (int j = jb; j < je; ++j) acc -= coef[j - jb] * a.Z[(size_t)j * n + i];
+                        zk[i] = acc;
+                    }
+                    __threadfence_block();
+                    __syncthreads();
+                }
+            }
+            double nn = 0.0;
+            for (int i = tid; i < n; i += EIG_THREADS) nn += zk[i] * zk[i];
+            nn = block_sum(nn, red);
+            if (tid == 0) bc[0] = nn;
+            __syncthreads();
+            const double sc = 1.0 / sqrt(bc[0]);
+            for (int i = tid; i < n; i += EIG_THREADS) zk[i] *= sc;
+            __threadfence_block();
+            __syncthreads();
+        }
+    }
+
+    // ---- 4. back-transformation z <- H_0 H_1 ... H_{n-3} z, one warp per vector ---------------------------------
+    for (int kb = 0; kb < K; kb += EIG_BT) {
+        const int k = kb + warp;
+        if (warp < EIG_BT && k < K) {
+            double* z = zs + (size_t)warp * n;
+            const double* zrow = a.Z + (size_t)k * n;
+            for (int i = lane; i < n; i += 32) z[i] = zrow[i];
+            __syncwarp();
+            for (int j = n - 3; j >= 0; --j) {
+                const double tau = a.tau[j];
+                if (tau == 0.0) continue;
+                const double* vh = a.Vh + (size_t)j * n;
+                double s = 0.0;
+                for (int i = j + 1 + lane; i < n; i += 32) s += vh[i] * z[i];
+                s = warp_sum(s) * tau;
+                for (int i = j + 1 + lane; i < n; i += 32) z[i] -= s * vh[i];
+                __syncwarp();
+            }
+            double* zout = a.Z + (size_t)k * n;
+            for (int i = lane; i < n; i += 32) zout[i] = z[i];
+        }
+        __syncthreads();
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // ---- 5. control ------------------------------------------------------------------------------------------
+    if (a.mode == 2) return;
+    if (a.mode == 0) {
+        double tr = 0.0;
+        for (int i = tid; i < n; i += EIG_THREADS) tr += a.G[(size_t)i * a.npad + i];
+        tr = block_sum(tr, red);
+        if (tid == 0) {
+            const double l0 = a.lam[0];
+            const double norm_two = sqrt(fmax(l0, 0.0));
+            st->norm_two = norm_two;
+            st->normD2 = tr;
+            st->norm_rowsum = a.comm_max[0];
+            st->dual_norm = fmax(norm_two, a.comm_max[0] / st->lambda);
+            st->mu = st->mu_scale / norm_two;
+            st->thresh = 1.0 / st->mu;
+            st->iter = 0; st->svp = 0; st->done = 0; st->converged = 0; st->zz = 0.0; st->err = 0.0;
+            st->maxS = 0.f; st->nnzS = 0ull;
+            if (!(norm_two > 0.0)) { st->done = 4; }       // all-zero input
+        }
+        return;
+    }
+    // mode 1
+    const double thresh = 1.0 / mu;
+    if (tid == 0) {
+        int svp = 0;
+        for (int k = 0; k < K; ++k) {
+            double sig = sqrt(fmax(a.lam[k], 0.0));
+            if (sig > thresh) svp = k + 1;               // last index with sigma > 1/mu (utils.py:215-217)
+        }
+        const int sv = K;
+        st->iter += 1;
+        st->sv_used = sv;                                // sv looked at this iteration
+        st->svp = svp;
+        st->thresh = thresh;
+        int svn = sv;
+        if (st->use_sv_prediction) svn = (svp < sv) ? svp + 1 : min(svp + st->round005d, st->d);
+        st->sv = svn;                                    // inexact_alm_lsd.py:145
+        if (st->break_on_rank0 && svp == 0) st->done = 3;  // group_sparse_RPCA.py:91-93
+        bc[0] = (double)svp;
+    }
+    __syncthreads();
+    const int svp = (int)bc[0];
+    for (int idx = tid; idx < n * svp; idx += EIG_THREADS) {
+        const int f = idx / svp, k = idx - f * svp;
+        const double sig = sqrt(fmax(a.lam[k], 0.0));
+        const double z = a.Z[(size_t)k * n + f];
+        a.Vr[(size_t)f * a.vstride + k] = (float)z;
+        a.VC[(size_t)f * a.vstride + k] = (float)(z * (1.0 - thresh / sig));
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+static size_t eig_phase_doubles(int n) {
+    return (size_t)3 * n + 4 * EIG_THREADS + EIG_THREADS / 2 + (size_t)EIG_BT * n + 16;
+}
+
+EigPlan make_eig_plan(int n, int npad) {
+    EigPlan p;
+    p.n = n; p.npad = npad;
+    int C = 1;
+    while (C < 16 && (n + C - 1) / C > 40) C *= 2;
+    const size_t cap = 200 * 1024;
+    auto bytes_for = [&](int Cc, bool in_smem) {
+        size_t rows = (size_t)(n + Cc - 1) / Cc;
+        size_t mat = in_smem ? rows * n : 0;
+        size_t ph = eig_phase_doubles(n);
+        return (2 * (size_t)n + 64 + (mat > ph ? mat : ph)) * sizeof(double);
+    };
+    p.in_smem = 1;
+    while (bytes_for(C, true) > cap && C < 16) C *= 2;
+    if (bytes_for(C, true) > cap) p.in_smem = 0;
+    p.C = C;
+    p.rows_per = (n + C - 1) / C;
+    p.smem_bytes = bytes_for(C, p.in_smem != 0);
+    p.kcap = n;
+    // workspace: Aglob + Vh + tau + dd + ee + pbuf + dotbuf + iw
+    p.work_doubles = (size_t)C * p.rows_per * n + (size_t)n * n + 3 * (size_t)n + 2 * (size_t)n + 32 + (size_t)6 * n * p.kcap;
+    return p;
+}
+
+int launch_eig(const EigPlan& p, const double* G, const double* comm_max, EigBuffers b, DevState* st, int mode,
+               int k_override, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        BSUB_CUDA_CHECK(cudaFuncSetAttribute(eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        BSUB_CUDA_CHECK(cudaFuncSetAttribute(eig_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        attr_set = true;
+    }
+    if (p.smem_bytes > 200 * 1024) { set_error("eig: n=%d needs %zu B of shared memory", p.n, p.smem_bytes); return -1; }
+    EigArgs a;
+    a.G = G; a.comm_max = comm_max; a.n = p.n; a.npad = p.npad; a.C = p.C; a.rows_per = p.rows_per;
+    a.in_smem = p.in_smem; a.kcap = p.kcap; a.mode = mode; a.k_override = k_override;
+    double* w = b.work;
+    a.Aglob = w; w += (size_t)p.C * p.rows_per * p.n;
+    a.Vh = w;    w += (size_t)p.n * p.n;
+    a.tau = w;   w += p.n;
+    a.dd = w;    w += p.n;
+    a.ee = w;    w += p.n;
+    a.pbuf = w;  w += 2 * (size_t)p.n;
+    a.dotbuf = w; w += 32;
+    a.iw = w;
+    a.lam = b.lam; a.Z = b.Z; a.Vr = b.Vr; a.VC = b.VC; a.vstride = b.vstride; a.st = st;
+
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.C); cfg.blockDim = dim3(EIG_THREADS); cfg.dynamicSmemBytes = p.smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = p.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    BSUB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, eig_kernel, a));
+    return 0;
+}
+
+}  // namespace bsub

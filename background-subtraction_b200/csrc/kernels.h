@@ -1,0 +1,112 @@
+// kernels.h -- host-side launch interfaces of the CUDA kernels (internal; the public boundary is
+// include/bsub_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include "common.cuh"
+
+namespace bsub {
+
+// ---------------------------------------------------------------- gram.cu
+struct GramPlan {
+    int n, npad, nb, ntasks, ntype, gridK;
+    long long nchunks;
+    size_t smem_bytes, partial_elems;
+};
+GramPlan make_gram_plan(int n, long long ld, int num_sms);
+void fill_gram_tasks(const GramPlan& p, int2* host_tasks);
+int launch_gram(const GramPlan& p, const float* D, const float* S, const float* Y, long long ld,
+                const int2* dev_tasks, const DevState* st, float inv_mu_override, double* partial, double* G,
+                cudaStream_t stream);
+
+// ---------------------------------------------------------------- eig.cu
+struct EigPlan {
+    int n, npad, C, rows_per, in_smem, kcap;
+    size_t smem_bytes;
+    size_t work_doubles;       // total doubles of the device workspace
+};
+struct EigBuffers {
+    double* work;              // workspace of EigPlan::work_doubles doubles
+    double* lam;               // [n] eigenvalues, descending (top K valid)
+    double* Z;                 // [n][n] eigenvectors, row k = vector k (top K valid)
+    float* Vr;                 // [n][vstride] right singular vectors (fp32), columns 0..svp-1
+    float* VC;                 // [n][vstride] Vr scaled by (1 - 1/(mu sigma_k))
+    int vstride;
+};
+EigPlan make_eig_plan(int n, int npad);
+// mode 0: init (K = 1; fills norm_two, normD2, dual_norm, mu, ...);  mode 1: ALM iteration control
+// mode 2: stand-alone top-K (K = k_override), no state update except lam/Z
+int launch_eig(const EigPlan& p, const double* G, const double* comm_max, EigBuffers b, DevState* st, int mode,
+               int k_override, cudaStream_t stream);
+
+// ---------------------------------------------------------------- shrink.cu
+struct ShrinkPlan {
+    int n, rows, cols, R, P, Cf, nf, threads, grid_clusters, kr;
+    long long ld, m;
+    int ntile_r, ntile_c;
+    long long ntiles;
+    size_t smem_bytes;
+    size_t tpart_floats;       // cross-CTA T partial scratch
+    int nparts;                // number of CTAs (length of the per-CTA partial arrays)
+};
+enum ShrinkMode { SHRINK_FLAT3 = 0, SHRINK_SPILL = 1, SHRINK_L1 = 2 };
+ShrinkPlan make_shrink_plan(int n, int rows, int cols, long long ld, int num_sms, int R_hint, int Cf_hint);
+struct ShrinkBuffers {
+    const float* D; float* S; float* Y;
+    float* T;                  // [tcap][ld] projected coefficients T = Vr^T W
+    float* U;                  // SPILL mode: G_S = D - L + Y/mu  ([n][ld])
+    float* tpart;              // scratch
+    const float* Vr; const float* VC; int vstride;
+    double* part_zz;           // [nparts]
+    unsigned long long* part_nnz;
+    float* part_max;
+    float* part_wmax;          // [nparts][?] reserved
+};
+int launch_shrink(const ShrinkPlan& p, ShrinkBuffers b, const DevState* st, int mode, cudaStream_t stream);
+
+// ---------------------------------------------------------------- elementwise.cu
+int launch_rowsum_max(const float* D, long long ld, long long m, int n, double* comm_max, cudaStream_t s);
+int launch_init_Y(const float* D, float* Y, float* S, long long ld, int n, const DevState* st, cudaStream_t s);
+int launch_control_post(DevState* st, const double* part_zz, const unsigned long long* part_nnz,
+                        const float* part_max, int nparts, double* comm_sum_tail, IterLog* log, HostMirror* mirror,
+                        int phase, cudaStream_t s);
+int launch_convert_f64(const double* src, long long src_ld, float* dst, long long ld, long long m, int n,
+                       cudaStream_t s);
+int launch_export_f64(const float* src, long long ld, double* dst, long long dst_ld, long long m, int n,
+                      cudaStream_t s);
+int launch_copy_f32(const float* src, long long src_ld, float* dst, long long ld, long long m, int n, cudaStream_t s);
+int launch_u8_stats(const unsigned char* src, long long count, unsigned long long* sum_minmax, cudaStream_t s);
+int launch_u8_to_D(const unsigned char* src, float* D, long long ld, long long m, int n, double lo, double scale,
+                   double mean, cudaStream_t s);
+// L = VC * T  (materialise the low-rank part), optionally masked statistics for foreground_mask
+int launch_materialize_L(const float* T, const float* VC, int vstride, const DevState* st, float* L, long long ld,
+                         long long m, int n, cudaStream_t s);
+// second half of the two-phase shrink (SPILL mode): given S_new, recompute L from T and update Y
+int launch_dual_update(const float* D, const float* Snew, float* S, float* Y, const float* T, const float* VC, int vstride,
+                       const DevState* st, float* Lscratch, long long ld, int n, double* part_zz,
+                       unsigned long long* part_nnz, float* part_max, int nparts, cudaStream_t s);
+
+// ---------------------------------------------------------------- mask.cu
+int launch_absmax(const float* S, long long ld, long long m, int n, double* out_max, cudaStream_t s);
+int launch_mask_stats(const float* D, const float* L, const float* S, long long ld, long long m, int n,
+                      const double* absmax, double* stats /*[3]: count, sum, sumsq*/, cudaStream_t s);
+int launch_mask_write(const float* S, long long ld, long long m, int n, const double* stats, double sigmas,
+                      unsigned char* mask, long long mask_ld, cudaStream_t s);
+
+// ---------------------------------------------------------------- prox.cu (operator-level + generic modes)
+int launch_prox_flat3(const float* U, float* V, long long ld, int rows, int cols, int n, float lam, cudaStream_t s);
+// st != nullptr: lambda1 = st->lambda / st->mu read on the device, and the kernel is skipped once st->done
+int launch_prox_groups_csr(const float* U, float* V, long long ld, long long m, int n, const int* gptr,
+                           const int* gidx, int ngroups, float lam, const DevState* st, cudaStream_t s);
+int launch_block_l2_sums(const float* U, const unsigned char* labels, long long ld, long long m, int n, int nlab,
+                         double* sums, const DevState* st, cudaStream_t s);
+int launch_block_l2_apply(const float* U, float* V, const unsigned char* labels, long long ld, long long m, int n,
+                          int nlab, const double* sums, const double* lam_table, const DevState* st,
+                          double mu_override, double non_block_lambda, cudaStream_t s);
+int launch_prox_l1(const float* U, float* V, long long ld, long long m, int n, float lam, cudaStream_t s);
+struct GraphProxPlan { int rows, cols, n; long long ld; size_t xi_floats; int max_sweeps; float tol; };
+int launch_prox_graph3(const float* U, float* V, float* xi, float* tot, const float* eta, long long ld, int rows,
+                       int cols, int n, float lam, int max_sweeps, float tol, int* sweeps_out, const DevState* st,
+                       cudaStream_t s);
+
+}  // namespace bsub

@@ -1,0 +1,340 @@
+// prox.cu -- stand-alone proximal operators (the reference's operator seams) and the prox stage of the two-phase
+// shrink used by the modes that cannot be fused into shrink.cu:
+//   prox_flat3        spams.proximalFlat 'group-lasso-linf' on the regular 3x3 tiling   (/root/reference/inexact_alm_lsd.py:71-79)
+//   prox_groups_csr   the same regulariser for an ARBITRARY int32 groups vector (any partition of the pixels)
+//   block_l2_*        block_shrinkage_operator                                           (/root/reference/group_sparse_RPCA.py:13-42)
+//   prox_l1           elementwise soft threshold                                         (/root/reference/lsd_improvement.py:176)
+//   prox_graph3       spams.proximalGraph 'graph' on the overlapping 3x3 windows         (/root/reference/inexact_alm_lsd.py:49-57)
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace bsub {
+
+constexpr int PX_THREADS = 256;
+
+__device__ __forceinline__ void px_cswap_desc(float& a, float& b) {
+    float hi = fmaxf(a, b), lo = fminf(a, b);
+    a = hi; b = lo;
+}
+
+// clip level theta of the l1-ball projection of k <= 9 non-negative values (sum a > z)
+__device__ __forceinline__ float px_clip_level9(const float* a_in, float z) {
+    float u[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) u[i] = a_in[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8 - i; ++j) px_cswap_desc(u[j], u[j + 1]);
+    const float inv[9] = {1.f, 0.5f, 1.f / 3.f, 0.25f, 0.2f, 1.f / 6.f, 1.f / 7.f, 0.125f, 1.f / 9.f};
+    float cs = 0.f, theta = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        cs += u[k];
+        float t = (cs - z) * inv[k];
+        if (u[k] > t) theta = t;
+    }
+    return theta;
+}
+
+// ---------------------------------------------------------------------------------------- flat 3x3 tiles
+__global__ void prox_flat3_kernel(const float* __restrict__ U, float* __restrict__ V, long long ld, int rows, int cols, int n,
+                                  float lam) {
+    const int gr = (rows + 2) / 3, gc = (cols + 2) / 3;
+    const long long ng = (long long)gr * gc;
+    for (int f = blockIdx.y; f < n; f += gridDim.y) {
+        const float* u = U + (size_t)f * ld;
+        float* v = V + (size_t)f * ld;
+        for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += (long long)gridDim.x * blockDim.x) {
+            const int tj = (int)(g / gr), ti = (int)(g - (long long)tj * gr);
+            float x[9], ax[9];
+            float sabs = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int dr = 0; dr < 3; ++dr) {
+                    const int i = 3 * ti + dr, j = 3 * tj + c;
+                    const bool ok = (i < rows) && (j < cols);
+                    const float val = ok ? u[(long long)j * rows + i] : 0.f;
+                    x[c * 3 + dr] = val; ax[c * 3 + dr] = fabsf(val); sabs += fabsf(val);
+                }
+            const bool nz = sabs > lam;
+            const float theta = nz ? px_clip_level9(ax, lam) : 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int dr = 0; dr < 3; ++dr) {
+                    const int i = 3 * ti + dr, j = 3 * tj + c;
+                    if (i < rows && j < cols) v[(long long)j * rows + i] = nz ? copysignf(fminf(ax[c * 3 + dr], theta), x[c * 3 + dr]) : 0.f;
+                }
+        }
+    }
+}
+
+int launch_prox_flat3(const float* U, float* V, long long ld, int rows, int cols, int n, float lam, cudaStream_t s) {
+    const long long ng = (long long)((rows + 2) / 3) * ((cols + 2) / 3);
+    long long gx = (ng + PX_THREADS - 1) / PX_THREADS;
+    if (gx > 2048) gx = 2048;
+    if (gx < 1) gx = 1;
+    dim3 g((unsigned)gx, n < 256 ? n : 256);
+    prox_flat3_kernel<<<g, PX_THREADS, 0, s>>>(U, V, ld, rows, cols, n, lam);
+    BSUB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------- arbitrary flat groups
+// gptr/gidx: CSR of group -> pixel list for ids >= 1; pixels with id 0 are copied through by the caller
+// (V is initialised with U).  One thread per (group, frame); Michelot's finite active-set iteration gives the
+// exact clip level without sorting or local arrays.
+__global__ void prox_groups_csr_kernel(const float* __restrict__ U, float* __restrict__ V, long long ld, int n,
+                                       const int* __restrict__ gptr, const int* __restrict__ gidx, int ngroups, float lam,
+                                       const DevState* st) {
+    if (st != nullptr) { if (st->done) return; lam = (float)(st->lambda / st->mu); }
+    for (int f = blockIdx.y; f < n; f += gridDim.y) {
+        const float* u = U + (size_t)f * ld;
+        float* v = V + (size_t)f * ld;
+        for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+            const int b = gptr[g], e = gptr[g + 1];
+            if (e <= b) continue;
+            float sabs = 0.f;
+            for (int q = b; q < e; ++q) sabs += fabsf(u[gidx[q]]);
+            if (sabs <= lam) { for (int q = b; q < e; ++q) v[gidx[q]] = 0.f; continue; }
+            float theta = (sabs - lam) / (float)(e - b);
+            for (int it = 0; it < e - b; ++it) {
+                float sum = 0.f; int cnt = 0;
+                for (int q = b; q < e; ++q) { const float a = fabsf(u[gidx[q]]); if (a > theta) { sum += a; ++cnt; } }
+                const float t2 = (sum - lam) / (float)cnt;
+                if (!(t2 > theta)) break;
+                theta = t2;
+            }
+            for (int q = b; q < e; ++q) { const float x = u[gidx[q]]; v[gidx[q]] = copysignf(fminf(fabsf(x), theta), x); }
+        }
+    }
+}
+
+int launch_prox_groups_csr(const float* U, float* V, long long ld, long long m, int n, const int* gptr, const int* gidx,
+                           int ngroups, float lam, const DevState* st, cudaStream_t s) {
+    (void)m;
+    if (U != V) BSUB_CUDA_CHECK(cudaMemcpyAsync(V, U, sizeof(float) * (size_t)ld * n, cudaMemcpyDeviceToDevice, s));
+    int gx = (ngroups + PX_THREADS - 1) / PX_THREADS;
+    if (gx > 2048) gx = 2048;
+    if (gx < 1) gx = 1;
+    dim3 g((unsigned)gx, n < 256 ? n : 256);
+    prox_groups_csr_kernel<<<g, PX_THREADS, 0, s>>>(U, V, ld, n, gptr, gidx, ngroups, lam, st);
+    BSUB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------- per-frame l2 blocks
+// labels[f][p] (uint8): 0 = complement group, b >= 1 = block b of that frame.  sums[f][nlab] = sum of squares.
+__global__ void block_l2_sums_kernel(const float* __restrict__ U, const unsigned char* __restrict__ labels, long long ld,
+                                     long long m, int nlab, double* __restrict__ sums, const DevState* st) {
+    __shared__ double red[32];
+    if (st != nullptr && st->done) return;
+    const int f = blockIdx.y;
+    const float* u = U + (size_t)f * ld;
+    const unsigned char* lab = labels + (size_t)f * m;
+    double s0 = 0.0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (long long)gridDim.x * blockDim.x) {
+        const float x = u[p];
+        const int l = lab[p];
+        if (l == 0) s0 += (double)x * (double)x;
+        else if (l < nlab) atomicAdd(sums + (size_t)f * nlab + l, (double)x * (double)x);
+    }
+    s0 = block_sum(s0, red);
+    if (threadIdx.x == 0) atomicAdd(sums + (size_t)f * nlab, s0);
+}
+
+int launch_block_l2_sums(const float* U, const unsigned char* labels, long long ld, long long m, int n, int nlab, double* sums,
+                         const DevState* st, cudaStream_t s) {
+    BSUB_CUDA_CHECK(cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)n * nlab, s));
+    long long gx = (m + PX_THREADS * 8 - 1) / (PX_THREADS * 8);
+    if (gx < 1) gx = 1;
+    if (gx > 256) gx = 256;
+    dim3 g((unsigned)gx, n);
+    block_l2_sums_kernel<<<g, PX_THREADS, 0, s>>>(U, labels, ld, m, nlab, sums, st);
+    BSUB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// factor = max(1 - eps/||G_g||_2, 0), zero-norm group -> 0 (group_sparse_RPCA.py:35,40 with max(-inf, 0) = 0)
+__global__ void block_l2_apply_kernel(const float* __restrict__ U, float* __restrict__ V, const unsigned char* __restrict__ labels,
+                                      long long ld, long long m, int nlab, const double* __restrict__ sums,
+                                      const double* __restrict__ lam_table, const DevState* st, double mu_override,
+                                      double non_block_lambda) {
+    extern __shared__ float fac_s[];
+    if (st != nullptr && st->done) return;
+    const int f = blockIdx.y;
+    const double mu = (st != nullptr) ? st->mu : mu_override;
+    if (st != nullptr) non_block_lambda = st->non_block_lambda;
+    for (int l = threadIdx.x; l < nlab; l += blockDim.x) {
+        const double eps = ((l == 0) ? non_block_lambda : lam_table[(size_t)f * nlab + l]) / mu;
+        const double nrm = sqrt(sums[(size_t)f * nlab + l]);
+        double t = (nrm > 0.0) ? 1.0 - eps / nrm : 0.0;
+        fac_s[l] = (float)(t > 0.0 ? t : 0.0);
+    }
+    __syncthreads();
+    const float* u = U + (size_t)f * ld;
+    float* v = V + (size_t)f * ld;
+    const unsigned char* lab = labels + (size_t)f * m;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (long long)gridDim.x * blockDim.x) {
+        const int l = lab[p];
+        v[p] = (l < nlab) ? fac_s[l] * u[p] : 0.f;
+    }
+}
+
+int launch_block_l2_apply(const float* U, float* V, const unsigned char* labels, long long ld, long long m, int n, int nlab,
+                          const double* sums, const double* lam_table, const DevState* st, double mu_override,
+                          double non_block_lambda, cudaStream_t s) {
+    long long gx = (m + PX_THREADS * 8 - 1) / (PX_THREADS * 8);
+    if (gx < 1) gx = 1;
+    if (gx > 256) gx = 256;
+    dim3 g((unsigned)gx, n);
+    block_l2_apply_kernel<<<g, PX_THREADS, sizeof(float) * nlab, s>>>(U, V, labels, ld, m, nlab, sums, lam_table, st, mu_override,
+                                                                     non_block_lambda);
+    BSUB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------- l1
+__global__ void prox_l1_kernel(const float* __restrict__ U, float* __restrict__ V, long long total, float lam) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const float x = U[i];
+        V[i] = copysignf(fmaxf(fabsf(x) - lam, 0.f), x);
+    }
+}
+int launch_prox_l1(const float* U, float* V, long long ld, long long m, int n, float lam, cudaStream_t s) {
+    (void)m;
+    const long long total = ld * n;
+    long long gx = (total + PX_THREADS * 8 - 1) / (PX_THREADS * 8);
+    if (gx < 1) gx = 1;
+    if (gx > 148 * 8) gx = 148 * 8;
+    prox_l1_kernel<<<(unsigned)gx, PX_THREADS, 0, s>>>(U, V, total, lam);
+    BSUB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------- overlapping 3x3 windows
+// Dual block-coordinate descent with the 9-colouring (i mod 3, j mod 3) of the window top-lefts: windows of one
+// colour are disjoint, so one colour step is one fully parallel pass.  Window geometry reproduces
+// get_vars_idx_top_left (/root/reference/utils.py:249-257): top-lefts i in [0, rows-3], j in [0, cols-3],
+// extent min(3, rows-1-i) x min(3, cols-1-j)  => last image row / column uncovered.
+// Per frame f: xi[f][w][9] dual variables, tot[f][p] = sum of duals on pixel p.  A persistent cooperative grid
+// sweeps until the largest dual change of a sweep is <= tol (checked every sweep through a device flag pair).
+struct GraphArgs {
+    const float* U; float* V; float* xi; float* tot; const float* eta;
+    long long ld; int rows, cols, n; float lam; int max_sweeps; float tol;
+    int* sweeps_out; unsigned int* change_bits;   // [2] ping-pong max-change (as float bits)
+    const DevState* st;
+};
+
+__global__ void __launch_bounds__(PX_THREADS) prox_graph3_kernel(GraphArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    if (a.st != nullptr) {
+        if (a.st->done) return;                                  // uniform over the grid
+        a.lam = (float)(a.st->lambda / a.st->mu);
+        a.tol = a.tol * a.lam;                                   // relative tolerance in solver mode
+    }
+    const int rows = a.rows, cols = a.cols;
+    const int nwi = rows - min(3, rows) + 1, nwj = cols - min(3, cols) + 1;     // numX, numY of the reference
+    const long long nw = (long long)nwi * nwj;
+    const long long gsz = (long long)gridDim.x * blockDim.x, gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // init
+    for (long long i = gid; i < (long long)a.n * a.ld; i += gsz) a.tot[i] = 0.f;
+    for (long long i = gid; i < (long long)a.n * nw * 9; i += gsz) a.xi[i] = 0.f;
+    if (gid == 0) { a.change_bits[0] = 0u; a.change_bits[1] = 0u; }
+    grid.sync();
+    int sw = 0;
+    for (; sw < a.max_sweeps; ++sw) {
+        float mych = 0.f;
+        for (int col = 0; col < 9; ++col) {
+            const int ci = col % 3, cj = col / 3;
+            const int ni = (nwi - ci + 2) / 3, nj = (nwj - cj + 2) / 3;       // windows of this colour per axis
+            const long long nwc = (ni > 0 && nj > 0) ? (long long)ni * nj : 0;
+            for (long long t = gid; t < nwc * a.n; t += gsz) {
+                const int f = (int)(t / nwc);
+                const long long wq = t - (long long)f * nwc;
+                const int wj = (int)(wq / ni) * 3 + cj, wi = (int)(wq % ni) * 3 + ci;
+                const int hh = min(3, rows - 1 - wi), ww = min(3, cols - 1 - wj);
+                if (hh <= 0 || ww <= 0) continue;
+                const long long widx = (long long)wj * nwi + wi;
+                const float* u = a.U + (size_t)f * a.ld;
+                float* tot = a.tot + (size_t)f * a.ld;
+                float* xi = a.xi + ((size_t)f * nw + widx) * 9;
+                const float radius = a.lam * (a.eta != nullptr ? a.eta[widx] : 1.f);
+                float r[9], ar[9], xo[9];
+                float sabs = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int dr = 0; dr < 3; ++dr) {
+                        const int e = c * 3 + dr;
+                        const bool ok = (dr < hh) && (c < ww);
+                        float val = 0.f, x0 = 0.f;
+                        if (ok) {
+                            const long long p = (long long)(wj + c) * rows + wi + dr;
+                            x0 = xi[e];
+                            val = u[p] - tot[p] + x0;
+                        }
+                        r[e] = val; ar[e] = fabsf(val); xo[e] = x0; sabs += fabsf(val);
+                    }
+                float theta = 0.f;
+                if (sabs > radius) theta = px_clip_level9(ar, radius);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int dr = 0; dr < 3; ++dr) {
+                        const int e = c * 3 + dr;
+                        if ((dr < hh) && (c < ww)) {
+                            const long long p = (long long)(wj + c) * rows + wi + dr;
+                            const float xn = copysignf(fmaxf(ar[e] - theta, 0.f), r[e]);   // projection on the l1 ball
+                            const float dlt = xn - xo[e];
+                            xi[e] = xn;
+                            tot[p] += dlt;
+                            mych = fmaxf(mych, fabsf(dlt));
+                        }
+                    }
+            }
+            grid.sync();
+        }
+        mych = warp_max(mych);
+        if ((threadIdx.x & 31) == 0 && mych > 0.f) atomicMax(a.change_bits + (sw & 1), __float_as_uint(mych));
+        grid.sync();
+        const float ch = __uint_as_float(*((volatile unsigned int*)(a.change_bits + (sw & 1))));
+        if (gid == 0) a.change_bits[(sw + 1) & 1] = 0u;
+        if (ch <= a.tol) { ++sw; break; }
+    }
+    grid.sync();
+    for (long long i = gid; i < (long long)a.n * a.ld; i += gsz) a.V[i] = a.U[i] - a.tot[i];
+    if (gid == 0 && a.sweeps_out != nullptr) *a.sweeps_out = sw;
+}
+
+int launch_prox_graph3(const float* U, float* V, float* xi, float* tot, const float* eta, long long ld, int rows, int cols, int n,
+                       float lam, int max_sweeps, float tol, int* sweeps_out, const DevState* st, cudaStream_t s) {
+    static int blocks_per_sm = 0, num_sms = 0;
+    static unsigned int* change_bits = nullptr;
+    if (blocks_per_sm == 0) {
+        int dev = 0;
+        BSUB_CUDA_CHECK(cudaGetDevice(&dev));
+        BSUB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        BSUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, prox_graph3_kernel, PX_THREADS, 0));
+        if (blocks_per_sm < 1) { set_error("prox_graph3: kernel does not fit"); return -1; }
+        BSUB_CUDA_CHECK(cudaMalloc(&change_bits, 2 * sizeof(unsigned int)));
+    }
+    GraphArgs a;
+    a.U = U; a.V = V; a.xi = xi; a.tot = tot; a.eta = eta; a.ld = ld; a.rows = rows; a.cols = cols; a.n = n; a.lam = lam;
+    a.max_sweeps = max_sweeps; a.tol = tol; a.sweeps_out = sweeps_out; a.change_bits = change_bits; a.st = st;
+    const long long nw9 = ((long long)rows * cols / 9 + 1) * n;
+    long long want = (nw9 + PX_THREADS - 1) / PX_THREADS;
+    long long maxb = (long long)blocks_per_sm * num_sms;
+    if (want > maxb) want = maxb;
+    if (want < 1) want = 1;
+    void* args[] = {&a};
+    BSUB_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)prox_graph3_kernel, dim3((unsigned)want), dim3(PX_THREADS), args, 0, s));
+    return 0;
+}
+
+}  // namespace bsub

@@ -1,0 +1,730 @@
+// solver.cu -- host orchestration and the extern "C" boundary (include/bsub_b200.h).
+//
+// One bsub_solver owns the device-resident state of one decomposition (D, S, Y, T, eigen workspace, control
+// state) on one GPU and one stream.  bsub_run() is the whole single-GPU solve; the bsub_step_* functions expose
+// the same sequence in pieces so that a pixel-sharded multi-GPU driver can all-reduce the frames x frames Gram
+// and a few scalars between them.  The ALM loop never waits on the host: every kernel
+// reads its scalars (mu, rank, stop flag) from DevState and returns immediately once the stop flag is set; the
+// host only limits how far ahead it enqueues by watching a mapped status word.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+#include "../../include/bsub_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bsub {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace bsub
+
+using namespace bsub;
+
+#define CK(expr) BSUB_CUDA_CHECK(expr)
+#define RET_IF(expr) do { int _rc = (expr); if (_rc != 0) return _rc; } while (0)
+
+static const int kCommTail = 16;     // doubles after the Gram in the sum buffer
+static const int kRunAhead = 3;      // iterations the host may enqueue ahead of the device
+
+struct bsub_solver {
+    bsub_config cfg;
+    int device = 0, num_sms = 148;
+    long long m = 0, ld = 0;
+    int n = 0, npad = 0;
+    float *D = nullptr, *S = nullptr, *Y = nullptr, *T = nullptr, *L = nullptr, *U = nullptr;
+    DevState* st = nullptr;
+    IterLog* log = nullptr;
+    HostMirror* mirror = nullptr;       // mapped pinned host memory
+    HostMirror* mirror_dev = nullptr;
+    double* comm_sum = nullptr;         // [npad*npad + kCommTail]
+    double* comm_max = nullptr;         // [8]
+    GramPlan gp; int2* tasks_dev = nullptr; double* gram_partial = nullptr;
+    EigPlan ep; EigBuffers eb;
+    ShrinkPlan sp; float* tpart = nullptr; double* part_zz = nullptr; unsigned long long* part_nnz = nullptr;
+    float* part_max = nullptr;
+    int shrink_mode = SHRINK_FLAT3;
+    // generic flat groups
+    int* gptr = nullptr; int* gidx = nullptr; int ngroups = 0; bool groups_set = false;
+    // overlapping graph
+    float* eta_dev = nullptr; float* xi = nullptr; float* tot = nullptr; int* sweeps_dev = nullptr; bool graph_set = false;
+    // l2 blocks
+    unsigned char* labels_dev = nullptr; double* lam_table = nullptr; double* bsums = nullptr; int nlab = 0; bool blocks_set = false;
+    bool loaded = false, finalized = false, initialised = false;
+    cudaEvent_t ev[kRunAhead + 1];
+    int iters_enqueued = 0;
+};
+
+static cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static int round_half_even_005(int d) {
+    // Python round(0.05 * d) -- banker's rounding on the double product
+    return (int)nearbyint(0.05 * (double)d);
+}
+
+extern "C" {
+
+const char* bsub_last_error(void) { return g_err; }
+int bsub_version(void) { return 100; }
+
+void bsub_default_config(bsub_config* c) {
+    memset(c, 0, sizeof(*c));
+    c->prox = BSUB_PROX_FLAT_LINF; c->group_rows = 3; c->group_cols = 3; c->delta = 10.0; c->mu_scale = 12.5; c->rho = 1.6;
+    c->tol = 1e-7; c->max_iter = 500; c->sv0 = 10; c->use_sv_prediction = 1; c->break_on_rank0 = 0;
+    c->non_block_lambda_scale = 100.0; c->graph_max_sweeps = 4000; c->graph_tol = 1e-6;
+}
+
+int bsub_destroy(bsub_solver* s) {
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {s->D, s->S, s->Y, s->T, s->L, s->U, s->st, s->log, s->comm_sum, s->comm_max, s->tasks_dev, s->gram_partial,
+                    s->eb.work, s->eb.lam, s->eb.Z, s->eb.Vr, s->eb.VC, s->tpart, s->part_zz, s->part_nnz, s->part_max, s->gptr,
+                    s->gidx, s->eta_dev, s->xi, s->tot, s->sweeps_dev, s->labels_dev, s->lam_table, s->bsums};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (s->mirror) cudaFreeHost((void*)s->mirror);
+    for (int i = 0; i <= kRunAhead; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    delete s;
+    return 0;
+}
+
+int bsub_create(const bsub_config* cfg, bsub_solver** out) {
+    if (!cfg || !out) { set_error("bsub_create: null argument"); return -1; }
+    if (cfg->m <= 0 || cfg->n <= 0) { set_error("bsub_create: empty matrix (m=%lld, n=%d)", (long long)cfg->m, cfg->n); return -1; }
+    if (cfg->prox < 0 || cfg->prox > 3) { set_error("bsub_create: unknown prox %d", cfg->prox); return -1; }
+    if ((cfg->prox == BSUB_PROX_FLAT_LINF || cfg->prox == BSUB_PROX_GRAPH_LINF) &&
+        ((long long)cfg->rows * cfg->cols != cfg->m)) {
+        set_error("bsub_create: rows*cols (%d*%d) != m (%lld)", cfg->rows, cfg->cols, (long long)cfg->m); return -1;
+    }
+    if (cfg->prox == BSUB_PROX_GRAPH_LINF && (cfg->group_rows != 3 || cfg->group_cols != 3)) {
+        set_error("bsub_create: overlapping windows are implemented for the reference's 3x3 BLOCK_SIZE only"); return -1;
+    }
+    bsub_solver* s = new bsub_solver();
+    for (int i = 0; i <= kRunAhead; ++i) s->ev[i] = nullptr;
+    memset(&s->eb, 0, sizeof(s->eb));
+    s->cfg = *cfg;
+    if (s->cfg.m_global <= 0) s->cfg.m_global = cfg->m;
+    if (s->cfg.max_iter <= 0) s->cfg.max_iter = 500;
+    if (s->cfg.max_iter > kMaxIterLog) s->cfg.max_iter = kMaxIterLog;
+    if (s->cfg.graph_max_sweeps <= 0) s->cfg.graph_max_sweeps = 4000;
+    if (s->cfg.graph_tol <= 0) s->cfg.graph_tol = 1e-6;
+    if (s->cfg.non_block_lambda_scale <= 0) s->cfg.non_block_lambda_scale = 100.0;
+    s->m = cfg->m; s->n = cfg->n;
+    s->ld = ((cfg->m + 31) / 32) * 32;
+    s->npad = ((cfg->n + 31) / 32) * 32;
+    int rc = 0;
+    do {
+        if (cudaGetDevice(&s->device) != cudaSuccess) { set_error("bsub_create: no CUDA device (the CUDA path is mandatory; there is no CPU fallback)"); rc = -1; break; }
+        cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, s->device);
+        const size_t mat = sizeof(float) * (size_t)s->ld * s->n;
+#define ALLOC(ptr, bytes) if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) { set_error("bsub_create: cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(cudaGetLastError())); rc = -1; break; }
+        ALLOC(s->D, mat); ALLOC(s->S, mat); ALLOC(s->Y, mat);
+        ALLOC(s->T, mat);                                    // T has up to n rows (rank <= n)
+        cudaMemset(s->T, 0, mat);                            // pad columns must read as zero
+        ALLOC(s->st, sizeof(DevState)); ALLOC(s->log, sizeof(IterLog) * kMaxIterLog);
+        ALLOC(s->comm_sum, sizeof(double) * ((size_t)s->npad * s->npad + kCommTail));
+        ALLOC(s->comm_max, sizeof(double) * 8);
+        cudaMemset(s->comm_sum, 0, sizeof(double) * ((size_t)s->npad * s->npad + kCommTail));
+        cudaMemset(s->comm_max, 0, sizeof(double) * 8);
+        cudaMemset(s->log, 0, sizeof(IterLog) * kMaxIterLog);
+        if (cudaHostAlloc((void**)&s->mirror, sizeof(HostMirror), cudaHostAllocMapped) != cudaSuccess) { set_error("bsub_create: cudaHostAlloc failed"); rc = -1; break; }
+        memset((void*)s->mirror, 0, sizeof(HostMirror));
+        if (cudaHostGetDevicePointer((void**)&s->mirror_dev, (void*)s->mirror, 0) != cudaSuccess) { set_error("bsub_create: cudaHostGetDevicePointer failed"); rc = -1; break; }
+        // Gram
+        s->gp = make_gram_plan(s->n, s->ld, s->num_sms);
+        std::vector<int2> tasks(s->gp.ntasks);
+        fill_gram_tasks(s->gp, tasks.data());
+        ALLOC(s->tasks_dev, sizeof(int2) * s->gp.ntasks);
+        cudaMemcpy(s->tasks_dev, tasks.data(), sizeof(int2) * s->gp.ntasks, cudaMemcpyHostToDevice);
+        ALLOC(s->gram_partial, sizeof(double) * s->gp.partial_elems);
+        // eigen solver
+        s->ep = make_eig_plan(s->n, s->npad);
+        ALLOC(s->eb.work, sizeof(double) * s->ep.work_doubles);
+        ALLOC(s->eb.lam, sizeof(double) * s->n);
+        ALLOC(s->eb.Z, sizeof(double) * (size_t)s->n * s->n);
+        s->eb.vstride = ((s->n + 3) / 4) * 4;
+        ALLOC(s->eb.Vr, sizeof(float) * (size_t)s->n * s->eb.vstride);
+        ALLOC(s->eb.VC, sizeof(float) * (size_t)s->n * s->eb.vstride);
+        cudaMemset(s->eb.Vr, 0, sizeof(float) * (size_t)s->n * s->eb.vstride);
+        cudaMemset(s->eb.VC, 0, sizeof(float) * (size_t)s->n * s->eb.vstride);
+        // shrink
+        int rows = cfg->rows, cols = cfg->cols;
+        if ((long long)rows * cols != s->m) {
+            // no image geometry (block-l2 / l1 modes do not depend on it): pick any factorisation m = rows*cols that
+            // tiles well (rows a multiple of 4, as large as fits a few tiles), else one long column.
+            rows = (int)s->m; cols = 1;
+            for (int r = 4096; r >= 48; r -= 4)
+                if (s->m % r == 0) { rows = r; cols = (int)(s->m / r); break; }
+        }
+        s->sp = make_shrink_plan(s->n, rows, cols, s->ld, s->num_sms, cfg->tile_rows, cfg->cluster_frames);
+        ALLOC(s->tpart, sizeof(float) * s->sp.tpart_floats);
+        int nparts = std::max(s->sp.nparts, s->num_sms * 8);
+        ALLOC(s->part_zz, sizeof(double) * nparts); ALLOC(s->part_nnz, sizeof(unsigned long long) * nparts);
+        ALLOC(s->part_max, sizeof(float) * nparts);
+        cudaMemset(s->part_zz, 0, sizeof(double) * nparts); cudaMemset(s->part_nnz, 0, sizeof(unsigned long long) * nparts);
+        cudaMemset(s->part_max, 0, sizeof(float) * nparts);
+        for (int i = 0; i <= kRunAhead; ++i)
+            if (cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming) != cudaSuccess) { set_error("bsub_create: event"); rc = -1; break; }
+        if (rc) break;
+        switch (cfg->prox) {
+            case BSUB_PROX_FLAT_LINF: s->shrink_mode = (cfg->group_rows == 3 && cfg->group_cols == 3) ? SHRINK_FLAT3 : SHRINK_SPILL; break;
+            case BSUB_PROX_L1: s->shrink_mode = SHRINK_L1; break;
+            default: s->shrink_mode = SHRINK_SPILL; break;
+        }
+        if (s->shrink_mode == SHRINK_SPILL) { ALLOC(s->U, mat); ALLOC(s->L, mat); cudaMemset(s->U, 0, mat); cudaMemset(s->L, 0, mat); }
+#undef ALLOC
+        if (cudaGetLastError() != cudaSuccess) { /* clear sticky-less errors from memset probing */ }
+    } while (0);
+    if (rc != 0) { bsub_destroy(s); return rc; }
+    *out = s;
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------------- groups
+int bsub_set_flat_groups(bsub_solver* s, const int32_t* g) {
+    if (!s || !g) { set_error("bsub_set_flat_groups: null argument"); return -1; }
+    if (s->cfg.prox != BSUB_PROX_FLAT_LINF) { set_error("bsub_set_flat_groups: solver was not created with BSUB_PROX_FLAT_LINF"); return -1; }
+    const long long m = s->m;
+    const int rows = s->cfg.rows, cols = s->cfg.cols;
+    // is it the regular 3x3 tiling of get_proximal_flat_groups_nonoverlap (lsd_improvement.py:24-34)?
+    bool regular = ((long long)rows * cols == m);
+    if (regular) {
+        const int ntr = (rows + 2) / 3;
+        for (int j = 0; j < cols && regular; ++j)
+            for (int i = 0; i < rows; ++i)
+                if (g[(long long)j * rows + i] != (j / 3) * ntr + (i / 3) + 1) { regular = false; break; }
+    }
+    s->groups_set = true;
+    if (regular) { s->shrink_mode = SHRINK_FLAT3; return 0; }
+    // generic partition: CSR of the ids >= 1
+    int gmax = 0;
+    for (long long p = 0; p < m; ++p) { if (g[p] < 0) { set_error("bsub_set_flat_groups: negative group id"); return -1; } gmax = std::max(gmax, (int)g[p]); }
+    std::vector<int> ptr((size_t)gmax + 1, 0), idx;
+    for (long long p = 0; p < m; ++p) if (g[p] > 0) ptr[g[p]]++;       // ptr[k] = size of group k (k >= 1)
+    std::vector<int> start((size_t)gmax + 1, 0);
+    int acc = 0;
+    for (int k = 1; k <= gmax; ++k) { start[k - 1] = acc; acc += ptr[k]; }
+    start[gmax] = acc;
+    idx.resize((size_t)std::max(acc, 1));
+    std::vector<int> fill(start.begin(), start.end());
+    for (long long p = 0; p < m; ++p) if (g[p] > 0) idx[fill[g[p] - 1]++] = (int)p;
+    if (s->gptr) cudaFree(s->gptr);
+    if (s->gidx) cudaFree(s->gidx);
+    CK(cudaMalloc((void**)&s->gptr, sizeof(int) * ((size_t)gmax + 1)));
+    CK(cudaMalloc((void**)&s->gidx, sizeof(int) * idx.size()));
+    CK(cudaMemcpy(s->gptr, start.data(), sizeof(int) * ((size_t)gmax + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->gidx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
+    s->ngroups = gmax;
+    s->shrink_mode = SHRINK_SPILL;
+    const size_t mat = sizeof(float) * (size_t)s->ld * s->n;
+    if (!s->U) { CK(cudaMalloc((void**)&s->U, mat)); CK(cudaMemset(s->U, 0, mat)); }
+    if (!s->L) { CK(cudaMalloc((void**)&s->L, mat)); CK(cudaMemset(s->L, 0, mat)); }
+    return 0;
+}
+
+int bsub_set_graph_windows(bsub_solver* s, const double* eta, int64_t n_eta) {
+    if (!s) { set_error("bsub_set_graph_windows: null solver"); return -1; }
+    if (s->cfg.prox != BSUB_PROX_GRAPH_LINF) { set_error("bsub_set_graph_windows: solver was not created with BSUB_PROX_GRAPH_LINF"); return -1; }
+    const int rows = s->cfg.rows, cols = s->cfg.cols;
+    const long long nwi = rows - std::min(3, rows) + 1, nwj = cols - std::min(3, cols) + 1, nw = nwi * nwj;
+    if (eta != nullptr) {
+        if (n_eta != nw) { set_error("bsub_set_graph_windows: eta has %lld entries, the %dx%d image has %lld windows", (long long)n_eta, rows, cols, nw); return -1; }
+        std::vector<float> ef((size_t)nw);
+        for (long long i = 0; i < nw; ++i) ef[i] = (float)eta[i];
+        if (!s->eta_dev) CK(cudaMalloc((void**)&s->eta_dev, sizeof(float) * nw));
+        CK(cudaMemcpy(s->eta_dev, ef.data(), sizeof(float) * nw, cudaMemcpyHostToDevice));
+    }
+    if (!s->xi) CK(cudaMalloc((void**)&s->xi, sizeof(float) * (size_t)s->n * nw * 9));
+    if (!s->tot) CK(cudaMalloc((void**)&s->tot, sizeof(float) * (size_t)s->n * s->ld));
+    if (!s->sweeps_dev) CK(cudaMalloc((void**)&s->sweeps_dev, sizeof(int)));
+    s->graph_set = true;
+    return 0;
+}
+
+int bsub_set_blocks(bsub_solver* s, const uint8_t* labels, const int32_t* lam_ptr, const double* lam) {
+    if (!s || !labels || !lam_ptr) { set_error("bsub_set_blocks: null argument"); return -1; }
+    if (s->cfg.prox != BSUB_PROX_BLOCK_L2) { set_error("bsub_set_blocks: solver was not created with BSUB_PROX_BLOCK_L2"); return -1; }
+    int maxb = 0;
+    for (int f = 0; f < s->n; ++f) maxb = std::max(maxb, lam_ptr[f + 1] - lam_ptr[f]);
+    if (maxb > 254) { set_error("bsub_set_blocks: more than 254 blocks in one frame"); return -1; }
+    s->nlab = maxb + 1;
+    std::vector<double> table((size_t)s->n * s->nlab, 0.0);
+    for (int f = 0; f < s->n; ++f)
+        for (int b = 0; b < lam_ptr[f + 1] - lam_ptr[f]; ++b) table[(size_t)f * s->nlab + b + 1] = lam[lam_ptr[f] + b];
+    if (s->labels_dev) cudaFree(s->labels_dev);
+    if (s->lam_table) cudaFree(s->lam_table);
+    if (s->bsums) cudaFree(s->bsums);
+    CK(cudaMalloc((void**)&s->labels_dev, (size_t)s->n * s->m));
+    CK(cudaMalloc((void**)&s->lam_table, sizeof(double) * table.size()));
+    CK(cudaMalloc((void**)&s->bsums, sizeof(double) * table.size()));
+    CK(cudaMemcpy(s->labels_dev, labels, (size_t)s->n * s->m, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->lam_table, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice));
+    s->blocks_set = true;
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------------- data in
+static int after_load(bsub_solver* s) { s->loaded = true; s->finalized = false; s->initialised = false; return 0; }
+
+int bsub_load_D_f32_dev(bsub_solver* s, const float* D, int64_t ld, void* stream) {
+    if (!s || !D || ld < s->m) { set_error("bsub_load_D_f32_dev: bad argument"); return -1; }
+    RET_IF(launch_copy_f32(D, ld, s->D, s->ld, s->m, s->n, as_stream(stream)));
+    return after_load(s);
+}
+
+int bsub_load_D_f32_host(bsub_solver* s, const float* D, int64_t ld, void* stream) {
+    if (!s || !D || ld < s->m) { set_error("bsub_load_D_f32_host: bad argument"); return -1; }
+    cudaStream_t st = as_stream(stream);
+    if (s->ld != s->m) CK(cudaMemsetAsync(s->D, 0, sizeof(float) * (size_t)s->ld * s->n, st));
+    CK(cudaMemcpy2DAsync(s->D, sizeof(float) * s->ld, D, sizeof(float) * ld, sizeof(float) * s->m, s->n, cudaMemcpyHostToDevice, st));
+    return after_load(s);
+}
+
+int bsub_load_D_f64_host(bsub_solver* s, const double* D, int64_t ld, void* stream) {
+    if (!s || !D || ld < s->m) { set_error("bsub_load_D_f64_host: bad argument"); return -1; }
+    cudaStream_t st = as_stream(stream);
+    // stage through the (not yet used) T buffer: it holds ld*n floats = ld*n/2 doubles -> two halves of the frames
+    double* stage = reinterpret_cast<double*>(s->T);
+    const long long cap_frames = std::max<long long>(1, ((long long)s->ld * s->n / 2) / s->m);
+    for (long long f0 = 0; f0 < s->n; f0 += cap_frames) {
+        const int nf = (int)std::min<long long>(cap_frames, s->n - f0);
+        CK(cudaMemcpy2DAsync(stage, sizeof(double) * s->m, D + (size_t)f0 * ld, sizeof(double) * ld, sizeof(double) * s->m, nf,
+                             cudaMemcpyHostToDevice, st));
+        RET_IF(launch_convert_f64(stage, s->m, s->D + (size_t)f0 * s->ld, s->ld, s->m, nf, st));
+    }
+    CK(cudaMemsetAsync(s->T, 0, sizeof(float) * (size_t)s->ld * s->n, st));     // T was the staging buffer
+    return after_load(s);
+}
+
+int bsub_load_u8_host(bsub_solver* s, const uint8_t* frames, double* lo, double* hi, double* mean_raw, int force, void* stream) {
+    if (!s || !frames) { set_error("bsub_load_u8_host: bad argument"); return -1; }
+    cudaStream_t st = as_stream(stream);
+    unsigned char* stage = reinterpret_cast<unsigned char*>(s->T);
+    const long long count = (long long)s->m * s->n;
+    CK(cudaMemcpyAsync(stage, frames, (size_t)count, cudaMemcpyHostToDevice, st));
+    double vlo, vhi, vmean;
+    if (force && lo && hi && mean_raw) { vlo = *lo; vhi = *hi; vmean = *mean_raw; }
+    else {
+        unsigned long long* acc = reinterpret_cast<unsigned long long*>(s->comm_max);   // scratch: 3 x u64
+        unsigned long long init[3] = {0ull, 255ull, 0ull}, res[3];
+        CK(cudaMemcpyAsync(acc, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        RET_IF(launch_u8_stats(stage, count, acc, st));
+        CK(cudaMemcpyAsync(res, acc, sizeof(res), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemsetAsync(s->comm_max, 0, sizeof(double) * 8, st));
+        vlo = (double)res[1]; vhi = (double)res[2]; vmean = (double)res[0] / (double)count;
+        if (lo) *lo = vlo; if (hi) *hi = vhi; if (mean_raw) *mean_raw = vmean;
+    }
+    // normalizeImage: x -= min; x *= 1/max(x)  (utils.py:220-223); then subtract the mean of the normalised cube
+    const double scale = (vhi > vlo) ? 1.0 / (vhi - vlo) : 0.0;
+    const double mean_n = (vmean - vlo) * scale;
+    RET_IF(launch_u8_to_D(stage, s->D, s->ld, s->m, s->n, vlo, scale, mean_n, st));
+    CK(cudaMemsetAsync(s->T, 0, sizeof(float) * (size_t)s->ld * s->n, st));     // T was the staging buffer
+    return after_load(s);
+}
+
+// --------------------------------------------------------------------------------------------------- steps
+static int upload_state(bsub_solver* s, cudaStream_t st) {
+    DevState h;
+    memset(&h, 0, sizeof(h));
+    const bsub_config& c = s->cfg;
+    const double mx = (double)std::max<long long>(c.m_global, c.n);
+    h.lambda = 1.0 / (sqrt(mx) * c.delta);
+    h.non_block_lambda = c.non_block_lambda_scale * h.lambda;
+    h.rho = c.rho; h.tol = c.tol; h.mu_scale = c.mu_scale;
+    h.max_iter = c.max_iter;
+    h.d = c.d_global > 0 ? c.d_global : (int)std::min<long long>(c.m_global, c.n);
+    h.round005d = round_half_even_005(h.d);
+    h.use_sv_prediction = c.use_sv_prediction;
+    h.break_on_rank0 = c.break_on_rank0;
+    h.sv = c.use_sv_prediction ? c.sv0 : h.d;
+    CK(cudaMemcpyAsync(s->st, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));     // h is a stack object
+    memset((void*)s->mirror, 0, sizeof(HostMirror));
+    return 0;
+}
+
+int bsub_comm_buffers(bsub_solver* s, double** sum_buf, int64_t* sum_count, double** max_buf, int64_t* max_count) {
+    if (!s) { set_error("bsub_comm_buffers: null solver"); return -1; }
+    if (sum_buf) *sum_buf = s->comm_sum;
+    if (sum_count) *sum_count = (int64_t)s->npad * s->npad + kCommTail;
+    if (max_buf) *max_buf = s->comm_max;
+    if (max_count) *max_count = 8;
+    return 0;
+}
+
+static int check_ready(bsub_solver* s) {
+    if (!s) { set_error("null solver"); return -1; }
+    if (!s->loaded) { set_error("no data loaded (call bsub_load_* first)"); return -1; }
+    if (s->cfg.prox == BSUB_PROX_FLAT_LINF && !s->groups_set) { set_error("one of graphs or groups must not be None"); return -1; }
+    if (s->cfg.prox == BSUB_PROX_GRAPH_LINF && !s->graph_set) { set_error("one of graphs or groups must not be None"); return -1; }
+    if (s->cfg.prox == BSUB_PROX_BLOCK_L2 && !s->blocks_set) { set_error("blocks_by_frame / lambdas_by_frame not set"); return -1; }
+    return 0;
+}
+
+int bsub_step_init_local(bsub_solver* s, void* stream) {
+    RET_IF(check_ready(s));
+    cudaStream_t st = as_stream(stream);
+    RET_IF(upload_state(s, st));
+    CK(cudaMemsetAsync(s->comm_max, 0, sizeof(double) * 8, st));
+    CK(cudaMemsetAsync(s->comm_sum + (size_t)s->npad * s->npad, 0, sizeof(double) * kCommTail, st));
+    RET_IF(launch_rowsum_max(s->D, s->ld, s->m, s->n, s->comm_max, st));
+    RET_IF(launch_gram(s->gp, s->D, nullptr, nullptr, s->ld, s->tasks_dev, nullptr, 0.f, s->gram_partial, s->comm_sum, st));
+    s->iters_enqueued = 0;
+    s->finalized = false;
+    return 0;
+}
+
+int bsub_step_init_finish(bsub_solver* s, void* stream) {
+    RET_IF(check_ready(s));
+    cudaStream_t st = as_stream(stream);
+    RET_IF(launch_eig(s->ep, s->comm_sum, s->comm_max, s->eb, s->st, 0, 1, st));
+    RET_IF(launch_init_Y(s->D, s->Y, s->S, s->ld, s->n, s->st, st));
+    s->initialised = true;
+    return 0;
+}
+
+int bsub_step_gram(bsub_solver* s, void* stream) {
+    if (!s || !s->initialised) { set_error("bsub_step_gram: solver not initialised"); return -1; }
+    return launch_gram(s->gp, s->D, s->S, s->Y, s->ld, s->tasks_dev, s->st, 0.f, s->gram_partial, s->comm_sum, as_stream(stream));
+}
+
+int bsub_step_solve(bsub_solver* s, void* stream) {
+    if (!s || !s->initialised) { set_error("bsub_step_solve: solver not initialised"); return -1; }
+    return launch_eig(s->ep, s->comm_sum, s->comm_max, s->eb, s->st, 1, 0, as_stream(stream));
+}
+
+int bsub_step_shrink(bsub_solver* s, void* stream) {
+    if (!s || !s->initialised) { set_error("bsub_step_shrink: solver not initialised"); return -1; }
+    cudaStream_t st = as_stream(stream);
+    ShrinkBuffers b;
+    b.D = s->D; b.S = s->S; b.Y = s->Y; b.T = s->T; b.U = s->U; b.tpart = s->tpart; b.Vr = s->eb.Vr; b.VC = s->eb.VC;
+    b.vstride = s->eb.vstride; b.part_zz = s->part_zz; b.part_nnz = s->part_nnz; b.part_max = s->part_max; b.part_wmax = nullptr;
+    RET_IF(launch_shrink(s->sp, b, s->st, s->shrink_mode, st));
+    int nparts = s->sp.nparts;
+    if (s->shrink_mode == SHRINK_SPILL) {
+        // two-phase: U = G_S -> prox -> S_new (written over S) -> dual update
+        if (s->cfg.prox == BSUB_PROX_FLAT_LINF) {
+            RET_IF(launch_prox_groups_csr(s->U, s->S, s->ld, s->m, s->n, s->gptr, s->gidx, s->ngroups, 0.f, s->st, st));
+        } else if (s->cfg.prox == BSUB_PROX_GRAPH_LINF) {
+            RET_IF(launch_prox_graph3(s->U, s->S, s->xi, s->tot, s->eta_dev, s->ld, s->cfg.rows, s->cfg.cols, s->n, 0.f,
+                                      s->cfg.graph_max_sweeps, (float)s->cfg.graph_tol, s->sweeps_dev, s->st, st));
+        } else {   // BSUB_PROX_BLOCK_L2
+            RET_IF(launch_block_l2_sums(s->U, s->labels_dev, s->ld, s->m, s->n, s->nlab, s->bsums, s->st, st));
+            RET_IF(launch_block_l2_apply(s->U, s->S, s->labels_dev, s->ld, s->m, s->n, s->nlab, s->bsums, s->lam_table, s->st, 0.0,
+                                         0.0, st));
+        }
+        nparts = s->num_sms * 8;
+        RET_IF(launch_dual_update(s->D, s->S, s->S, s->Y, s->T, s->eb.VC, s->eb.vstride, s->st, s->L, s->ld, s->n, s->part_zz,
+                                  s->part_nnz, s->part_max, nparts, st));
+    }
+    RET_IF(launch_control_post(s->st, s->part_zz, s->part_nnz, s->part_max, nparts, s->comm_sum + (size_t)s->npad * s->npad, s->log,
+                               s->mirror_dev, 1, st));
+    return 0;
+}
+
+int bsub_step_finish_iter(bsub_solver* s, void* stream) {
+    if (!s || !s->initialised) { set_error("bsub_step_finish_iter: solver not initialised"); return -1; }
+    cudaStream_t st = as_stream(stream);
+    RET_IF(launch_control_post(s->st, s->part_zz, s->part_nnz, s->part_max, 0, s->comm_sum + (size_t)s->npad * s->npad, s->log,
+                               s->mirror_dev, 2, st));
+    CK(cudaEventRecord(s->ev[s->iters_enqueued % (kRunAhead + 1)], st));
+    s->iters_enqueued++;
+    return 0;
+}
+
+static void fill_status(bsub_solver* s, bsub_status* out, const DevState* h) {
+    memset(out, 0, sizeof(*out));
+    if (h) {
+        out->iter = h->iter; out->converged = h->converged; out->done = h->done; out->svp = h->svp_L; out->err = h->err; out->mu = h->mu;
+        out->norm_two = h->norm_two; out->norm_fro = sqrt(h->normD2); out->norm_rowsum = h->norm_rowsum; out->lambda = h->lambda;
+    } else {
+        out->iter = s->mirror->iter; out->converged = s->mirror->converged; out->done = s->mirror->done; out->svp = s->mirror->svp;
+        out->err = s->mirror->err;
+    }
+}
+
+int bsub_poll(bsub_solver* s, bsub_status* out) {
+    if (!s || !out) { set_error("bsub_poll: null argument"); return -1; }
+    fill_status(s, out, nullptr);
+    return 0;
+}
+
+int bsub_sync_status(bsub_solver* s, bsub_status* out, void* stream) {
+    if (!s || !out) { set_error("bsub_sync_status: null argument"); return -1; }
+    DevState h;
+    CK(cudaMemcpyAsync(&h, s->st, sizeof(h), cudaMemcpyDeviceToHost, as_stream(stream)));
+    CK(cudaStreamSynchronize(as_stream(stream)));
+    fill_status(s, out, &h);
+    return 0;
+}
+
+int bsub_run(bsub_solver* s, void* stream) {
+    RET_IF(bsub_step_init_local(s, stream));
+    RET_IF(bsub_step_init_finish(s, stream));
+    const int max_iter = s->cfg.max_iter;
+    for (int it = 0; it < max_iter + 1; ++it) {
+        // bounded run-ahead: wait for iteration it - kRunAhead, then look at the mapped stop flag (no device sync)
+        if (it >= kRunAhead) {
+            CK(cudaEventSynchronize(s->ev[(it - kRunAhead) % (kRunAhead + 1)]));
+            if (s->mirror->done) break;
+        }
+        RET_IF(bsub_step_gram(s, stream));
+        RET_IF(bsub_step_solve(s, stream));
+        RET_IF(bsub_step_shrink(s, stream));
+        RET_IF(bsub_step_finish_iter(s, stream));
+    }
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------------- results
+int bsub_finalize(bsub_solver* s, void* stream) {
+    if (!s || !s->initialised) { set_error("bsub_finalize: nothing has been solved"); return -1; }
+    if (s->finalized) return 0;
+    if (!s->L) { CK(cudaMalloc((void**)&s->L, sizeof(float) * (size_t)s->ld * s->n)); }
+    RET_IF(launch_materialize_L(s->T, s->eb.VC, s->eb.vstride, s->st, s->L, s->ld, s->m, s->n, as_stream(stream)));
+    s->finalized = true;
+    return 0;
+}
+
+static float* pick(bsub_solver* s, int which) {
+    switch (which) { case 0: return s->L; case 1: return s->S; case 2: return s->D; case 3: return s->Y; default: return nullptr; }
+}
+int bsub_get_L_f32_dev(bsub_solver* s, float** L, int64_t* ld) {
+    if (!s || !s->finalized) { set_error("bsub_get_L_f32_dev: call bsub_finalize first"); return -1; }
+    *L = s->L; if (ld) *ld = s->ld; return 0;
+}
+int bsub_get_S_f32_dev(bsub_solver* s, float** S, int64_t* ld) { if (!s) return -1; *S = s->S; if (ld) *ld = s->ld; return 0; }
+int bsub_get_D_f32_dev(bsub_solver* s, float** D, int64_t* ld) { if (!s) return -1; *D = s->D; if (ld) *ld = s->ld; return 0; }
+int bsub_get_Y_f32_dev(bsub_solver* s, float** Y, int64_t* ld) { if (!s) return -1; *Y = s->Y; if (ld) *ld = s->ld; return 0; }
+
+int bsub_download_f32(bsub_solver* s, int which, float* dst, int64_t ld, void* stream) {
+    if (!s || !dst || ld < s->m) { set_error("bsub_download_f32: bad argument"); return -1; }
+    if (which == 0 && !s->finalized) RET_IF(bsub_finalize(s, stream));
+    float* src = pick(s, which);
+    if (!src) { set_error("bsub_download_f32: bad selector %d", which); return -1; }
+    CK(cudaMemcpy2DAsync(dst, sizeof(float) * ld, src, sizeof(float) * s->ld, sizeof(float) * s->m, s->n, cudaMemcpyDeviceToHost,
+                         as_stream(stream)));
+    CK(cudaStreamSynchronize(as_stream(stream)));
+    return 0;
+}
+
+int bsub_download_f64(bsub_solver* s, int which, double* dst, int64_t ld, void* stream) {
+    if (!s || !dst || ld < s->m) { set_error("bsub_download_f64: bad argument"); return -1; }
+    cudaStream_t st = as_stream(stream);
+    if (which == 0 && !s->finalized) RET_IF(bsub_finalize(s, stream));
+    float* src = pick(s, which);
+    if (!src) { set_error("bsub_download_f64: bad selector %d", which); return -1; }
+    // widen on the device in frame batches through the tpart / gram scratch would be fragile: use a dedicated buffer
+    const long long batch = std::max<long long>(1, std::min<long long>(s->n, (64ll << 20) / std::max<long long>(1, s->m)));
+    double* stage = nullptr;
+    CK(cudaMalloc((void**)&stage, sizeof(double) * (size_t)batch * s->m));
+    int rc = 0;
+    for (long long f0 = 0; f0 < s->n && rc == 0; f0 += batch) {
+        const int nf = (int)std::min<long long>(batch, s->n - f0);
+        rc = launch_export_f64(src + (size_t)f0 * s->ld, s->ld, stage, s->m, s->m, nf, st);
+        if (rc == 0 && cudaMemcpy2DAsync(dst + (size_t)f0 * ld, sizeof(double) * ld, stage, sizeof(double) * s->m, sizeof(double) * s->m,
+                                         nf, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("bsub_download_f64: copy failed"); rc = -1; }
+        if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_download_f64: sync failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    }
+    cudaFree(stage);
+    return rc;
+}
+
+int bsub_get_log(bsub_solver* s, bsub_iter_log* out, int32_t cap, int32_t* count) {
+    if (!s || !out || !count) { set_error("bsub_get_log: null argument"); return -1; }
+    DevState h;
+    CK(cudaMemcpy(&h, s->st, sizeof(h), cudaMemcpyDeviceToHost));
+    std::vector<IterLog> tmp(kMaxIterLog);
+    CK(cudaMemcpy(tmp.data(), s->log, sizeof(IterLog) * kMaxIterLog, cudaMemcpyDeviceToHost));
+    int n = 0;
+    for (int i = 0; i < kMaxIterLog && i < h.iter && n < cap; ++i) {
+        if (tmp[i].iter != i + 1) break;         // an aborted (rank-0) iteration has no log line, like the reference
+        out[n].iter = tmp[i].iter; out[n].svp = tmp[i].svp; out[n].sv = tmp[i].sv; out[n].reserved = 0; out[n].err = tmp[i].err;
+        out[n].mu = tmp[i].mu; out[n].nnz = tmp[i].nnz; ++n;
+    }
+    *count = n;
+    return 0;
+}
+
+// foreground mask on the solver's own buffers -------------------------------------------------------------------
+int bsub_mask_stats_local(bsub_solver* s, int phase, void* stream) {
+    if (!s || !s->initialised) { set_error("bsub_mask_stats_local: nothing has been solved"); return -1; }
+    cudaStream_t st = as_stream(stream);
+    if (!s->finalized) RET_IF(bsub_finalize(s, stream));
+    double* tail = s->comm_sum + (size_t)s->npad * s->npad;
+    if (phase == 0) {
+        CK(cudaMemsetAsync(s->comm_max, 0, sizeof(double) * 8, st));
+        return launch_absmax(s->S, s->ld, s->m, s->n, s->comm_max + 1, st);
+    }
+    CK(cudaMemsetAsync(tail + 4, 0, sizeof(double) * 3, st));
+    return launch_mask_stats(s->D, s->L, s->S, s->ld, s->m, s->n, s->comm_max + 1, tail + 4, st);
+}
+
+int bsub_mask_dev(bsub_solver* s, double sigmas, uint8_t* mask_dev, void* stream) {
+    if (!s || !mask_dev) { set_error("bsub_mask_dev: null argument"); return -1; }
+    double* tail = s->comm_sum + (size_t)s->npad * s->npad;
+    return launch_mask_write(s->S, s->ld, s->m, s->n, tail + 4, sigmas, mask_dev, s->m, as_stream(stream));
+}
+
+int bsub_mask_host(bsub_solver* s, double sigmas, uint8_t* mask_host, void* stream) {
+    if (!s || !mask_host) { set_error("bsub_mask_host: null argument"); return -1; }
+    cudaStream_t st = as_stream(stream);
+    RET_IF(bsub_mask_stats_local(s, 0, stream));
+    RET_IF(bsub_mask_stats_local(s, 1, stream));
+    unsigned char* dev = nullptr;
+    CK(cudaMalloc((void**)&dev, (size_t)s->n * s->m));
+    int rc = bsub_mask_dev(s, sigmas, dev, stream);
+    if (rc == 0 && cudaMemcpyAsync(mask_host, dev, (size_t)s->n * s->m, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("bsub_mask_host: copy failed"); rc = -1; }
+    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_mask_host: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    cudaFree(dev);
+    return rc;
+}
+
+// --------------------------------------------------------------------------------------------------- operators
+int bsub_foreground_mask_dev(const float* D, const float* L, const float* S, int64_t ld, int64_t m, int32_t n, double sigmas,
+                             uint8_t* mask, void* stream) {
+    if (!D || !L || !S || !mask || ld < m || (ld % 4) != 0) { set_error("bsub_foreground_mask_dev: bad argument (ld must be a multiple of 4, pad columns zero)"); return -1; }
+    cudaStream_t st = as_stream(stream);
+    double* buf = nullptr;
+    CK(cudaMalloc((void**)&buf, sizeof(double) * 4));
+    CK(cudaMemsetAsync(buf, 0, sizeof(double) * 4, st));
+    int rc = launch_absmax(S, ld, m, n, buf, st);
+    if (rc == 0) rc = launch_mask_stats(D, L, S, ld, m, n, buf, buf + 1, st);
+    if (rc == 0) rc = launch_mask_write(S, ld, m, n, buf + 1, sigmas, mask, m, st);
+    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_foreground_mask_dev: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    cudaFree(buf);
+    return rc;
+}
+
+int bsub_prox_flat3_dev(const float* U, float* V, int64_t ld, int32_t rows, int32_t cols, int32_t n, double lambda1, void* stream) {
+    if (!U || !V || (long long)rows * cols > ld) { set_error("bsub_prox_flat3_dev: bad argument"); return -1; }
+    return launch_prox_flat3(U, V, ld, rows, cols, n, (float)lambda1, as_stream(stream));
+}
+
+int bsub_prox_flat_groups_dev(const float* U, float* V, int64_t ld, int64_t m, int32_t n, const int32_t* g, double lambda1, void* stream) {
+    if (!U || !V || !g || ld < m) { set_error("bsub_prox_flat_groups_dev: bad argument"); return -1; }
+    int gmax = 0;
+    for (long long p = 0; p < m; ++p) { if (g[p] < 0) { set_error("bsub_prox_flat_groups_dev: negative group id"); return -1; } gmax = std::max(gmax, (int)g[p]); }
+    std::vector<int> cnt((size_t)gmax + 1, 0), start((size_t)gmax + 1, 0);
+    for (long long p = 0; p < m; ++p) if (g[p] > 0) cnt[g[p]]++;
+    int acc = 0;
+    for (int k = 1; k <= gmax; ++k) { start[k - 1] = acc; acc += cnt[k]; }
+    start[gmax] = acc;
+    std::vector<int> idx((size_t)std::max(acc, 1)), fill(start.begin(), start.end());
+    for (long long p = 0; p < m; ++p) if (g[p] > 0) idx[fill[g[p] - 1]++] = (int)p;
+    int *gptr = nullptr, *gidx = nullptr;
+    CK(cudaMalloc((void**)&gptr, sizeof(int) * ((size_t)gmax + 1)));
+    CK(cudaMalloc((void**)&gidx, sizeof(int) * idx.size()));
+    CK(cudaMemcpy(gptr, start.data(), sizeof(int) * ((size_t)gmax + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(gidx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
+    int rc = launch_prox_groups_csr(U, V, ld, m, n, gptr, gidx, gmax, (float)lambda1, nullptr, as_stream(stream));
+    if (rc == 0 && cudaStreamSynchronize(as_stream(stream)) != cudaSuccess) { set_error("bsub_prox_flat_groups_dev: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    cudaFree(gptr); cudaFree(gidx);
+    return rc;
+}
+
+int bsub_prox_graph3_dev(const float* U, float* V, int64_t ld, int32_t rows, int32_t cols, int32_t n, double lambda1,
+                         const double* eta_host, int32_t max_sweeps, double tol, int32_t* sweeps_used, void* stream) {
+    if (!U || !V || (long long)rows * cols > ld) { set_error("bsub_prox_graph3_dev: bad argument"); return -1; }
+    cudaStream_t st = as_stream(stream);
+    const long long nwi = rows - std::min(3, rows) + 1, nwj = cols - std::min(3, cols) + 1, nw = nwi * nwj;
+    float *xi = nullptr, *tot = nullptr, *eta = nullptr; int* sw = nullptr;
+    CK(cudaMalloc((void**)&xi, sizeof(float) * (size_t)n * nw * 9));
+    CK(cudaMalloc((void**)&tot, sizeof(float) * (size_t)n * ld));
+    CK(cudaMalloc((void**)&sw, sizeof(int)));
+    if (eta_host) {
+        std::vector<float> ef((size_t)nw);
+        for (long long i = 0; i < nw; ++i) ef[i] = (float)eta_host[i];
+        CK(cudaMalloc((void**)&eta, sizeof(float) * nw));
+        CK(cudaMemcpy(eta, ef.data(), sizeof(float) * nw, cudaMemcpyHostToDevice));
+    }
+    int rc = launch_prox_graph3(U, V, xi, tot, eta, ld, rows, cols, n, (float)lambda1, max_sweeps > 0 ? max_sweeps : 4000, (float)tol, sw,
+                                nullptr, st);
+    int sw_h = 0;
+    if (rc == 0 && cudaMemcpyAsync(&sw_h, sw, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_prox_graph3_dev: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    if (sweeps_used) *sweeps_used = sw_h;
+    cudaFree(xi); cudaFree(tot); cudaFree(sw); if (eta) cudaFree(eta);
+    return rc;
+}
+
+int bsub_block_shrink_dev(const float* G, float* R, int64_t ld, int64_t m, int32_t n, const uint8_t* labels, const int32_t* lam_ptr,
+                          const double* lam, double mu, double non_block_lambda, void* stream) {
+    if (!G || !R || !labels || !lam_ptr || ld < m) { set_error("bsub_block_shrink_dev: bad argument"); return -1; }
+    cudaStream_t st = as_stream(stream);
+    int maxb = 0;
+    for (int f = 0; f < n; ++f) maxb = std::max(maxb, lam_ptr[f + 1] - lam_ptr[f]);
+    const int nlab = maxb + 1;
+    std::vector<double> table((size_t)n * nlab, 0.0);
+    for (int f = 0; f < n; ++f)
+        for (int b = 0; b < lam_ptr[f + 1] - lam_ptr[f]; ++b) table[(size_t)f * nlab + b + 1] = lam[lam_ptr[f] + b];
+    unsigned char* lab_d = nullptr; double *tab_d = nullptr, *sums = nullptr;
+    CK(cudaMalloc((void**)&lab_d, (size_t)n * m));
+    CK(cudaMalloc((void**)&tab_d, sizeof(double) * table.size()));
+    CK(cudaMalloc((void**)&sums, sizeof(double) * table.size()));
+    CK(cudaMemcpy(lab_d, labels, (size_t)n * m, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(tab_d, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice));
+    int rc = launch_block_l2_sums(G, lab_d, ld, m, n, nlab, sums, nullptr, st);
+    if (rc == 0) rc = launch_block_l2_apply(G, R, lab_d, ld, m, n, nlab, sums, tab_d, nullptr, mu, non_block_lambda, st);
+    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_block_shrink_dev: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    cudaFree(lab_d); cudaFree(tab_d); cudaFree(sums);
+    return rc;
+}
+
+int bsub_gram_dev(const float* D, const float* S, const float* Y, int64_t ld, int64_t m, int32_t n, double mu, double* G_host,
+                  void* stream) {
+    if (!D || !G_host || ld < m || (ld % 32) != 0) { set_error("bsub_gram_dev: bad argument (ld must be a multiple of 32, pad columns zero)"); return -1; }
+    if ((S == nullptr) != (Y == nullptr)) { set_error("bsub_gram_dev: S and Y must both be given or both be NULL"); return -1; }
+    cudaStream_t st = as_stream(stream);
+    int dev = 0, sms = 148;
+    CK(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    GramPlan gp = make_gram_plan(n, ld, sms);
+    std::vector<int2> tasks(gp.ntasks);
+    fill_gram_tasks(gp, tasks.data());
+    int2* tasks_d = nullptr; double *partial = nullptr, *G = nullptr;
+    CK(cudaMalloc((void**)&tasks_d, sizeof(int2) * gp.ntasks));
+    CK(cudaMalloc((void**)&partial, sizeof(double) * gp.partial_elems));
+    CK(cudaMalloc((void**)&G, sizeof(double) * (size_t)gp.npad * gp.npad));
+    CK(cudaMemcpy(tasks_d, tasks.data(), sizeof(int2) * gp.ntasks, cudaMemcpyHostToDevice));
+    int rc = launch_gram(gp, D, S, Y, ld, tasks_d, nullptr, (float)(S ? 1.0 / mu : 0.0), partial, G, st);
+    if (rc == 0 && cudaMemcpy2DAsync(G_host, sizeof(double) * n, G, sizeof(double) * gp.npad, sizeof(double) * n, n, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("bsub_gram_dev: copy failed"); rc = -1; }
+    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_gram_dev: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    cudaFree(tasks_d); cudaFree(partial); cudaFree(G);
+    return rc;
+}
+
+int bsub_eig_topk(const double* G_host, int32_t n, int32_t k, double* lam_host, double* vec_host) {
+    if (!G_host || n <= 0 || k <= 0 || k > n || !lam_host) { set_error("bsub_eig_topk: bad argument"); return -1; }
+    const int npad = ((n + 31) / 32) * 32;
+    EigPlan ep = make_eig_plan(n, npad);
+    EigBuffers eb;
+    memset(&eb, 0, sizeof(eb));
+    double* G = nullptr; DevState* st = nullptr;
+    CK(cudaMalloc((void**)&G, sizeof(double) * (size_t)npad * npad));
+    CK(cudaMemset(G, 0, sizeof(double) * (size_t)npad * npad));
+    CK(cudaMemcpy2D(G, sizeof(double) * npad, G_host, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void**)&eb.work, sizeof(double) * ep.work_doubles));
+    CK(cudaMalloc((void**)&eb.lam, sizeof(double) * n));
+    CK(cudaMalloc((void**)&eb.Z, sizeof(double) * (size_t)n * n));
+    CK(cudaMalloc((void**)&st, sizeof(DevState)));
+    CK(cudaMemset(st, 0, sizeof(DevState)));
+    eb.vstride = n;
+    int rc = launch_eig(ep, G, nullptr, eb, st, 2, k, 0);
+    if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) { set_error("bsub_eig_topk: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    if (rc == 0) {
+        cudaMemcpy(lam_host, eb.lam, sizeof(double) * k, cudaMemcpyDeviceToHost);
+        if (vec_host) cudaMemcpy(vec_host, eb.Z, sizeof(double) * (size_t)k * n, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(G); cudaFree(eb.work); cudaFree(eb.lam); cudaFree(eb.Z); cudaFree(st);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+/*
+ * bsub_b200.h -- C ABI of libbsub_b200.so: the B200 (sm_100a) implementation of the reference's inexact-ALM
+ * low-rank + structured-sparse decomposition (yakovdan/Background-Subtraction).
+ *
+ * The reference has no native plugin/FFI interface (it is pure Python); its boundary for
+ * this path is the Python call surface.  Each entry point below names the reference interface it replaces
+ * (file:line under /root/reference).  A binding only needs plain pointers and sizes (ctypes / cffi / cgo style);
+ * no torch or CUDA types appear in the signatures -- streams are passed as void* (cudaStream_t, 0 = default).
+ *
+ * Matrix convention: the reference's pixels x frames matrix in Fortran order (inexact_alm_lsd.py:84-88,225) is
+ * byte-for-byte a row-major [n_frames][m_pixels] array; every matrix pointer below uses that layout with a row
+ * pitch `ld` (elements) >= m.  Pixel index p = j*rows + i for image row i, column j (utils.py:230-231).
+ *
+ * All functions return 0 on success and a non-zero status on failure; bsub_last_error() then returns a message
+ * (the host-side mirror turns it into the reference's error convention, `raise Exception(msg)`).
+ */
+#ifndef BSUB_B200_H
+#define BSUB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bsub_solver bsub_solver;   /* opaque */
+
+/* proximal operator of the S-step */
+enum {
+    BSUB_PROX_FLAT_LINF = 0,   /* spams.proximalFlat 'group-lasso-linf'      inexact_alm_lsd.py:71-79,153-155 */
+    BSUB_PROX_GRAPH_LINF = 1,  /* spams.proximalGraph 'graph' (overlapping)   inexact_alm_lsd.py:49-57,159     */
+    BSUB_PROX_BLOCK_L2 = 2,    /* block_shrinkage_operator                    group_sparse_RPCA.py:13-42       */
+    BSUB_PROX_L1 = 3           /* elementwise soft threshold                  lsd_improvement.py:176           */
+};
+
+/* Replaces the hard-coded constants of inexact_alm_lsd.py:102-125 / group_sparse_RPCA.py:53-77. */
+typedef struct {
+    int64_t m;                 /* pixels held by THIS solver (a pixel-row shard in multi-GPU runs)            */
+    int64_t m_global;          /* pixels of the whole matrix (lambda = 1/(sqrt(max(m_global,n))*delta)); 0 = m */
+    int32_t n;                 /* frames                                                                       */
+    int32_t rows, cols;        /* image geometry of this solver's pixels, rows*cols == m (0,0 if not an image) */
+    int32_t prox;              /* BSUB_PROX_*                                                                  */
+    int32_t group_rows, group_cols; /* tile / window shape; only 3x3 (the reference's BLOCK_SIZE) is fused      */
+    double delta;              /* 10                                                                           */
+    double mu_scale;           /* 12.5 (inexact_alm_lsd.py:114) or 1.25 (group_sparse_RPCA.py:67)              */
+    double rho;                /* 1.6                                                                          */
+    double tol;                /* 1e-7                                                                         */
+    int32_t max_iter;          /* 500                                                                          */
+    int32_t sv0;               /* 10                                                                           */
+    int32_t use_sv_prediction; /* 1                                                                            */
+    int32_t break_on_rank0;    /* 1 for group_sparse_RPCA.py:91-93                                             */
+    double non_block_lambda_scale; /* 100 (group_sparse_RPCA.py:57)                                            */
+    int32_t d_global;          /* min(m_global, n) used by the sv predictor; 0 = derive                        */
+    int32_t graph_max_sweeps;  /* overlapping prox: BCD sweep cap per ALM iteration (0 = default 4000)         */
+    double graph_tol;          /* overlapping prox: stop when the largest dual change of a sweep <= tol*lambda/mu (0 = 1e-6) */
+    int32_t tile_rows;         /* tuning: rows per shrink tile (0 = default)                                   */
+    int32_t cluster_frames;    /* tuning: CTAs per cluster splitting the frames (0 = default)                  */
+    int32_t reserved[6];
+} bsub_config;
+
+typedef struct {
+    int32_t iter;              /* reference iter_out                                                            */
+    int32_t converged;         /* reference `converged`                                                         */
+    int32_t done;              /* 0 running, 1 converged, 2 max_iter, 3 rank-0 break, 4 zero input              */
+    int32_t svp;               /* rank of L                                                                     */
+    double err;                /* ||Z||_F / ||D||_F of the last completed iteration                             */
+    double mu;                 /* mu after the last update                                                      */
+    double norm_two, norm_fro, norm_rowsum, lambda;
+} bsub_status;
+
+typedef struct {
+    int32_t iter, svp, sv, reserved;
+    double err, mu;
+    uint64_t nnz;              /* ||S||_0 (the reference prints it every iteration, inexact_alm_lsd.py:170)      */
+} bsub_iter_log;
+
+const char* bsub_last_error(void);
+int bsub_version(void);
+void bsub_default_config(bsub_config* cfg);
+
+/* ---- solver life cycle ------------------------------------------------------------------------------------ */
+int bsub_create(const bsub_config* cfg, bsub_solver** out);
+int bsub_destroy(bsub_solver* s);
+
+/* group / graph / block descriptions: the hot-path *types* of SURVEY.md 8a (a8-a11).
+ * flat: int32[m] 1-based ids from get_proximal_flat_groups_nonoverlap (lsd_improvement.py:14-34); a regular 3x3
+ *       tiling of the rows x cols image is recognised and fused, anything else takes the generic two-phase path. */
+int bsub_set_flat_groups(bsub_solver* s, const int32_t* groups_host);
+/* graph: overlapping windows of getGraphSPAMS_all_groups (inexact_alm_lsd.py:13-46); eta_host may be NULL (all 1) */
+int bsub_set_graph_windows(bsub_solver* s, const double* eta_host, int64_t n_eta);
+/* blocks: blocks_by_frame / lambdas_by_frame of group_sparse_RPCA.py:45 as a label map uint8[n][m] (0 = complement,
+ *       b = block b of that frame) plus the CSR (lam_ptr[n+1], lam) of the per-frame lambda lists. */
+int bsub_set_blocks(bsub_solver* s, const uint8_t* labels_host, const int32_t* lam_ptr, const double* lam);
+
+/* ---- data in ---------------------------------------------------------------------------------------------- */
+int bsub_load_D_f64_host(bsub_solver* s, const double* D, int64_t ld, void* stream);      /* host float64 (NumPy)   */
+int bsub_load_D_f32_host(bsub_solver* s, const float* D, int64_t ld, void* stream);       /* host float32 (pinned)  */
+int bsub_load_D_f32_dev(bsub_solver* s, const float* D, int64_t ld, void* stream);        /* device float32         */
+/* LSD() pre-processing on the device (inexact_alm_lsd.py:211-225): uint8 cube [n][m] -> normalise to [0,1] over the
+ * whole cube, subtract the global mean.  lo/hi/mean in raw units are returned (and may be forced by the caller for
+ * sharded runs when force != 0). */
+int bsub_load_u8_host(bsub_solver* s, const uint8_t* frames, double* lo, double* hi, double* mean_raw, int force, void* stream);
+
+/* ---- whole solve on one GPU: inexact_alm_lsd.py:82-179 / group_sparse_RPCA.py:45-126 ------------------------ */
+int bsub_run(bsub_solver* s, void* stream);
+
+/* ---- step interface for pixel-sharded multi-GPU runs (the caller all-reduces between the steps) -------------- */
+int bsub_comm_buffers(bsub_solver* s, double** sum_buf, int64_t* sum_count, double** max_buf, int64_t* max_count);
+int bsub_step_init_local(bsub_solver* s, void* stream);    /* Gram(D) partial + row-sum max partial                */
+int bsub_step_init_finish(bsub_solver* s, void* stream);   /* ||D||_2, mu0, Y0, S0                                  */
+int bsub_step_gram(bsub_solver* s, void* stream);          /* partial Gram of W into sum_buf                        */
+int bsub_step_solve(bsub_solver* s, void* stream);         /* eigensolve + rank logic                               */
+int bsub_step_shrink(bsub_solver* s, void* stream);        /* fused pass B; leaves sum Z^2 etc. in the sum_buf tail  */
+int bsub_step_finish_iter(bsub_solver* s, void* stream);   /* err, mu update, stop flags                            */
+int bsub_poll(bsub_solver* s, bsub_status* st);            /* non-blocking: host mirror written by the device       */
+int bsub_sync_status(bsub_solver* s, bsub_status* st, void* stream);   /* blocking                                 */
+
+/* ---- results ---------------------------------------------------------------------------------------------- */
+int bsub_finalize(bsub_solver* s, void* stream);           /* materialise L = U (sigma - 1/mu) V^T                  */
+int bsub_get_L_f32_dev(bsub_solver* s, float** L, int64_t* ld);
+int bsub_get_S_f32_dev(bsub_solver* s, float** S, int64_t* ld);
+int bsub_get_D_f32_dev(bsub_solver* s, float** D, int64_t* ld);
+int bsub_get_Y_f32_dev(bsub_solver* s, float** Y, int64_t* ld);
+int bsub_download_f64(bsub_solver* s, int which /*0 L, 1 S, 2 D, 3 Y*/, double* dst_host, int64_t ld, void* stream);
+int bsub_download_f32(bsub_solver* s, int which, float* dst_host, int64_t ld, void* stream);
+int bsub_get_log(bsub_solver* s, bsub_iter_log* out, int32_t cap, int32_t* count);
+/* foreground_mask(D, L, S, sigmas) of utils.py:139-149 on the solver's own D, L, S; mask uint8[n][m] on the host */
+int bsub_mask_stats_local(bsub_solver* s, int phase /*0: max|S|, 1: count/sum/sumsq*/, void* stream);
+int bsub_mask_host(bsub_solver* s, double sigmas, uint8_t* mask_host, void* stream);
+int bsub_mask_dev(bsub_solver* s, double sigmas, uint8_t* mask_dev, void* stream);
+
+/* ---- operator-level entry points (the reference's unit-test seams); device pointers ------------ */
+/* foreground_mask(D, L, S, sigmas_from_mean)   utils.py:139-149 */
+int bsub_foreground_mask_dev(const float* D, const float* L, const float* S, int64_t ld, int64_t m, int32_t n, double sigmas,
+                             uint8_t* mask, void* stream);
+/* prox_flat(G_S, lambda1, groups) on the 3x3 tiling   inexact_alm_lsd.py:71-79 */
+int bsub_prox_flat3_dev(const float* U, float* V, int64_t ld, int32_t rows, int32_t cols, int32_t n, double lambda1, void* stream);
+/* prox_flat for an arbitrary groups vector (host int32[m]) */
+int bsub_prox_flat_groups_dev(const float* U, float* V, int64_t ld, int64_t m, int32_t n, const int32_t* groups_host,
+                              double lambda1, void* stream);
+/* prox(G_S, lambda1, graph) on the overlapping 3x3 windows   inexact_alm_lsd.py:49-57 */
+int bsub_prox_graph3_dev(const float* U, float* V, int64_t ld, int32_t rows, int32_t cols, int32_t n, double lambda1,
+                         const double* eta_host, int32_t max_sweeps, double tol, int32_t* sweeps_used, void* stream);
+/* block_shrinkage_operator(G, blocks_by_frame, lambdas_by_frame, mu, non_block_lambda)   group_sparse_RPCA.py:13-42 */
+int bsub_block_shrink_dev(const float* G, float* R, int64_t ld, int64_t m, int32_t n, const uint8_t* labels_host,
+                          const int32_t* lam_ptr, const double* lam, double mu, double non_block_lambda, void* stream);
+/* G = W W^T, W = D - S + Y/mu (S, Y may be NULL): fp64 frames x frames Gram, G_host double[n][n] */
+int bsub_gram_dev(const float* D, const float* S, const float* Y, int64_t ld, int64_t m, int32_t n, double mu, double* G_host,
+                  void* stream);
+/* top-k eigenpairs of a symmetric double[n][n] host matrix: svd_k_largest's n x n core (utils.py:204-212).
+ * lam_host double[k] descending, vec_host double[k][n] (row i = eigenvector i). */
+int bsub_eig_topk(const double* G_host, int32_t n, int32_t k, double* lam_host, double* vec_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSUB_B200_H */

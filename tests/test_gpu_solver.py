@@ -1,0 +1,133 @@
+"""-m gpu: end-to-end parity of the CUDA ALM solvers (through the Python mirror -> C ABI) against the CPU oracle
+and the committed golden vectors.  Tolerances are the north-star ones: rel-Frobenius(L), (S) <= 1e-4 (fp32),
+iteration count within +-1, masks identical on >= 99.9 % of the pixels."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, crop_D, rel_fro
+
+pytestmark = pytest.mark.gpu
+
+TOL_F = 1e-4
+
+
+@pytest.fixture(scope="module")
+def B():
+    import background_subtraction_b200 as B
+    return B
+
+
+def _report(name, dec_or_log, it, conv, L, S, Lr, Sr):
+    print(f"[{name}] iters={it} conv={conv} relF(L)={rel_fro(L, Lr):.3e} relF(S)={rel_fro(S, Sr):.3e}")
+
+
+@pytest.mark.parametrize("case", ["flat_a", "flat_b"])
+def test_flat_lsd_golden_small(B, golden_cases, watersurface_u8, case):
+    D, shp = crop_D(watersurface_u8, golden_cases[case + "_crop"])
+    groups = golden_cases[case + "_groups"]
+    dec = B.lsd_decomposition(D, groups=groups)
+    st = dec.status()
+    L, S = dec.download('L'), dec.download('S')
+    log = dec.log()
+    _report(case, log, st.iter, st.converged, L, S, golden_cases[case + "_L"], golden_cases[case + "_S"])
+    print("svp gpu", [l['svp'] for l in log], "ref", golden_cases[case + "_svp"].tolist())
+    print("err gpu", ["%.2e" % l['err'] for l in log][-4:], "ref", golden_cases[case + "_err"][-4:])
+    assert abs(st.iter - int(golden_cases[case + "_iter"])) <= 1
+    assert bool(st.converged) == bool(golden_cases[case + "_conv"])
+    assert rel_fro(L, golden_cases[case + "_L"]) <= TOL_F
+    assert rel_fro(S, golden_cases[case + "_S"]) <= TOL_F
+    mask = dec.mask(2)
+    ref = np.unpackbits(golden_cases[case + "_mask"])[:D.size].reshape(D.shape, order='F').astype(bool)
+    assert (mask == ref).mean() >= 0.999
+
+
+def test_flat_lsd_watersurface(B, watersurface_u8):
+    from oracle import alm_oracle as O
+    with open(os.path.join(GOLDEN, "golden_summary.json")) as f:
+        gold = json.load(f)["watersurface_flat_delta10"]
+    D, _x, _mean = O.normalize_and_center(watersurface_u8)
+    groups = B.get_proximal_flat_groups_nonoverlap((128, 160), (3, 3))
+    L, S, it, conv = B.inexact_alm_lsd(D, groups=groups)
+    assert np.isfortran(L) and L.dtype == np.float64 and L.shape == D.shape
+    olog = []
+    Lr, Sr, itr, convr = O.inexact_alm_lsd(D, groups=groups, log=olog)
+    _report("watersurface flat", None, it, conv, L, S, Lr, Sr)
+    assert itr == gold["iters"] and [l["svp"] for l in olog] == gold["svp"]      # oracle == reference golden
+    assert abs(it - gold["iters"]) <= 1 and conv == gold["converged"]
+    assert rel_fro(L, Lr) <= TOL_F and rel_fro(S, Sr) <= TOL_F
+    assert abs(np.linalg.norm(L) - gold["normL"]) <= 1e-4 * gold["normL"]
+    mask = B.foreground_mask(D, L, S)
+    mref = O.foreground_mask(D, Lr, Sr)
+    assert (mask == mref).mean() >= 0.999
+    gm = np.unpackbits(np.load(os.path.join(GOLDEN, "watersurface_flat_mask.npz"))["mask"])[:D.size]
+    assert (mask.ravel(order='F') == gm.astype(bool)).mean() >= 0.999
+
+
+def test_flat_lsd_delta1_and_tuning(B, watersurface_u8):
+    from oracle import alm_oracle as O
+    D, _x, _mean = O.normalize_and_center(watersurface_u8[:64, :96, :24])
+    groups = B.get_proximal_flat_groups_nonoverlap((64, 96), (3, 3))
+    Lr, Sr, itr, convr = O.inexact_alm_lsd(D, groups=groups, delta=1)
+    for tune in (dict(), dict(tile_rows=12, cluster_frames=1), dict(tile_rows=24, cluster_frames=4), dict(tile_rows=60, cluster_frames=8)):
+        L, S, it, conv = B.inexact_alm_lsd(D, groups=groups, delta=1, **tune)
+        _report("delta1 %s" % tune, None, it, conv, L, S, Lr, Sr)
+        assert abs(it - itr) <= 1 and conv == convr
+        assert rel_fro(L, Lr) <= TOL_F and rel_fro(S, Sr) <= TOL_F
+
+
+def test_flat_generic_groups(B, watersurface_u8):
+    """An arbitrary partition (4x2 tiles) takes the generic two-phase path."""
+    from oracle import alm_oracle as O
+    D, _x, _mean = O.normalize_and_center(watersurface_u8[:40, :50, :12])
+    groups = O.flat_groups_nonoverlap((40, 50), (4, 2))
+    Lr, Sr, itr, convr = O.inexact_alm_lsd(D, groups=groups)
+    L, S, it, conv = B.inexact_alm_lsd(D, groups=groups)
+    _report("generic groups", None, it, conv, L, S, Lr, Sr)
+    assert abs(it - itr) <= 1 and conv == convr
+    assert rel_fro(L, Lr) <= TOL_F and rel_fro(S, Sr) <= TOL_F
+
+
+def test_group_sparse_golden(B, golden_cases, watersurface_u8):
+    D, shp = crop_D(watersurface_u8, golden_cases["gs_a_crop"])
+    labels = golden_cases["gs_a_labels"]
+    ptr, lam = golden_cases["gs_a_lam_ptr"], golden_cases["gs_a_lam"]
+    n, m = labels.shape
+    blocks = [[labels[f] == b + 1 for b in range(ptr[f + 1] - ptr[f])] for f in range(n)]
+    lambdas = [[lam[ptr[f] + b] for b in range(ptr[f + 1] - ptr[f])] for f in range(n)]
+    L, S, it, conv = B.inexact_alm_group_sparse_RPCA(D, blocks, lambdas, delta=10)
+    _report("gs_a", None, it, conv, L, S, golden_cases["gs_a_L"], golden_cases["gs_a_S"])
+    assert abs(it - int(golden_cases["gs_a_iter"])) <= 1
+    assert conv == bool(golden_cases["gs_a_conv"])
+    assert rel_fro(L, golden_cases["gs_a_L"]) <= TOL_F and rel_fro(S, golden_cases["gs_a_S"]) <= TOL_F
+
+
+def test_graph_lsd_golden(B, golden_cases, watersurface_u8):
+    D, shp = crop_D(watersurface_u8, golden_cases["graph_a_crop"])
+    graph = B.getGraphSPAMS_all_groups(shp[:2], (3, 3))
+    L, S, it, conv = B.inexact_alm_lsd(D, graphs=graph, graph_tol=1e-6, graph_max_sweeps=20000)
+    _report("graph_a", None, it, conv, L, S, golden_cases["graph_a_L"], golden_cases["graph_a_S"])
+    assert abs(it - int(golden_cases["graph_a_iter"])) <= 1 and conv == bool(golden_cases["graph_a_conv"])
+    assert rel_fro(L, golden_cases["graph_a_L"]) <= 1e-3 and rel_fro(S, golden_cases["graph_a_S"]) <= 1e-3
+
+
+def test_rpca_l1(B, watersurface_u8):
+    from oracle import alm_oracle as O
+    D, _x, _mean = O.normalize_and_center(watersurface_u8[:48, :60, :20])
+    Lr, Sr, itr, convr = O.inexact_alm_rpca(D, delta=10)
+    L, S, it, conv = B.inexact_alm_rpca(D, delta=10)
+    _report("rpca", None, it, conv, L, S, Lr, Sr)
+    assert abs(it - itr) <= 1 and conv == convr
+    assert rel_fro(L, Lr) <= TOL_F and rel_fro(S, Sr) <= 5e-4
+
+
+def test_errors(B):
+    D = np.zeros((36, 4), order='F')
+    with pytest.raises(Exception, match="one of graphs or groups must not be None"):
+        B.inexact_alm_lsd(D)
+    with pytest.raises(Exception, match="only one of graphs or groups"):
+        B.inexact_alm_lsd(D, graphs=B.getGraphSPAMS_all_groups((6, 6), (3, 3)), groups=np.ones(36, dtype=np.int32))
+    with pytest.raises(Exception):
+        B.inexact_alm_lsd(D, groups=np.ones(35, dtype=np.int32))
