@@ -1,0 +1,179 @@
+"""Pixel-row sharded multi-GPU driver (one process per GPU, torch.distributed for the plumbing).
+
+The path shards by image columns (pixel index p = j*rows + i, so a block of whole columns is a contiguous pixel
+range of every frame): rank r owns the column triples [t0, t1) so that no 3x3 tile straddles two ranks
+(SURVEY.md section 8e).  Per ALM iteration the only exchanges are
+  * all-reduce(SUM) of the frames x frames fp64 Gram partial (+ nothing else in that message),
+  * all-reduce(SUM) of 3 doubles after the shrink pass (sum Z^2, ||S||_0, -),
+plus at init all-reduce(SUM) Gram(D), all-reduce(MAX) of the row-sum maximum, and at the end all-reduce(MAX/SUM) of
+the foreground-mask statistics.  The eigensolve is replicated (bit-identical inputs after the all-reduce), so no
+broadcast is needed.  The same driver runs world_size == 1 without any collective.
+
+The numerical work is done by a *step solver* object; the product one is `CudaStepSolver` (libbsub_b200.so through
+the C ABI).  The collective choreography is backend-agnostic (`comm` only needs all_reduce_sum / all_reduce_max on
+array-like buffers), which is what the world_size-2 gloo tests on CPU exercise with a NumPy stand-in step solver.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _cabi as C
+from . import api
+
+
+def shard_columns(cols, world, rank):
+    """Column range [c0, c1) of `rank`: whole column triples, as even as possible."""
+    ntrip = (cols + 2) // 3
+    base, extra = divmod(ntrip, world)
+    t0 = rank * base + min(rank, extra)
+    t1 = t0 + base + (1 if rank < extra else 0)
+    return min(3 * t0, cols), min(3 * t1, cols)
+
+
+class TorchComm:
+    """all-reduce on torch tensors over torch.distributed (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def all_reduce_max(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+
+
+class CudaStepSolver:
+    """Thin object view of the bsub_step_* C entry points for one shard."""
+
+    def __init__(self, rows, cols_local, n, m_global, delta=10, max_iter=500, tile_rows=0, cluster_frames=0):
+        self.m = rows * cols_local
+        cfg = api.make_config(self.m, n, C.PROX_FLAT_LINF, rows, cols_local, delta=delta, m_global=m_global,
+                              d_global=min(m_global, n), max_iter=max_iter, tile_rows=tile_rows,
+                              cluster_frames=cluster_frames)
+        self.dec = api.Decomposition(cfg)
+        self.dec.set_flat_groups(api.get_proximal_flat_groups_nonoverlap((rows, cols_local), api.BLOCK_SIZE))
+        self.lib, self.h = self.dec.lib, self.dec.h
+        self.n = n
+        sp, mp = ctypes.c_void_p(), ctypes.c_void_p()
+        sc, mc = ctypes.c_int64(0), ctypes.c_int64(0)
+        C.check(self.lib.bsub_comm_buffers(self.h, ctypes.byref(sp), ctypes.byref(sc), ctypes.byref(mp), ctypes.byref(mc)))
+        import torch
+        self.sum_buf = api._wrap_device(sp.value, (sc.value,), torch.float64)
+        self.max_buf = api._wrap_device(mp.value, (mc.value,), torch.float64)
+        self.ngram = sc.value - 16
+
+    def _s(self):
+        return self.dec.stream()
+
+    def load(self, D):
+        self.dec.load(D)
+
+    def init_local(self):
+        C.check(self.lib.bsub_step_init_local(self.h, self._s()))
+
+    def init_finish(self):
+        C.check(self.lib.bsub_step_init_finish(self.h, self._s()))
+
+    def gram(self):
+        C.check(self.lib.bsub_step_gram(self.h, self._s()))
+
+    def solve(self):
+        C.check(self.lib.bsub_step_solve(self.h, self._s()))
+
+    def shrink(self):
+        C.check(self.lib.bsub_step_shrink(self.h, self._s()))
+
+    def finish_iter(self):
+        C.check(self.lib.bsub_step_finish_iter(self.h, self._s()))
+
+    def gram_view(self):
+        return self.sum_buf[:self.ngram]
+
+    def tail_view(self):
+        return self.sum_buf[self.ngram:self.ngram + 4]
+
+    def mask_tail_view(self):
+        return self.sum_buf[self.ngram + 4:self.ngram + 8]
+
+    def max_view(self):
+        return self.max_buf
+
+    def done(self):
+        """Non-blocking look at the device-written status word."""
+        return self.dec.poll().done != 0
+
+    def wait_iter(self, k):
+        pass
+
+    def status(self):
+        return self.dec.status()
+
+    def finalize(self):
+        self.dec.finalize()
+
+    def mask_stats(self, phase):
+        C.check(self.lib.bsub_mask_stats_local(self.h, phase, self._s()))
+
+    def mask_device(self, sigmas=2.0):
+        import torch
+        out = torch.empty((self.n, self.m), dtype=torch.uint8, device="cuda")
+        C.check(self.lib.bsub_mask_dev(self.h, float(sigmas), ctypes.c_void_p(out.data_ptr()), self._s()))
+        return out
+
+
+class ShardedLSD:
+    """inexact_alm_lsd (flat 3x3 groups) over `comm.world` shards.  hooks: optional callbacks
+    hooks[name](phase) with phase in {'begin', 'end'} around 'gram', 'solve', 'shrink' for timing."""
+
+    def __init__(self, solver, comm, run_ahead=3, max_iter=500, fence=None):
+        self.s, self.comm, self.run_ahead, self.max_iter = solver, comm, run_ahead, max_iter
+        self.fence = fence            # callable(iteration) -> object with .synchronize(); bounds host run-ahead
+        self.iters_enqueued = 0
+
+    def solve(self, hooks=None):
+        s, comm = self.s, self.comm
+        hk = hooks or (lambda name, phase: None)
+        s.init_local()
+        comm.all_reduce_sum(s.gram_view())
+        comm.all_reduce_max(s.max_view())
+        s.init_finish()
+        fences = []
+        self.iters_enqueued = 0
+        for it in range(self.max_iter):
+            if it >= self.run_ahead:
+                if self.fence is not None:
+                    fences[it - self.run_ahead].synchronize()
+                if s.done():
+                    break
+            hk('gram', 'begin'); s.gram(); comm.all_reduce_sum(s.gram_view()); hk('gram', 'end')
+            hk('solve', 'begin'); s.solve(); hk('solve', 'end')
+            hk('shrink', 'begin'); s.shrink(); comm.all_reduce_sum(s.tail_view()); s.finish_iter(); hk('shrink', 'end')
+            if self.fence is not None:
+                fences.append(self.fence(it))
+            self.iters_enqueued += 1
+        return self
+
+    def finish(self, sigmas=2.0, want_mask=True):
+        s, comm = self.s, self.comm
+        s.finalize()
+        if not want_mask:
+            return None
+        s.mask_stats(0)
+        comm.all_reduce_max(s.max_view())
+        s.mask_stats(1)
+        comm.all_reduce_sum(s.mask_tail_view())
+        return s.mask_device(sigmas)
+
+
+def cuda_fence(_it):
+    import torch
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    return ev

@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: frames/s decomposed, synthetic 1920x1080 x 300 frames, flat-3x3 LSD (BASELINE.json).
+
+  python bench.py --gpus 1 --steps K --warmup W                  # this repo (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K --warmup W  # the reference algorithm on the host cores
+  torchrun ... bench.py --gpus N ...                              # N > 1: pixel-column shards, NCCL Gram all-reduce
+
+A "step" is one complete decomposition of the resident clip: init norms, all ALM iterations, materialisation of L and
+the foreground mask.  `value` is timed with CUDA events with D already in HBM; `e2e` is the same job through the
+public host-buffer API (pinned float32 D in, L + S + mask out) with both PCIe directions inside the timed region.
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (rows, cols, frames, seed, rectangles)
+    "synthetic_1080p_300": (1080, 1920, 300, 0, 6),
+    "synthetic_4k_600": (2160, 3840, 600, 1, 12),
+    "synthetic_qvga_200": (240, 320, 200, 100, 3),
+    "synthetic_small": (240, 320, 48, 5, 3),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="synthetic_1080p_300", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-div", type=int, default=8, help="CPU baseline: keep 1/div of the rows and of the columns")
+    ap.add_argument("--tile-rows", type=int, default=0)
+    ap.add_argument("--cluster-frames", type=int, default=0)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); power.append(float(p[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = samples in the upper half of the power range seen
+        thr = 0.5 * (min(power) + max(power))
+        load = [s for s, pw in zip(sm, power) if pw >= thr] or sm
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(power)), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_port_solve(D64, rows, cols, threads):
+    """The oracle port of inexact_alm_lsd (flat 3x3) + foreground_mask on the host cores (float64, NumPy/LAPACK +
+    the OpenMP C prox) -- test/bench infrastructure, not the product."""
+    from oracle import alm_oracle as O
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    groups = O.flat_groups_nonoverlap((rows, cols), (3, 3))
+    t0 = time.perf_counter()
+    L, S, it, conv = O.inexact_alm_lsd(D64, groups=groups)
+    O.foreground_mask(D64, L, S)
+    return time.perf_counter() - t0, it, conv
+
+
+def cpu_sample(video_u8, rows, cols, frames, div):
+    """Bounded sample of the same workload: a (rows/div) x (cols/div) window of every frame (all reference costs are
+    linear in the pixel count -- SURVEY 8d), rows/cols kept multiples of 3 so that the tiling is unchanged."""
+    r = max(3, (rows // div) // 3 * 3)
+    c = max(3, (cols // div) // 3 * 3)
+    cube = video_u8.reshape(frames, cols, rows)[:, :c, :r]                 # [n][col][row]
+    x = cube.astype(np.float64)
+    lo, hi = float(video_u8.min()), float(video_u8.max())
+    x = (x - lo) / (hi - lo)
+    x -= x.mean()
+    D = np.asfortranarray(x.reshape(frames, c * r).T)                       # m x n, F-order
+    return D, r, c
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is pure Python and is not
+    present on the GPU box) on all host cores, bounded sample, same metric/config."""
+    if rank != 0:
+        return None
+    from background_subtraction_b200 import synth
+    rows, cols, frames, seed, nrect = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    video, _ = synth.make_clip(rows, cols, frames, seed=seed, n_rect=nrect)
+    D, r, c = cpu_sample(video, rows, cols, frames, args.cpu_sample_div)
+    scale = (rows * cols) / float(r * c)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, it, conv = cpu_port_solve(D, r, c, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times)) * scale
+    val = frames / t
+    sample = f"{r}x{c} pixel window of every frame ({r * c}/{rows * cols} of the pixels), full solve, time scaled x{scale:.1f}"
+    return {"impl": "reference", "metric": "frames/s decomposed", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "rows": rows, "cols": cols, "frames": frames, "prox": "flat 3x3 l_inf (LSD)",
+                       "delta": 10},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample,
+                             "iters": it, "converged": bool(conv)},
+            "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import background_subtraction_b200 as B
+    from background_subtraction_b200 import synth
+    from background_subtraction_b200 import dist as bdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the CUDA path is the product; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    comm = bdist.TorchComm()
+    rows, cols, frames, seed, nrect = WORKLOADS[args.workload]
+    m = rows * cols
+
+    # ---- data: every rank generates the same seeded clip and keeps its column shard ----
+    t_gen = time.perf_counter()
+    video, _ = synth.make_clip(rows, cols, frames, seed=seed, n_rect=nrect)
+    c0, c1 = bdist.shard_columns(cols, world, rank)
+    cols_local = c1 - c0
+    m_local = rows * cols_local
+    lo, hi = float(video.min()), float(video.max())
+    mean = float(video.mean(dtype=np.float64))
+    shard_u8 = np.ascontiguousarray(video.reshape(frames, cols, rows)[:, c0:c1, :].reshape(frames, m_local))
+    scale = 1.0 / (hi - lo)
+    mean_n = (mean - lo) * scale
+    D_host = torch.empty((frames, m_local), dtype=torch.float32).pin_memory()
+    Dh = D_host.numpy()
+    stepf = max(1, (1 << 24) // m_local)
+    for f0 in range(0, frames, stepf):
+        Dh[f0:f0 + stepf] = ((shard_u8[f0:f0 + stepf].astype(np.float64) - lo) * scale - mean_n).astype(np.float32)
+    t_gen = time.perf_counter() - t_gen
+
+    solver = bdist.CudaStepSolver(rows, cols_local, frames, m, tile_rows=args.tile_rows, cluster_frames=args.cluster_frames)
+    solver.load(Dh)
+    torch.cuda.synchronize()
+    driver = bdist.ShardedLSD(solver, comm, fence=bdist.cuda_fence)
+
+    # ---- per-kernel timing hooks (CUDA events on the launching stream) ----
+    stream = torch.cuda.current_stream()
+    ev = {"gram": [], "solve": [], "shrink": []}
+    pending = {}
+
+    def hooks(name, phase):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        if phase == 'begin':
+            pending[name] = e
+        else:
+            ev[name].append((pending.pop(name), e))
+
+    def one_step(timed):
+        driver.solve(hooks if timed else None)
+        return driver.finish(2.0, want_mask=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        one_step(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        mask = one_step(True)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_step = float(tmax.item()) / args.steps
+    st = solver.status()
+    iters = int(st.iter)
+
+    def phase_ms(name):
+        v = [a.elapsed_time(b) for a, b in ev[name]]
+        return (float(np.mean(v)) if v else 0.0), len(v)
+
+    gram_ms, n_gram = phase_ms("gram")
+    solve_ms, n_solve = phase_ms("solve")
+    shrink_ms, n_shrink = phase_ms("shrink")
+    launches_per_iter = 2 + 1 + 1 + 2          # gram + reduce, eig, shrink, control x2
+    gpu_launches = int(args.steps * (iters * launches_per_iter + 2 + 1 + 1 + 1 + 1 + 2 + 1))
+
+    # ---- end to end through the public host-buffer API (single GPU only) ----
+    e2e = None
+    if not args.no_e2e and world == 1:
+        Lh = torch.empty((frames, m), dtype=torch.float32).pin_memory()
+        Sh = torch.empty((frames, m), dtype=torch.float32).pin_memory()
+        Mh = torch.empty((frames, m), dtype=torch.uint8).pin_memory()
+        dec = solver.dec
+
+        def e2e_step():
+            dec.load(Dh)                                        # H2D from pinned memory
+            dec.run()                                           # the C loop (bsub_run)
+            import ctypes
+            from background_subtraction_b200 import _cabi as C
+            C.check(dec.lib.bsub_download_f32(dec.h, 0, ctypes.c_void_p(Lh.data_ptr()), m, dec.stream()))
+            C.check(dec.lib.bsub_download_f32(dec.h, 1, ctypes.c_void_p(Sh.data_ptr()), m, dec.stream()))
+            C.check(dec.lib.bsub_mask_host(dec.h, 2.0, ctypes.c_void_p(Mh.data_ptr()), dec.stream()))
+
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        e2e = {"value": frames / dt, "unit": "frames/s", "h2d_bytes_per_step": int(4 * frames * m),
+               "d2h_bytes_per_step": int(9 * frames * m), "ms_per_step": dt * 1e3,
+               "what": "pinned float32 D in; float32 L, S and uint8 mask out (bsub_load_D_f32_host, bsub_run, bsub_download_f32 x2, bsub_mask_host)"}
+    elif world > 1:
+        e2e = {"value": None, "unit": "frames/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+               "what": "not measured for N > 1"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (per launch, algorithmic bytes) ----
+    peak, peak_src = measured_peaks()
+    elems_local = float(frames) * m_local
+    kern = {
+        "shrink_kernel": {"ms": shrink_ms, "launches": n_shrink, "alg_bytes": 20.0 * elems_local, "bound": "hbm"},
+        "gram_dmma_kernel": {"ms": gram_ms, "launches": n_gram, "alg_bytes": 12.0 * elems_local, "bound": "hbm"},
+        "eig_kernel": {"ms": solve_ms, "launches": n_solve, "alg_bytes": 8.0 * frames * frames, "bound": "latency"},
+    }
+    for k in kern.values():
+        k["gbs"] = (k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9) if k["ms"] > 0 else 0.0
+        k["share"] = (k["ms"] * k["launches"]) / (ms_step * args.steps) if ms_step > 0 else 0.0
+    dom = max(("shrink_kernel", "gram_dmma_kernel"), key=lambda n: kern[n]["ms"] * kern[n]["launches"])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": kern[dom]["alg_bytes"],
+                "note": "phase time = kernel + its small companions (gram: +reduce, +NCCL all-reduce when N>1; shrink: +2 control launches)"}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        D64, r, c = cpu_sample(video, rows, cols, frames, args.cpu_sample_div)
+        threads = os.cpu_count() or 1
+        dt, it_c, conv_c = cpu_port_solve(D64, r, c, threads)
+        sc = (rows * cols) / float(r * c)
+        cpu = {"value": frames / (dt * sc), "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"{r}x{c} pixel window of every frame ({r * c}/{rows * cols} of the pixels), full solve {dt:.1f} s, scaled x{sc:.1f}",
+               "iters": it_c, "converged": bool(conv_c)}
+
+    out = {"metric": "frames/s decomposed", "value": frames / (ms_step * 1e-3), "unit": "frames/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32 storage / f64 Gram+eigensolve", "data": "synthetic",
+           "config": {"workload": args.workload, "rows": rows, "cols": cols, "frames": frames, "prox": "flat 3x3 l_inf (LSD)",
+                      "delta": 10, "sharding": f"pixel columns over {world} GPU(s)", "l2": "inputs (2.5 GB/matrix) larger than L2",
+                      "tile_rows": solver.dec.cfg.tile_rows, "cluster_frames": solver.dec.cfg.cluster_frames},
+           "alm_iters": iters, "converged": bool(st.converged), "rank_L": int(st.svp), "err": float(st.err),
+           "mask_fraction": float(mask.float().mean().item()),
+           "kernels": kern, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
+           "clocks": clocks, "datagen_s": t_gen}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
