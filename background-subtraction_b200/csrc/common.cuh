@@ -38,6 +38,7 @@ struct DevState {
     int converged;
     int max_iter, round005d, d, use_sv_prediction, break_on_rank0;
     int eig_info;           // diagnostics of the eigen solver (bisection rounds etc.)
+    long long eig_clk[8];   // clock64() at the phase boundaries of the last eig_kernel (CTA 0)
 };
 
 struct IterLog {

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
         return a.in_smem ? (Asm + (size_t)li * n) : (a.Aglob + ((size_t)c * a.rows_per + li) * n);
     };
 
+    if (c == 0 && tid == 0) st->eig_clk[0] = clock64();
     // ---- load my rows -------------------------------------------------------------------------------------
     for (int li = warp; li < a.rows_per; li += EIG_WARPS) {
         int i = c + li * C;
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
     }
     cluster.sync();
     if (c != 0) return;
+    if (tid == 0) st->eig_clk[1] = clock64();
 
     // ---- 2. top-K eigenvalues of the tridiagonal matrix: multisection on Sturm counts ------------------------
     // shared-memory carve-up for the remaining phases (the matrix rows are dead now)
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
     }
     __threadfence_block();
     __syncthreads();
+    if (tid == 0) st->eig_clk[2] = clock64();
 
     // ---- 3. eigenvectors of the tridiagonal matrix: inverse iteration, one thread per vector ---------------------
     const int kcap = a.kcap;
@@ -304,6 +307,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
     }
     __threadfence_block();
     __syncthreads();
+    if (tid == 0) st->eig_clk[3] = clock64();
 
     // ---- 3b. CGS2 re-orthogonalisation among close eigenvalues (descending order) -------------------------------
     {
@@ -347,6 +351,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
         }
     }
 
+    if (tid == 0) st->eig_clk[4] = clock64();
     // ---- 4. back-transformation z <- H_0 H_1 ... H_{n-3} z, one warp per vector ---------------------------------
     for (int kb = 0; kb < K; kb += EIG_BT) {
         const int k = kb + warp;
@@ -373,6 +378,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
     __threadfence_block();
     __syncthreads();
 
+    if (tid == 0) st->eig_clk[5] = clock64();
     // ---- 5. control ------------------------------------------------------------------------------------------
     if (a.mode == 2) return;
     if (a.mode == 0) {

@@ -17,8 +17,11 @@
 
 namespace bsub {
 
-constexpr int GR_KC = 32;           // pixels per stage (128 B per frame row)
-constexpr int GR_LDS = GR_KC + 4;   // smem row stride in floats: 36 = 4 (mod 32) -> conflict-free fragment loads
+constexpr int GR_KC = 32;           // pixels per load step (128 B per frame row)
+// The W tile is kept in shared memory as fp64 (converted once by the producer warps): F2F.F64.F32 runs at
+// 1/4 rate, and every fragment is read by up to 14 warps, so converting at fragment-load time made the kernel
+// conversion-bound (ncu r1a: DMMA pipe 35 % active).  Row stride kc+4 doubles = 4 (mod 16): the 16 lanes of a
+// half-warp (r = 0..3, c = 0..3) hit 16 distinct 8-byte banks.
 constexpr int GR_MMA_WARPS = 14;
 constexpr int GR_PROD_WARPS = 2;
 constexpr int GR_THREADS = 32 * (GR_MMA_WARPS + GR_PROD_WARPS);
@@ -31,25 +34,27 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 struct GramArgs {
     const float* D; const float* S; const float* Y;   // S == nullptr -> W = D (init pass)
     long long ld;
-    int n, npad, ntasks, ntype, gridK;
-    long long nchunks;                                  // ld / GR_KC
+    int n, npad, ntasks, ntype, gridK, kc, lds;        // kc = pixels per stage (32, 16 or 8), lds = kc + 4
+    long long nchunks;                                  // ld / kc
     const int2* tasks;                                  // (bi, bj), bi <= bj
     const DevState* st;                                 // may be nullptr (stand-alone use)
     float inv_mu_override;                              // used when st == nullptr
     double* partial;                                    // [gridK][ntasks][32*32]
 };
 
-// Fill one stage: rows = frames (zero beyond n), 32 pixels each.
-__device__ __forceinline__ void gram_fill_stage(float* buf, const GramArgs& a, long long chunk, float inv_mu, int tp) {
-    const int q = tp & 7;       // float4 slot inside the 32-pixel row
-    const int r0 = tp >> 3;     // 0..7
-    const long long p0 = chunk * GR_KC + 4 * q;
+// Fill one stage: rows = frames (zero beyond n), kc pixels each, stored as fp64.
+__device__ __forceinline__ void gram_fill_stage(double* buf, const GramArgs& a, long long chunk, float inv_mu, int tp) {
+    const int qpr = a.kc >> 2;            // float4 slots per row (8, 4 or 2)
+    const int q = tp % qpr;
+    const int r0 = tp / qpr;
+    const int rstep = 64 / qpr;           // rows covered by the 64 producer threads per pass
+    const long long p0 = chunk * a.kc + 4 * q;
     const bool combo = (a.S != nullptr);
-    for (int f = r0; f < a.npad; f += 32) {
+    for (int f = r0; f < a.npad; f += 4 * rstep) {
         float4 d[4], s[4], y[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            int ff = f + 8 * u;
+            int ff = f + rstep * u;
             d[u] = make_float4(0.f, 0.f, 0.f, 0.f); s[u] = d[u]; y[u] = d[u];
             if (ff < a.n) {
                 long long off = (long long)ff * a.ld + p0;
@@ -59,15 +64,16 @@ __device__ __forceinline__ void gram_fill_stage(float* buf, const GramArgs& a, l
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            int ff = f + 8 * u;
+            int ff = f + rstep * u;
             if (ff < a.npad) {
-                float4 w;
                 // same fp32 expression as the shrink pass so that both passes see the same W
-                w.x = (d[u].x - s[u].x) + y[u].x * inv_mu;
-                w.y = (d[u].y - s[u].y) + y[u].y * inv_mu;
-                w.z = (d[u].z - s[u].z) + y[u].z * inv_mu;
-                w.w = (d[u].w - s[u].w) + y[u].w * inv_mu;
-                *reinterpret_cast<float4*>(buf + ff * GR_LDS + 4 * q) = w;
+                const float wx = (d[u].x - s[u].x) + y[u].x * inv_mu;
+                const float wy = (d[u].y - s[u].y) + y[u].y * inv_mu;
+                const float wz = (d[u].z - s[u].z) + y[u].z * inv_mu;
+                const float ww = (d[u].w - s[u].w) + y[u].w * inv_mu;
+                double* dst = buf + (size_t)ff * a.lds + 4 * q;
+                *reinterpret_cast<double2*>(dst) = make_double2((double)wx, (double)wy);
+                *reinterpret_cast<double2*>(dst + 2) = make_double2((double)wz, (double)ww);
             }
         }
     }
@@ -75,8 +81,8 @@ __device__ __forceinline__ void gram_fill_stage(float* buf, const GramArgs& a, l
 
 __global__ void __launch_bounds__(GR_THREADS, 1) gram_dmma_kernel(GramArgs a) {
     if (a.st != nullptr && a.st->done) return;
-    extern __shared__ __align__(16) float gram_smem[];
-    float* bufs[2] = {gram_smem, gram_smem + (size_t)a.npad * GR_LDS};
+    extern __shared__ __align__(16) double gram_smem[];
+    double* bufs[2] = {gram_smem, gram_smem + (size_t)a.npad * a.lds};
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int type = blockIdx.x % a.ntype;
@@ -108,15 +114,16 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_dmma_kernel(GramArgs a) {
         if (producer) {
             if (it + 1 < niter) gram_fill_stage(bufs[cur ^ 1], a, kslot + (it + 1) * a.gridK, inv_mu, tp);
         } else if (has_task) {
-            const float* rowA = bufs[cur] + (bi * 32 + fr) * GR_LDS + fc;
-            const float* rowB = bufs[cur] + (bj * 32 + fr) * GR_LDS + fc;
+            const double* rowA = bufs[cur] + (size_t)(bi * 32 + fr) * a.lds + fc;
+            const double* rowB = bufs[cur] + (size_t)(bj * 32 + fr) * a.lds + fc;
+            const int nks = a.kc >> 2, rs8 = 8 * a.lds;
 #pragma unroll 2
-            for (int ks = 0; ks < GR_KC / 4; ++ks) {
+            for (int ks = 0; ks < nks; ++ks) {
                 double af[4], bf[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    af[i] = (double)rowA[i * 8 * GR_LDS + ks * 4];
-                    bf[i] = (double)rowB[i * 8 * GR_LDS + ks * 4];
+                    af[i] = rowA[i * rs8 + ks * 4];
+                    bf[i] = rowB[i * rs8 + ks * 4];
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -165,13 +172,16 @@ GramPlan make_gram_plan(int n, long long ld, int num_sms) {
     p.nb = p.npad / 32;
     p.ntasks = p.nb * (p.nb + 1) / 2;
     p.ntype = (p.ntasks + GR_MMA_WARPS - 1) / GR_MMA_WARPS;
-    p.nchunks = ld / GR_KC;
+    // largest stage width whose two fp64 stages fit in shared memory
+    p.kc = GR_KC;
+    while (p.kc > 8 && (size_t)2 * p.npad * (p.kc + 4) * sizeof(double) > 200 * 1024) p.kc >>= 1;
+    p.nchunks = ld / p.kc;
     long long gk = num_sms / p.ntype;
     if (gk < 1) gk = 1;
     if (gk > p.nchunks) gk = p.nchunks;
     if (gk < 1) gk = 1;
     p.gridK = (int)gk;
-    p.smem_bytes = (size_t)2 * p.npad * GR_LDS * sizeof(float);
+    p.smem_bytes = (size_t)2 * p.npad * (p.kc + 4) * sizeof(double);
     p.partial_elems = (size_t)p.gridK * p.ntasks * 1024;
     return p;
 }
@@ -194,7 +204,7 @@ int launch_gram(const GramPlan& p, const float* D, const float* S, const float* 
     if (p.smem_bytes > 200 * 1024) { set_error("gram: n=%d too large for the shared-memory W tile", p.n); return -1; }
     GramArgs a;
     a.D = D; a.S = S; a.Y = Y; a.ld = ld; a.n = p.n; a.npad = p.npad; a.ntasks = p.ntasks; a.ntype = p.ntype;
-    a.gridK = p.gridK; a.nchunks = p.nchunks; a.tasks = dev_tasks; a.st = st; a.inv_mu_override = inv_mu_override;
+    a.gridK = p.gridK; a.kc = p.kc; a.lds = p.kc + 4; a.nchunks = p.nchunks; a.tasks = dev_tasks; a.st = st; a.inv_mu_override = inv_mu_override;
     a.partial = partial;
     gram_dmma_kernel<<<p.gridK * p.ntype, GR_THREADS, p.smem_bytes, stream>>>(a);
     BSUB_CUDA_CHECK(cudaGetLastError());

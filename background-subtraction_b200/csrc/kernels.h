@@ -9,7 +9,7 @@ namespace bsub {
 
 // ---------------------------------------------------------------- gram.cu
 struct GramPlan {
-    int n, npad, nb, ntasks, ntype, gridK;
+    int n, npad, nb, ntasks, ntype, gridK, kc;
     long long nchunks;
     size_t smem_bytes, partial_elems;
 };

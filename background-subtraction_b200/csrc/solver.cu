@@ -537,6 +537,14 @@ int bsub_download_f64(bsub_solver* s, int which, double* dst, int64_t ld, void* 
     return rc;
 }
 
+int bsub_debug_eig_cycles(bsub_solver* s, int64_t* out8) {
+    if (!s || !out8) { set_error("bsub_debug_eig_cycles: null argument"); return -1; }
+    DevState h;
+    CK(cudaMemcpy(&h, s->st, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) out8[i] = (int64_t)h.eig_clk[i];
+    return 0;
+}
+
 int bsub_get_log(bsub_solver* s, bsub_iter_log* out, int32_t cap, int32_t* count) {
     if (!s || !out || !count) { set_error("bsub_get_log: null argument"); return -1; }
     DevState h;

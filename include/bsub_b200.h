@@ -124,6 +124,8 @@ int bsub_get_Y_f32_dev(bsub_solver* s, float** Y, int64_t* ld);
 int bsub_download_f64(bsub_solver* s, int which /*0 L, 1 S, 2 D, 3 Y*/, double* dst_host, int64_t ld, void* stream);
 int bsub_download_f32(bsub_solver* s, int which, float* dst_host, int64_t ld, void* stream);
 int bsub_get_log(bsub_solver* s, bsub_iter_log* out, int32_t cap, int32_t* count);
+/* diagnostics: SM clock at the phase boundaries of the last eigensolve (load, tridiag, eigenvalues, vectors, reorth, back-transform) */
+int bsub_debug_eig_cycles(bsub_solver* s, int64_t* out8);
 /* foreground_mask(D, L, S, sigmas) of utils.py:139-149 on the solver's own D, L, S; mask uint8[n][m] on the host */
 int bsub_mask_stats_local(bsub_solver* s, int phase /*0: max|S|, 1: count/sum/sumsq*/, void* stream);
 int bsub_mask_host(bsub_solver* s, double sigmas, uint8_t* mask_host, void* stream);
