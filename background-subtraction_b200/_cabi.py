@@ -42,6 +42,7 @@ SIGNATURES = {
     "bsub_last_error": (ctypes.c_char_p, []),
     "bsub_version": (ctypes.c_int, []),
     "bsub_default_config": (None, [ctypes.POINTER(Config)]),
+    "bsub_abi_sizes": (None, [c_int32_p]),
     "bsub_create": (ctypes.c_int, [ctypes.POINTER(Config), ctypes.POINTER(vp)]),
     "bsub_destroy": (ctypes.c_int, [vp]),
     "bsub_set_flat_groups": (ctypes.c_int, [vp, c_int32_p]),

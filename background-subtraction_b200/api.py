@@ -82,10 +82,11 @@ def detect_flat_tiling(groups, img_shape=None):
     dec = np.nonzero(g[1:] < g[:-1])[0]
     if dec.size:
         cands.append((int(dec[0]) + 1, m // (int(dec[0]) + 1)))
-    else:                                   # ids never decrease: at most 3 columns
+    else:                                   # ids never decrease: at most 3 columns, or at most 3 rows
         for c in (1, 2, 3):
             if m % c == 0:
                 cands.append((m // c, c))
+                cands.append((c, m // c))
     for rows, cols in cands:
         if rows * cols == m and np.array_equal(get_proximal_flat_groups_nonoverlap((rows, cols), BLOCK_SIZE), g):
             return rows, cols

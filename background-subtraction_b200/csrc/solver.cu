@@ -73,6 +73,10 @@ extern "C" {
 const char* bsub_last_error(void) { return g_err; }
 int bsub_version(void) { return 100; }
 
+void bsub_abi_sizes(int32_t out3[3]) {
+    out3[0] = (int32_t)sizeof(bsub_config); out3[1] = (int32_t)sizeof(bsub_status); out3[2] = (int32_t)sizeof(bsub_iter_log);
+}
+
 void bsub_default_config(bsub_config* c) {
     memset(c, 0, sizeof(*c));
     c->prox = BSUB_PROX_FLAT_LINF; c->group_rows = 3; c->group_cols = 3; c->delta = 10.0; c->mu_scale = 12.5; c->rho = 1.6;

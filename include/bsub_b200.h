@@ -77,6 +77,8 @@ typedef struct {
 const char* bsub_last_error(void);
 int bsub_version(void);
 void bsub_default_config(bsub_config* cfg);
+/* sizeof(bsub_config), sizeof(bsub_status), sizeof(bsub_iter_log): lets a binding verify its struct layouts */
+void bsub_abi_sizes(int32_t out3[3]);
 
 /* ---- solver life cycle ------------------------------------------------------------------------------------ */
 int bsub_create(const bsub_config* cfg, bsub_solver** out);

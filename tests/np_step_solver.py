@@ -1,0 +1,93 @@
+"""Test-only NumPy (float64) implementation of the step-solver protocol of background-subtraction_b200/dist.py.
+It lets the sharded driver's collective choreography run on CPU ranks under gloo; the arithmetic of one shard is the
+oracle's (this file lives under tests/ and is never imported by the product)."""
+import numpy as np
+import torch
+
+from oracle import alm_oracle as O
+
+
+class NumpyStepSolver:
+    def __init__(self, D_local, rows, cols_local, n, m_global, delta=10, mu_scale=12.5, rho=1.6, tol=1e-7, max_iter=500):
+        self.D = np.asfortranarray(D_local, dtype=np.float64)          # m_local x n
+        self.rows, self.cols, self.n = rows, cols_local, n
+        self.groups = O.flat_groups_nonoverlap((rows, cols_local), (3, 3))
+        self.lam = 1.0 / (np.sqrt(max(m_global, n)) * delta)
+        self.d = min(m_global, n)
+        self.mu_scale, self.rho, self.tol, self.max_iter = mu_scale, rho, tol, max_iter
+        self.sum_buf = torch.zeros(n * n + 16, dtype=torch.float64)
+        self.max_buf = torch.zeros(8, dtype=torch.float64)
+        self.ngram = n * n
+        self.log = []
+
+    # -- views used by the driver's all-reduces
+    def gram_view(self): return self.sum_buf[:self.ngram]
+    def tail_view(self): return self.sum_buf[self.ngram:self.ngram + 4]
+    def mask_tail_view(self): return self.sum_buf[self.ngram + 4:self.ngram + 8]
+    def max_view(self): return self.max_buf
+
+    def init_local(self):
+        self.sum_buf.zero_(); self.max_buf.zero_()
+        self.sum_buf[:self.ngram] = torch.from_numpy((self.D.T @ self.D).ravel())
+        self.max_buf[0] = float(np.abs(self.D).sum(axis=1).max())
+        self.iter, self.done_flag, self.converged, self.sv = 0, 0, False, 10
+
+    def init_finish(self):
+        G = self.sum_buf[:self.ngram].numpy().reshape(self.n, self.n)
+        self.norm_two = float(np.sqrt(np.linalg.eigvalsh(G)[-1]))
+        self.normD2 = float(np.trace(G))
+        dual = max(self.norm_two, float(self.max_buf[0]) / self.lam)
+        self.Y = self.D / dual
+        self.S = np.zeros_like(self.D)
+        self.L = np.zeros_like(self.D)
+        self.mu = self.mu_scale / self.norm_two
+
+    def gram(self):
+        if self.done_flag: return
+        self.W = self.D - self.S + self.Y / self.mu
+        self.sum_buf[:self.ngram] = torch.from_numpy((self.W.T @ self.W).ravel())
+
+    def solve(self):
+        if self.done_flag: return
+        G = self.sum_buf[:self.ngram].numpy().reshape(self.n, self.n)
+        w, v = np.linalg.eigh(G)
+        s = np.sqrt(np.maximum(w[::-1][:self.sv], 0)); v = v[:, ::-1][:, :self.sv]
+        self.iter += 1
+        self.svp, self.sv = O.rank_logic(s, self.sv, self.mu, self.d)
+        self.P = (v[:, :self.svp] * (1 - 1 / (self.mu * s[:self.svp]))) @ v[:, :self.svp].T
+
+    def shrink(self):
+        if self.done_flag: return
+        self.L = self.W @ self.P
+        G_S = self.D - self.L + self.Y / self.mu
+        self.S = O.prox_flat(G_S, self.lam / self.mu, self.groups)
+        Z = self.D - self.L - self.S
+        self.Y = self.Y + self.mu * Z
+        self.sum_buf[self.ngram:self.ngram + 4] = torch.tensor([float((Z * Z).sum()), float(np.count_nonzero(self.S)), 0.0, 0.0],
+                                                              dtype=torch.float64)
+
+    def finish_iter(self):
+        if self.done_flag: return
+        err = float(np.sqrt(float(self.sum_buf[self.ngram]) / self.normD2))
+        self.log.append((self.iter, self.svp, err))
+        self.mu *= self.rho
+        if err < self.tol: self.done_flag, self.converged = 1, True
+        elif self.iter >= self.max_iter: self.done_flag = 2
+
+    def done(self): return self.done_flag != 0
+    def finalize(self): pass
+
+    def mask_stats(self, phase):
+        if phase == 0:
+            self.max_buf.zero_(); self.max_buf[1] = float(np.abs(self.S).max())
+        else:
+            A = np.abs(self.S)
+            dl = np.abs(self.D - self.L) * (A < 0.5 * float(self.max_buf[1]))
+            pos = dl[dl > 0]
+            self.sum_buf[self.ngram + 4:self.ngram + 8] = torch.tensor([pos.size, pos.sum(), (pos ** 2).sum(), 0.0], dtype=torch.float64)
+
+    def mask_device(self, sigmas=2.0):
+        cnt, s1, s2 = [float(x) for x in self.sum_buf[self.ngram + 4:self.ngram + 7]]
+        mean = s1 / cnt
+        th = mean + sigmas * np.sqrt(max(s2 / cnt - mean * mean, 0.0))
+        return np.abs(self.S) > th
