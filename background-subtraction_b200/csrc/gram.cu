@@ -7,24 +7,25 @@
 // Work decomposition:
 //   * the symmetric output is cut into 32x32 "macro tiles" (bi <= bj); one warp owns one macro tile
 //     = 4x4 DMMA blocks = 32 fp64 accumulators per thread;
-//   * a CTA has 14 MMA warps (14 macro tiles) + 2 producer warps; ceil(ntasks/14) CTA "types" cover
-//     the whole upper triangle, CTAs of different type that share a k-slot walk the same pixel chunks
-//     at the same time so the re-reads hit L2;
+//   * a CTA has 14 MMA warps (14 macro tiles); ceil(ntasks/14) CTA "types" cover the whole upper triangle,
+//     CTAs of different type that share a k-slot walk the same pixel chunks at the same time so the
+//     re-reads hit L2;
+//   * the raw D, S, Y chunks ([frames][kc pixels]) are brought in by TMA (cp.async.bulk.tensor.2d, frames
+//     beyond n zero-filled by the hardware) one whole chunk ahead of the math: ncu r1a showed that two
+//     producer warps with plain loads could not keep the DMMA pipe fed (35 % active);
+//   * all 16 warps combine raw -> W (fp32, padded rows) between two chunks; fragments are widened to fp64 at
+//     load time;
 //   * K (= pixels) is split across k-slots; every CTA writes its partial tile to a scratch buffer and a
 //     second kernel sums the k-slots in a fixed order (deterministic, no atomics).
 #include "common.cuh"
 #include "kernels.h"
+#include "tma.cuh"
 
 namespace bsub {
 
-constexpr int GR_KC = 32;           // pixels per load step (128 B per frame row)
-// The W tile is kept in shared memory as fp64 (converted once by the producer warps): F2F.F64.F32 runs at
-// 1/4 rate, and every fragment is read by up to 14 warps, so converting at fragment-load time made the kernel
-// conversion-bound (ncu r1a: DMMA pipe 35 % active).  Row stride kc+4 doubles = 4 (mod 16): the 16 lanes of a
-// half-warp (r = 0..3, c = 0..3) hit 16 distinct 8-byte banks.
 constexpr int GR_MMA_WARPS = 14;
-constexpr int GR_PROD_WARPS = 2;
-constexpr int GR_THREADS = 32 * (GR_MMA_WARPS + GR_PROD_WARPS);
+constexpr int GR_THREADS = 512;
+constexpr size_t GR_SMEM_CAP = 227 * 1024 - 256;
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -32,9 +33,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 struct GramArgs {
-    const float* D; const float* S; const float* Y;   // S == nullptr -> W = D (init pass)
-    long long ld;
-    int n, npad, ntasks, ntype, gridK, kc, lds;        // kc = pixels per stage (32, 16 or 8), lds = kc + 4
+    int n, npad, ntasks, ntype, gridK, narr, kc, nbox, boxrows;
     long long nchunks;                                  // ld / kc
     const int2* tasks;                                  // (bi, bj), bi <= bj
     const DevState* st;                                 // may be nullptr (stand-alone use)
@@ -42,59 +41,27 @@ struct GramArgs {
     double* partial;                                    // [gridK][ntasks][32*32]
 };
 
-// Fill one stage: rows = frames (zero beyond n), kc pixels each, stored as fp64.
-__device__ __forceinline__ void gram_fill_stage(double* buf, const GramArgs& a, long long chunk, float inv_mu, int tp) {
-    const int qpr = a.kc >> 2;            // float4 slots per row (8, 4 or 2)
-    const int q = tp % qpr;
-    const int r0 = tp / qpr;
-    const int rstep = 64 / qpr;           // rows covered by the 64 producer threads per pass
-    const long long p0 = chunk * a.kc + 4 * q;
-    const bool combo = (a.S != nullptr);
-    for (int f = r0; f < a.npad; f += 4 * rstep) {
-        float4 d[4], s[4], y[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            int ff = f + rstep * u;
-            d[u] = make_float4(0.f, 0.f, 0.f, 0.f); s[u] = d[u]; y[u] = d[u];
-            if (ff < a.n) {
-                long long off = (long long)ff * a.ld + p0;
-                d[u] = ldg4_stream(a.D + off);
-                if (combo) { s[u] = ldg4_stream(a.S + off); y[u] = ldg4_stream(a.Y + off); }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            int ff = f + rstep * u;
-            if (ff < a.npad) {
-                // same fp32 expression as the shrink pass so that both passes see the same W
-                const float wx = (d[u].x - s[u].x) + y[u].x * inv_mu;
-                const float wy = (d[u].y - s[u].y) + y[u].y * inv_mu;
-                const float wz = (d[u].z - s[u].z) + y[u].z * inv_mu;
-                const float ww = (d[u].w - s[u].w) + y[u].w * inv_mu;
-                double* dst = buf + (size_t)ff * a.lds + 4 * q;
-                *reinterpret_cast<double2*>(dst) = make_double2((double)wx, (double)wy);
-                *reinterpret_cast<double2*>(dst + 2) = make_double2((double)wz, (double)ww);
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(GR_THREADS, 1) gram_dmma_kernel(GramArgs a) {
+__global__ void __launch_bounds__(GR_THREADS, 1)
+gram_dmma_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_constant__ CUtensorMap mapS,
+                 const __grid_constant__ CUtensorMap mapY, GramArgs a) {
     if (a.st != nullptr && a.st->done) return;
-    extern __shared__ __align__(16) double gram_smem[];
-    double* bufs[2] = {gram_smem, gram_smem + (size_t)a.npad * a.lds};
+    extern __shared__ __align__(128) unsigned char gram_smem_raw[];
+    const int kc = a.kc, lds = kc + 4;
+    const int rawrows = a.nbox * a.boxrows;
+    float* raw = reinterpret_cast<float*>(gram_smem_raw);                       // [3][rawrows][kc]
+    float* wt = raw + (size_t)3 * rawrows * kc;                                 // [2][npad][lds]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wt + (size_t)2 * a.npad * lds); // full barrier
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int type = blockIdx.x % a.ntype;
     const int kslot = blockIdx.x / a.ntype;
-    const bool producer = warp >= GR_MMA_WARPS;
     const int task = type * GR_MMA_WARPS + warp;
-    const bool has_task = !producer && task < a.ntasks;
+    const bool has_task = warp < GR_MMA_WARPS && task < a.ntasks;
     int bi = 0, bj = 0;
     if (has_task) { int2 t = a.tasks[task]; bi = t.x; bj = t.y; }
     const bool diag = (bi == bj);
     float inv_mu = 0.f;
-    if (a.S != nullptr) inv_mu = (a.st != nullptr) ? (float)(1.0 / a.st->mu) : a.inv_mu_override;
+    if (a.narr == 3) inv_mu = (a.st != nullptr) ? (float)(1.0 / a.st->mu) : a.inv_mu_override;
 
     double acc[4][4][2];
 #pragma unroll
@@ -104,26 +71,69 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_dmma_kernel(GramArgs a) {
 
     long long niter = 0;
     if (kslot < a.nchunks) niter = (a.nchunks - kslot + a.gridK - 1) / a.gridK;
-    const int tp = threadIdx.x - GR_MMA_WARPS * 32;   // producer thread id 0..63
 
-    if (producer && niter > 0) gram_fill_stage(bufs[0], a, kslot, inv_mu, tp);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&mapD);
+        if (a.narr == 3) { tma_prefetch_desc(&mapS); tma_prefetch_desc(&mapY); }
+    }
     __syncthreads();
+
+    const uint32_t tx_bytes = (uint32_t)(a.narr * rawrows * kc * sizeof(float));
+    auto issue = [&](long long chunk) {        // one elected thread
+        mbar_expect_tx(bar, tx_bytes);
+        const int x = (int)(chunk * kc);
+        for (int b = 0; b < a.nbox; ++b) {
+            tma_load_2d(raw + (size_t)(0 * rawrows + b * a.boxrows) * kc, &mapD, bar, x, b * a.boxrows);
+            if (a.narr == 3) {
+                tma_load_2d(raw + (size_t)(1 * rawrows + b * a.boxrows) * kc, &mapS, bar, x, b * a.boxrows);
+                tma_load_2d(raw + (size_t)(2 * rawrows + b * a.boxrows) * kc, &mapY, bar, x, b * a.boxrows);
+            }
+        }
+    };
+    const int qpr = kc >> 2;
+    auto combine = [&](float* dst) {           // all threads: W = (D - S) + Y/mu, rows >= n are zero (TMA OOB fill)
+        const float* rd = raw;
+        const float* rs = raw + (size_t)rawrows * kc;
+        const float* ry = raw + (size_t)2 * rawrows * kc;
+        for (int idx = threadIdx.x; idx < a.npad * qpr; idx += GR_THREADS) {
+            const int row = idx / qpr, q = idx - row * qpr;
+            const float4 d = *reinterpret_cast<const float4*>(rd + (size_t)row * kc + 4 * q);
+            float4 w = d;
+            if (a.narr == 3) {
+                const float4 s = *reinterpret_cast<const float4*>(rs + (size_t)row * kc + 4 * q);
+                const float4 y = *reinterpret_cast<const float4*>(ry + (size_t)row * kc + 4 * q);
+                // same fp32 expression as the shrink pass so that both passes see the same W
+                w.x = (d.x - s.x) + y.x * inv_mu; w.y = (d.y - s.y) + y.y * inv_mu;
+                w.z = (d.z - s.z) + y.z * inv_mu; w.w = (d.w - s.w) + y.w * inv_mu;
+            }
+            *reinterpret_cast<float4*>(dst + (size_t)row * lds + 4 * q) = w;
+        }
+    };
+
+    if (niter > 0) {
+        if (threadIdx.x == 0) issue(kslot);
+        mbar_wait(bar, 0);
+        combine(wt);
+        __syncthreads();
+        if (niter > 1 && threadIdx.x == 0) issue(kslot + a.gridK);
+    }
     const int fr = lane >> 2, fc = lane & 3;
+    const int nks = kc >> 2, rs8 = 8 * lds;
     for (long long it = 0; it < niter; ++it) {
         const int cur = (int)(it & 1);
-        if (producer) {
-            if (it + 1 < niter) gram_fill_stage(bufs[cur ^ 1], a, kslot + (it + 1) * a.gridK, inv_mu, tp);
-        } else if (has_task) {
-            const double* rowA = bufs[cur] + (size_t)(bi * 32 + fr) * a.lds + fc;
-            const double* rowB = bufs[cur] + (size_t)(bj * 32 + fr) * a.lds + fc;
-            const int nks = a.kc >> 2, rs8 = 8 * a.lds;
+        if (has_task) {
+            const float* wb = wt + (size_t)cur * a.npad * lds;
+            const float* rowA = wb + (size_t)(bi * 32 + fr) * lds + fc;
+            const float* rowB = wb + (size_t)(bj * 32 + fr) * lds + fc;
 #pragma unroll 2
             for (int ks = 0; ks < nks; ++ks) {
                 double af[4], bf[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    af[i] = rowA[i * rs8 + ks * 4];
-                    bf[i] = rowB[i * rs8 + ks * 4];
+                    af[i] = (double)rowA[i * rs8 + ks * 4];
+                    bf[i] = (double)rowB[i * rs8 + ks * 4];
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
@@ -132,7 +142,12 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gram_dmma_kernel(GramArgs a) {
                         if (!diag || i <= j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
         }
-        __syncthreads();
+        if (it + 1 < niter) {
+            mbar_wait(bar, (uint32_t)((it + 1) & 1));              // chunk it+1 has landed in raw
+            combine(wt + (size_t)(cur ^ 1) * a.npad * lds);        // wt[cur^1] was last read in iteration it-1
+            __syncthreads();                                       // raw is free, wt[cur^1] is complete
+            if (it + 2 < niter && threadIdx.x == 0) issue(kslot + (it + 2) * a.gridK);
+        }
     }
     if (has_task) {
         double* out = a.partial + ((size_t)kslot * a.ntasks + task) * 1024;
@@ -165,6 +180,10 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partial, const int
 }
 
 // ---------------------------------------------------------------------------------------------------------
+static size_t gram_smem_bytes(int npad, int kc, int nbox, int boxrows) {
+    return (size_t)3 * nbox * boxrows * kc * sizeof(float) + (size_t)2 * npad * (kc + 4) * sizeof(float) + 16;
+}
+
 GramPlan make_gram_plan(int n, long long ld, int num_sms) {
     GramPlan p;
     p.n = n;
@@ -172,44 +191,94 @@ GramPlan make_gram_plan(int n, long long ld, int num_sms) {
     p.nb = p.npad / 32;
     p.ntasks = p.nb * (p.nb + 1) / 2;
     p.ntype = (p.ntasks + GR_MMA_WARPS - 1) / GR_MMA_WARPS;
-    // largest stage width whose two fp64 stages fit in shared memory
-    p.kc = GR_KC;
-    while (p.kc > 8 && (size_t)2 * p.npad * (p.kc + 4) * sizeof(double) > 200 * 1024) p.kc >>= 1;
+    p.nbox = (p.npad + 255) / 256;
+    p.boxrows = (((p.npad + p.nbox - 1) / p.nbox) + 7) / 8 * 8;
+    p.kc = 32;
+    while (p.kc > 8 && gram_smem_bytes(p.npad, p.kc, p.nbox, p.boxrows) > GR_SMEM_CAP) p.kc >>= 1;
     p.nchunks = ld / p.kc;
     long long gk = num_sms / p.ntype;
     if (gk < 1) gk = 1;
     if (gk > p.nchunks) gk = p.nchunks;
     if (gk < 1) gk = 1;
     p.gridK = (int)gk;
-    p.smem_bytes = (size_t)2 * p.npad * (p.kc + 4) * sizeof(double);
+    p.smem_bytes = gram_smem_bytes(p.npad, p.kc, p.nbox, p.boxrows);
     p.partial_elems = (size_t)p.gridK * p.ntasks * 1024;
     return p;
 }
 
 void fill_gram_tasks(const GramPlan& p, int2* host_tasks) {
-    // order tasks so that the macro tiles of one CTA type share frame rows as much as possible
     int t = 0;
     for (int bi = 0; bi < p.nb; ++bi)
         for (int bj = bi; bj < p.nb; ++bj) host_tasks[t++] = make_int2(bi, bj);
 }
 
-int launch_gram(const GramPlan& p, const float* D, const float* S, const float* Y, long long ld,
-                const int2* dev_tasks, const DevState* st, float inv_mu_override, double* partial, double* G,
-                cudaStream_t stream) {
+int make_gram_maps(const GramPlan& p, const float* D, const float* S, const float* Y, long long ld, GramMaps* maps) {
+    const uint64_t dims[2] = {(uint64_t)ld, (uint64_t)p.n};
+    const uint64_t strides[1] = {(uint64_t)ld * sizeof(float)};
+    const uint32_t box[2] = {(uint32_t)p.kc, (uint32_t)p.boxrows};
+    if (make_tensor_map_f32(&maps->D, D, 2, dims, strides, box) != 0) return -1;
+    maps->narr = 1;
+    if (S != nullptr && Y != nullptr) {
+        if (make_tensor_map_f32(&maps->S, S, 2, dims, strides, box) != 0) return -1;
+        if (make_tensor_map_f32(&maps->Y, Y, 2, dims, strides, box) != 0) return -1;
+        maps->narr = 3;
+    } else {
+        maps->S = maps->D; maps->Y = maps->D;
+    }
+    return 0;
+}
+
+int launch_gram(const GramPlan& p, const GramMaps& maps, bool combo, const int2* dev_tasks, const DevState* st,
+                float inv_mu_override, double* partial, double* G, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        BSUB_CUDA_CHECK(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        BSUB_CUDA_CHECK(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM_CAP));
         attr_set = true;
     }
-    if (p.smem_bytes > 200 * 1024) { set_error("gram: n=%d too large for the shared-memory W tile", p.n); return -1; }
+    if (p.smem_bytes > GR_SMEM_CAP) { set_error("gram: n=%d too large for the shared-memory tiles", p.n); return -1; }
+    if (combo && maps.narr != 3) { set_error("gram: S/Y tensor maps missing"); return -1; }
     GramArgs a;
-    a.D = D; a.S = S; a.Y = Y; a.ld = ld; a.n = p.n; a.npad = p.npad; a.ntasks = p.ntasks; a.ntype = p.ntype;
-    a.gridK = p.gridK; a.kc = p.kc; a.lds = p.kc + 4; a.nchunks = p.nchunks; a.tasks = dev_tasks; a.st = st; a.inv_mu_override = inv_mu_override;
-    a.partial = partial;
-    gram_dmma_kernel<<<p.gridK * p.ntype, GR_THREADS, p.smem_bytes, stream>>>(a);
+    a.n = p.n; a.npad = p.npad; a.ntasks = p.ntasks; a.ntype = p.ntype; a.gridK = p.gridK; a.narr = combo ? 3 : 1;
+    a.kc = p.kc; a.nbox = p.nbox; a.boxrows = p.boxrows; a.nchunks = p.nchunks; a.tasks = dev_tasks; a.st = st;
+    a.inv_mu_override = inv_mu_override; a.partial = partial;
+    gram_dmma_kernel<<<p.gridK * p.ntype, GR_THREADS, p.smem_bytes, stream>>>(maps.D, maps.S, maps.Y, a);
     BSUB_CUDA_CHECK(cudaGetLastError());
     gram_reduce_kernel<<<p.ntasks, 256, 0, stream>>>(partial, dev_tasks, p.ntasks, p.gridK, p.npad, G, st);
     BSUB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tensor-map creation through the driver entry point
+typedef CUresult (*PFN_tmap_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box) {
+    static PFN_tmap_encode fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || p == nullptr || qres != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver (%s)", cudaGetErrorString(e));
+            return -1;
+        }
+        fn = reinterpret_cast<PFN_tmap_encode>(p);
+    }
+    cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu box %u,%u,%u", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), (unsigned long long)(rank > 2 ? dims[2] : 0),
+                  box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0);
+        return -1;
+    }
     return 0;
 }
 

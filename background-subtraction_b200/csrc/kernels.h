@@ -1,6 +1,7 @@
 // kernels.h -- host-side launch interfaces of the CUDA kernels (internal; the public boundary is
 // include/bsub_b200.h).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include "common.cuh"
@@ -9,15 +10,17 @@ namespace bsub {
 
 // ---------------------------------------------------------------- gram.cu
 struct GramPlan {
-    int n, npad, nb, ntasks, ntype, gridK, kc;
+    int n, npad, nb, ntasks, ntype, gridK, kc, nbox, boxrows;
     long long nchunks;
     size_t smem_bytes, partial_elems;
 };
+struct GramMaps { CUtensorMap D, S, Y; int narr; };     // TMA descriptors of the [n][ld] float32 matrices
 GramPlan make_gram_plan(int n, long long ld, int num_sms);
 void fill_gram_tasks(const GramPlan& p, int2* host_tasks);
-int launch_gram(const GramPlan& p, const float* D, const float* S, const float* Y, long long ld,
-                const int2* dev_tasks, const DevState* st, float inv_mu_override, double* partial, double* G,
-                cudaStream_t stream);
+int make_gram_maps(const GramPlan& p, const float* D, const float* S, const float* Y, long long ld, GramMaps* maps);
+// combo: W = D - S + Y/mu (needs the S/Y maps); otherwise W = D
+int launch_gram(const GramPlan& p, const GramMaps& maps, bool combo, const int2* dev_tasks, const DevState* st,
+                float inv_mu_override, double* partial, double* G, cudaStream_t stream);
 
 // ---------------------------------------------------------------- eig.cu
 struct EigPlan {

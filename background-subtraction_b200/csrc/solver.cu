@@ -45,7 +45,7 @@ struct bsub_solver {
     HostMirror* mirror_dev = nullptr;
     double* comm_sum = nullptr;         // [npad*npad + kCommTail]
     double* comm_max = nullptr;         // [8]
-    GramPlan gp; int2* tasks_dev = nullptr; double* gram_partial = nullptr;
+    GramPlan gp; GramMaps gmaps; int2* tasks_dev = nullptr; double* gram_partial = nullptr;
     EigPlan ep; EigBuffers eb;
     ShrinkPlan sp; float* tpart = nullptr; double* part_zz = nullptr; unsigned long long* part_nnz = nullptr;
     float* part_max = nullptr;
@@ -142,6 +142,7 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
         if (cudaHostGetDevicePointer((void**)&s->mirror_dev, (void*)s->mirror, 0) != cudaSuccess) { set_error("bsub_create: cudaHostGetDevicePointer failed"); rc = -1; break; }
         // Gram
         s->gp = make_gram_plan(s->n, s->ld, s->num_sms);
+        if (make_gram_maps(s->gp, s->D, s->S, s->Y, s->ld, &s->gmaps) != 0) { rc = -1; break; }
         std::vector<int2> tasks(s->gp.ntasks);
         fill_gram_tasks(s->gp, tasks.data());
         ALLOC(s->tasks_dev, sizeof(int2) * s->gp.ntasks);
@@ -379,7 +380,7 @@ int bsub_step_init_local(bsub_solver* s, void* stream) {
     CK(cudaMemsetAsync(s->comm_max, 0, sizeof(double) * 8, st));
     CK(cudaMemsetAsync(s->comm_sum + (size_t)s->npad * s->npad, 0, sizeof(double) * kCommTail, st));
     RET_IF(launch_rowsum_max(s->D, s->ld, s->m, s->n, s->comm_max, st));
-    RET_IF(launch_gram(s->gp, s->D, nullptr, nullptr, s->ld, s->tasks_dev, nullptr, 0.f, s->gram_partial, s->comm_sum, st));
+    RET_IF(launch_gram(s->gp, s->gmaps, false, s->tasks_dev, nullptr, 0.f, s->gram_partial, s->comm_sum, st));
     s->iters_enqueued = 0;
     s->finalized = false;
     return 0;
@@ -396,7 +397,7 @@ int bsub_step_init_finish(bsub_solver* s, void* stream) {
 
 int bsub_step_gram(bsub_solver* s, void* stream) {
     if (!s || !s->initialised) { set_error("bsub_step_gram: solver not initialised"); return -1; }
-    return launch_gram(s->gp, s->D, s->S, s->Y, s->ld, s->tasks_dev, s->st, 0.f, s->gram_partial, s->comm_sum, as_stream(stream));
+    return launch_gram(s->gp, s->gmaps, true, s->tasks_dev, s->st, 0.f, s->gram_partial, s->comm_sum, as_stream(stream));
 }
 
 int bsub_step_solve(bsub_solver* s, void* stream) {
@@ -706,7 +707,9 @@ int bsub_gram_dev(const float* D, const float* S, const float* Y, int64_t ld, in
     CK(cudaMalloc((void**)&partial, sizeof(double) * gp.partial_elems));
     CK(cudaMalloc((void**)&G, sizeof(double) * (size_t)gp.npad * gp.npad));
     CK(cudaMemcpy(tasks_d, tasks.data(), sizeof(int2) * gp.ntasks, cudaMemcpyHostToDevice));
-    int rc = launch_gram(gp, D, S, Y, ld, tasks_d, nullptr, (float)(S ? 1.0 / mu : 0.0), partial, G, st);
+    GramMaps gm;
+    int rc = make_gram_maps(gp, D, S, Y, ld, &gm);
+    if (rc == 0) rc = launch_gram(gp, gm, S != nullptr, tasks_d, nullptr, (float)(S ? 1.0 / mu : 0.0), partial, G, st);
     if (rc == 0 && cudaMemcpy2DAsync(G_host, sizeof(double) * n, G, sizeof(double) * gp.npad, sizeof(double) * n, n, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("bsub_gram_dev: copy failed"); rc = -1; }
     if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_gram_dev: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
     cudaFree(tasks_d); cudaFree(partial); cudaFree(G);
