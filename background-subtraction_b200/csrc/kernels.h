@@ -67,6 +67,30 @@ struct ShrinkBuffers {
 };
 int launch_shrink(const ShrinkPlan& p, ShrinkBuffers b, const DevState* st, int mode, cudaStream_t stream);
 
+// ---------------------------------------------------------------- shrink_tma.cu (fast path, rows % 4 == 0)
+struct ShrinkTmaPlan {
+    int n, rows, cols, R, P, Cf, nf, KR, grid_clusters, nparts, ntile_r, ntile_c, bufstride, NT, occ;
+    long long ld, ntiles;
+    size_t smem_bytes, tpart_floats;
+};
+struct ShrinkTmaMaps { CUtensorMap D, S, Y, U; bool has_U; };
+bool make_shrink_tma_plan(int n, int rows, int cols, long long ld, int num_sms, int R_hint, int Cf_hint, ShrinkTmaPlan* out);
+int make_shrink_tma_maps(const ShrinkTmaPlan& p, const float* D, float* S, float* Y, float* U, ShrinkTmaMaps* m);
+int launch_shrink_tma(const ShrinkTmaPlan& p, const ShrinkTmaMaps& maps, ShrinkBuffers b, const DevState* st, int mode,
+                      int min_rank, cudaStream_t stream);
+
+// ---------------------------------------------------------------- shrink_stream.cu (fastest path: rank <= 16, rows % 4 == 0)
+struct ShrinkStreamPlan {
+    int n, rows, cols, R, P, FC, NS, NCW, nchunkf, grid, nparts, ntile_r, ntile_c, bufstride;
+    long long ld, ntiles;
+    size_t smem_bytes;
+};
+constexpr int kStreamMaxRank = 16;
+bool make_shrink_stream_plan(int n, int rows, int cols, long long ld, int num_sms, int R_hint, ShrinkStreamPlan* out);
+int make_shrink_stream_maps(const ShrinkStreamPlan& p, const float* D, float* S, float* Y, float* U, ShrinkTmaMaps* m);
+int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, ShrinkBuffers b, const DevState* st, int mode,
+                         cudaStream_t stream);
+
 // ---------------------------------------------------------------- elementwise.cu
 int launch_rowsum_max(const float* D, long long ld, long long m, int n, double* comm_max, cudaStream_t s);
 int launch_init_Y(const float* D, float* Y, float* S, long long ld, int n, const DevState* st, cudaStream_t s);

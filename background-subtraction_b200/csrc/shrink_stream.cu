@@ -1,0 +1,459 @@
+// shrink_stream.cu -- pass B of the ALM iteration as a warp-specialised, TMA-ring streamed kernel (fast path for
+// rank <= 16 and image heights that are a multiple of 4).
+//
+//   T = Vr^T W ; L = VC T ; G_S = D - L + Y/mu ; S = prox(G_S) ; Z = D - L - S ; Y += mu Z ; sum Z^2
+//   (/root/reference/inexact_alm_lsd.py:131-167; prox_flat :71-79 as the closed-form l_inf tile prox)
+//
+// A persistent CTA (one per SM) owns tiles of 3 image columns x R rows x ALL n frames and streams each tile twice
+// through a ring of shared-memory stages (FC frames per stage) filled by 3-D TMA box loads:
+//   phase A  D,S,Y  -> W on the fly -> T accumulated in registers over all frames (one reduction per tile)
+//   phase B  D,Y    -> per 3x3 group and frame: L from T, G_S, prox, dual update, results written in place and sent
+//                      out with TMA box stores (S and Y).  The second read of D,Y hits L2 (a tile's D,Y are
+//                      n*P*8 bytes; 148 tiles in flight ~ 51 MB << 126 MB of L2).
+// Roles: warp 0 lane 0 = loader (TMA loads), warp 1 lane 0 = storer (TMA stores, stage recycling), the remaining
+// warps compute.  All hand-offs are mbarriers (full / done / free per stage); the only CTA-wide barriers are the two
+// named barriers of the per-tile T reduction.  No thread-block clusters, no cross-CTA exchange.
+// HBM traffic: read D,S,Y + write S,Y = 20 B per matrix element (+8 B of L2 re-reads).
+#include <stdlib.h>
+#include <algorithm>
+#include "common.cuh"
+#include "kernels.h"
+#include "tma.cuh"
+
+namespace bsub {
+
+constexpr int SS_KC = 16;                 // largest rank handled by this kernel
+constexpr int SS_KRED = 8;                // singular vectors per round of the per-tile T reduction
+constexpr size_t SS_SMEM_CAP = 227 * 1024 - 256;
+
+struct ShrinkStreamArgs {
+    float* T; const float* Vr; const float* VC; int vstride;
+    long long ld;
+    int n, rows, cols, R, P, NQ, NFL, FC, NS, BS, nchunkf;
+    int ntile_r; long long ntiles;
+    const DevState* st;
+    double* part_zz; unsigned long long* part_nnz; float* part_max;
+    int mode;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+#define SS_CE(i, j) { const float hi_ = fmaxf(u[i], u[j]), lo_ = fminf(u[i], u[j]); u[i] = hi_; u[j] = lo_; }
+// clip level of the l1-ball projection of 9 non-negative values (25-comparator sorting network, descending)
+__device__ __forceinline__ float ss_clip_level9(const float* a_in, float z) {
+    float u[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) u[i] = a_in[i];
+    SS_CE(0, 3) SS_CE(1, 7) SS_CE(2, 5) SS_CE(4, 8)
+    SS_CE(0, 7) SS_CE(2, 4) SS_CE(3, 8) SS_CE(5, 6)
+    SS_CE(0, 2) SS_CE(1, 3) SS_CE(4, 5) SS_CE(7, 8)
+    SS_CE(1, 4) SS_CE(3, 6) SS_CE(5, 7)
+    SS_CE(0, 1) SS_CE(2, 4) SS_CE(3, 5) SS_CE(6, 8)
+    SS_CE(2, 3) SS_CE(4, 5) SS_CE(6, 7)
+    SS_CE(1, 2) SS_CE(3, 4) SS_CE(5, 6)
+    const float inv[9] = {1.f, 0.5f, 1.f / 3.f, 0.25f, 0.2f, 1.f / 6.f, 1.f / 7.f, 0.125f, 1.f / 9.f};
+    float cs = 0.f, theta = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        cs += u[k];
+        const float t = (cs - z) * inv[k];
+        if (u[k] > t) theta = t;
+    }
+    return theta;
+}
+
+// phase A, one stage: T partial of this thread's pixel quad over its frames of the stage
+template <int KCNT>
+__device__ __forceinline__ void ss_accumulate(float (&acc)[SS_KC][4], const float* bD, const float* bS, const float* bY,
+                                              const float* Vr_s, int P, int qd, int fl, int NFL, int FC, int fbase, int n,
+                                              float inv_mu) {
+    for (int f = fl; f < FC; f += NFL) {
+        const int fg = fbase + f;
+        if (fg >= n) break;
+        const float4 d4 = *reinterpret_cast<const float4*>(bD + (size_t)f * P + 4 * qd);
+        const float4 s4 = *reinterpret_cast<const float4*>(bS + (size_t)f * P + 4 * qd);
+        const float4 y4 = *reinterpret_cast<const float4*>(bY + (size_t)f * P + 4 * qd);
+        float4 w;
+        w.x = (d4.x - s4.x) + y4.x * inv_mu; w.y = (d4.y - s4.y) + y4.y * inv_mu;
+        w.z = (d4.z - s4.z) + y4.z * inv_mu; w.w = (d4.w - s4.w) + y4.w * inv_mu;
+        const float* vrow = Vr_s + (size_t)fg * SS_KC;
+        float vv[SS_KC];
+#pragma unroll
+        for (int k4 = 0; k4 < (KCNT + 3) / 4; ++k4) {
+            const float4 v = *reinterpret_cast<const float4*>(vrow + 4 * k4);
+            vv[4 * k4] = v.x; vv[4 * k4 + 1] = v.y; vv[4 * k4 + 2] = v.z; vv[4 * k4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < KCNT; ++k) {
+            acc[k][0] = fmaf(vv[k], w.x, acc[k][0]); acc[k][1] = fmaf(vv[k], w.y, acc[k][1]);
+            acc[k][2] = fmaf(vv[k], w.z, acc[k][2]); acc[k][3] = fmaf(vv[k], w.w, acc[k][3]);
+        }
+    }
+}
+
+// phase B, one 3x3 group of one frame: L from T, prox, dual update, in place in the stage
+template <int KCNT>
+__device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg, const float* vc, int R, int P, float inv_mu,
+                                         float mu_f, float lamq, int mode, double& zz_acc, unsigned int& nnz_acc, float& max_acc) {
+    float vv[SS_KC];
+#pragma unroll
+    for (int k4 = 0; k4 < (KCNT + 3) / 4; ++k4) {
+        const float4 v = *reinterpret_cast<const float4*>(vc + 4 * k4);
+        vv[4 * k4] = v.x; vv[4 * k4 + 1] = v.y; vv[4 * k4 + 2] = v.z; vv[4 * k4 + 3] = v.w;
+    }
+    float av[9], yv[9], x[9], ax[9];
+    float sabs = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int dr = 0; dr < 3; ++dr) {
+            const int e = c * 3 + dr, o = c * R + dr;
+            float l = 0.f;
+#pragma unroll
+            for (int k = 0; k < KCNT; ++k) l = fmaf(vv[k], Tg[(size_t)k * P + o], l);
+            av[e] = dsp[o] - l;                           // a = D - L
+            yv[e] = ysp[o];
+            x[e] = fmaf(yv[e], inv_mu, av[e]);            // G_S
+            ax[e] = fabsf(x[e]);
+            sabs += ax[e];
+        }
+    float zl = 0.f;
+    if (mode == SHRINK_FLAT3) {
+        if (!(sabs > lamq)) {                             // whole tile inside the l1 ball: S = 0, Z = D - L
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int dr = 0; dr < 3; ++dr) {
+                    const int e = c * 3 + dr, o = c * R + dr;
+                    dsp[o] = 0.f;
+                    ysp[o] = fmaf(mu_f, av[e], yv[e]);
+                    zl = fmaf(av[e], av[e], zl);
+                }
+        } else {
+            const float theta = ss_clip_level9(ax, lamq);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int dr = 0; dr < 3; ++dr) {
+                    const int e = c * 3 + dr, o = c * R + dr;
+                    const float sv = copysignf(fminf(ax[e], theta), x[e]);
+                    const float z = av[e] - sv;            // Z = D - L - S
+                    dsp[o] = sv;
+                    ysp[o] = fmaf(mu_f, z, yv[e]);         // Y += mu Z
+                    zl = fmaf(z, z, zl);
+                    nnz_acc += (sv != 0.f);
+                    max_acc = fmaxf(max_acc, fabsf(sv));
+                }
+        }
+        zz_acc += (double)zl;
+    } else if (mode == SHRINK_L1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dr = 0; dr < 3; ++dr) {
+                const int e = c * 3 + dr, o = c * R + dr;
+                const float sv = copysignf(fmaxf(ax[e] - lamq, 0.f), x[e]);
+                const float z = av[e] - sv;
+                dsp[o] = sv;
+                ysp[o] = fmaf(mu_f, z, yv[e]);
+                zl = fmaf(z, z, zl);
+                nnz_acc += (sv != 0.f);
+                max_acc = fmaxf(max_acc, fabsf(sv));
+            }
+        zz_acc += (double)zl;
+    } else {                                              // SHRINK_SPILL: hand G_S to a separate prox
+#pragma unroll
+        for (int e = 0; e < 9; ++e) dsp[(e / 3) * R + (e % 3)] = x[e];
+    }
+}
+
+#define SS_DISPATCH_K(kcnt, CALL)                         \
+    switch (kcnt) {                                       \
+        case 0: { constexpr int K_ = 0; CALL; } break;    \
+        case 1: { constexpr int K_ = 1; CALL; } break;    \
+        case 2: { constexpr int K_ = 2; CALL; } break;    \
+        case 3: { constexpr int K_ = 3; CALL; } break;    \
+        case 4: { constexpr int K_ = 4; CALL; } break;    \
+        case 5: { constexpr int K_ = 5; CALL; } break;    \
+        case 6: { constexpr int K_ = 6; CALL; } break;    \
+        case 7: { constexpr int K_ = 7; CALL; } break;    \
+        case 8: { constexpr int K_ = 8; CALL; } break;    \
+        case 9: case 10: { constexpr int K_ = 10; CALL; } break;  \
+        case 11: case 12: { constexpr int K_ = 12; CALL; } break; \
+        default: { constexpr int K_ = 16; CALL; } break;  \
+    }
+
+template <int NCW>      // number of consumer warps; block = 32 * (NCW + 2)
+__global__ void __launch_bounds__(32 * (NCW + 2), 1)
+shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_constant__ CUtensorMap mapS,
+                     const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapOut, ShrinkStreamArgs a) {
+    constexpr int NTC = 32 * NCW;
+    const DevState* st = a.st;
+    if (st->done) return;
+    const int r = st->svp;
+    if (r > SS_KC) {                                       // large ranks take the fallback kernel launched next
+        if (threadIdx.x == 0) { a.part_zz[blockIdx.x] = 0.0; a.part_nnz[blockIdx.x] = 0ull; a.part_max[blockIdx.x] = 0.f; }
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int P = a.P, NQ = a.NQ, NFL = a.NFL, R = a.R, FC = a.FC, NS = a.NS;
+    const double mu_d = st->mu;
+    const float inv_mu = (float)(1.0 / mu_d), mu_f = (float)mu_d;
+    const float lamq = (float)(st->lambda / mu_d);
+
+    extern __shared__ __align__(128) unsigned char ss_smem_raw[];
+    const size_t stage_floats = (size_t)3 * a.BS;
+    float* ring = reinterpret_cast<float*>(ss_smem_raw);            // [NS][3][BS]
+    float* scr = ring + (size_t)NS * stage_floats;                  // [NFL][SS_KRED][P]   (T reduction)
+    float* Tp = scr + (size_t)NFL * SS_KRED * P;                    // [SS_KC][P]
+    float* Vr_s = Tp + (size_t)SS_KC * P;                           // [n][SS_KC]
+    float* VC_s = Vr_s + (size_t)a.n * SS_KC;                       // [n][SS_KC]
+    uint64_t* full = reinterpret_cast<uint64_t*>(VC_s + (size_t)a.n * SS_KC);   // [NS]
+    uint64_t* done = full + NS;                                     // [NS]
+    uint64_t* freeb = done + NS;                                    // [NS]
+    __shared__ double redd[32];
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], NCW); mbar_init(&freeb[s], 1); }
+        mbar_fence_init();
+        tma_prefetch_desc(&mapD); tma_prefetch_desc(&mapS); tma_prefetch_desc(&mapY); tma_prefetch_desc(&mapOut);
+    }
+    for (int idx = threadIdx.x; idx < a.n * SS_KC; idx += blockDim.x) {
+        const int f = idx / SS_KC, k = idx - f * SS_KC;
+        const bool ok = k < r;
+        Vr_s[idx] = ok ? a.Vr[(size_t)f * a.vstride + k] : 0.f;
+        VC_s[idx] = ok ? a.VC[(size_t)f * a.vstride + k] : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < SS_KC * P; idx += blockDim.x) Tp[idx] = 0.f;   // rows >= svp stay zero
+    __syncthreads();
+
+    auto tile_origin = [&](long long tl, int& j0, int& i0) {
+        const int tcx = (int)(tl / a.ntile_r), trx = (int)(tl - (long long)tcx * a.ntile_r);
+        j0 = 3 * tcx; i0 = trx * R;
+    };
+    const int ncf = a.nchunkf;                              // frame chunks per tile
+    const bool phaseA = r > 0;                              // rank 0: L = 0, no T needed
+    const int chunks_per_tile = (phaseA ? ncf : 0) + ncf;
+
+    double zz_acc = 0.0;
+    unsigned int nnz_acc = 0u;
+    float max_acc = 0.f;
+
+    if (warp == 0) {
+        // ===================== loader =====================
+        if (lane == 0) {
+            long long q = 0;
+            for (long long tl = blockIdx.x; tl < a.ntiles; tl += gridDim.x) {
+                int j0, i0;
+                tile_origin(tl, j0, i0);
+                for (int c = 0; c < chunks_per_tile; ++c, ++q) {
+                    const int s = (int)(q % NS);
+                    const long long u = q / NS;
+                    if (u > 0) mbar_wait(&freeb[s], (uint32_t)((u - 1) & 1));
+                    float* b = ring + (size_t)s * stage_floats;
+                    const bool isA = phaseA && c < ncf;
+                    const int fbase = (isA ? c : c - (phaseA ? ncf : 0)) * FC;
+                    mbar_expect_tx(&full[s], (uint32_t)((isA ? 3 : 2) * (size_t)FC * P * sizeof(float)));
+                    tma_load_3d(b, &mapD, &full[s], i0, j0, fbase);
+                    tma_load_3d(b + (size_t)2 * a.BS, &mapY, &full[s], i0, j0, fbase);
+                    if (isA) tma_load_3d(b + (size_t)a.BS, &mapS, &full[s], i0, j0, fbase);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== storer: TMA stores of finished phase-B stages, stage recycling =====================
+        if (lane == 0) {
+            long long q = 0;
+            for (long long tl = blockIdx.x; tl < a.ntiles; tl += gridDim.x) {
+                int j0, i0;
+                tile_origin(tl, j0, i0);
+                for (int c = 0; c < chunks_per_tile; ++c, ++q) {
+                    const int s = (int)(q % NS);
+                    const long long u = q / NS;
+                    mbar_wait(&done[s], (uint32_t)(u & 1));
+                    const bool isA = phaseA && c < ncf;
+                    if (!isA) {
+                        float* b = ring + (size_t)s * stage_floats;
+                        const int fbase = (c - (phaseA ? ncf : 0)) * FC;
+                        tma_store_3d(&mapOut, b, i0, j0, fbase);                                   // S_new (or G_S)
+                        if (a.mode != SHRINK_SPILL) tma_store_3d(&mapY, b + (size_t)2 * a.BS, i0, j0, fbase);
+                        tma_store_commit();
+                        tma_store_wait_read<0>();                                                  // stage may be overwritten
+                    }
+                    mbar_arrive(&freeb[s]);
+                }
+            }
+            tma_store_wait_all<0>();
+        }
+        __syncwarp();
+    } else {
+        // ===================== consumers =====================
+        const int ct = threadIdx.x - 64;                    // consumer thread id 0..NTC-1
+        const int qd = ct % NQ, fl = ct / NQ;
+        const bool tact = fl < NFL;
+        const int NG = R / 3, RQ = R / 4;
+        long long q = 0;
+        for (long long tl = blockIdx.x; tl < a.ntiles; tl += gridDim.x) {
+            int j0, i0;
+            tile_origin(tl, j0, i0);
+            if (phaseA) {
+                float acc[SS_KC][4];
+#pragma unroll
+                for (int k = 0; k < SS_KC; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
+                for (int c = 0; c < ncf; ++c, ++q) {
+                    const int s = (int)(q % NS);
+                    const long long u = q / NS;
+                    mbar_wait(&full[s], (uint32_t)(u & 1));
+                    const float* b = ring + (size_t)s * stage_floats;
+                    if (tact) { SS_DISPATCH_K(r, (ss_accumulate<K_>(acc, b, b + a.BS, b + 2 * a.BS, Vr_s, P, qd, fl, NFL, FC, c * FC, a.n, inv_mu))); }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&done[s]);
+                }
+                // one reduction per tile over the NFL frame lanes (SS_KRED vectors per round)
+                for (int kr0 = 0; kr0 < r; kr0 += SS_KRED) {
+                    if (tact) {
+#pragma unroll
+                        for (int k = 0; k < SS_KC; ++k)
+                            if (k >= kr0 && k < kr0 + SS_KRED && k < r)
+                                *reinterpret_cast<float4*>(scr + ((size_t)(fl * SS_KRED + (k - kr0))) * P + 4 * qd) =
+                                    make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+                    }
+                    named_bar_sync(1, NTC);
+                    const int kend = min(SS_KRED, r - kr0);
+                    for (int idx = ct; idx < kend * NQ; idx += NTC) {
+                        const int k = idx / NQ, qq = idx - k * NQ;
+                        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int l = 0; l < NFL; ++l) {
+                            const float4 v = *reinterpret_cast<const float4*>(scr + ((size_t)(l * SS_KRED + k)) * P + 4 * qq);
+                            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+                        }
+                        *reinterpret_cast<float4*>(Tp + (size_t)(kr0 + k) * P + 4 * qq) = sum;
+                        // keep T for the final materialisation of L (rows % 4 == 0 on this path)
+                        const int c2 = qq / RQ, i2 = (qq - c2 * RQ) * 4;
+                        const int j2 = j0 + c2, row2 = i0 + i2;
+                        if (j2 < a.cols && row2 < a.rows) stg4(a.T + (size_t)(kr0 + k) * a.ld + (long long)j2 * a.rows + row2, sum);
+                    }
+                    named_bar_sync(1, NTC);
+                }
+            }
+            // phase B
+            for (int c = 0; c < ncf; ++c, ++q) {
+                const int s = (int)(q % NS);
+                const long long u = q / NS;
+                mbar_wait(&full[s], (uint32_t)(u & 1));
+                float* b = ring + (size_t)s * stage_floats;
+                const int fbase = c * FC;
+                for (int itx = ct; itx < FC * NG; itx += NTC) {
+                    const int f = itx / NG, g = itx - f * NG;
+                    const int fg = fbase + f;
+                    if (fg >= a.n) continue;
+                    float* dsp = b + (size_t)f * P + 3 * g;
+                    float* ysp = b + (size_t)2 * a.BS + (size_t)f * P + 3 * g;
+                    SS_DISPATCH_K(r, (ss_group<K_>(dsp, ysp, Tp + 3 * g, VC_s + (size_t)fg * SS_KC, R, P, inv_mu, mu_f, lamq, a.mode,
+                                                   zz_acc, nnz_acc, max_acc)));
+                }
+                fence_proxy_async_smem();                   // my writes -> visible to the storer's TMA stores
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&done[s]);
+            }
+        }
+    }
+    __syncthreads();
+    double zt = block_sum(zz_acc, redd);
+    if (threadIdx.x == 0) a.part_zz[blockIdx.x] = zt;
+    double nt = block_sum((double)nnz_acc, redd);
+    if (threadIdx.x == 0) a.part_nnz[blockIdx.x] = (unsigned long long)(nt + 0.5);
+    double mt = block_max((double)max_acc, redd);
+    if (threadIdx.x == 0) a.part_max[blockIdx.x] = (float)mt;
+}
+
+// -------------------------------------------------------------------------------------------------------------
+static size_t ss_smem_bytes(int n, int R, int FC, int NS, int NTC) {
+    const int P = 3 * R, NQ = P / 4, NFL = NTC / NQ;
+    const size_t bs = ((size_t)FC * P + 31) / 32 * 32;
+    size_t fl = (size_t)NS * 3 * bs + (size_t)NFL * SS_KRED * P + (size_t)SS_KC * P + (size_t)2 * n * SS_KC;
+    return fl * sizeof(float) + (size_t)3 * NS * sizeof(uint64_t) + 64;
+}
+
+bool make_shrink_stream_plan(int n, int rows, int cols, long long ld, int num_sms, int R_hint, ShrinkStreamPlan* out) {
+    if (rows % 4 != 0 || rows < 12) return false;
+    ShrinkStreamPlan p;
+    p.n = n; p.rows = rows; p.cols = cols; p.ld = ld;
+    const char* env_w = getenv("BSUB_STREAM_WARPS");
+    const char* env_ns = getenv("BSUB_STREAM_STAGES");
+    const char* env_fc = getenv("BSUB_STREAM_FC");
+    int NCW = env_w ? atoi(env_w) : 8;
+    if (NCW != 16) NCW = 8;
+    const int NTC = 32 * NCW;
+    int R = R_hint > 0 ? ((R_hint + 11) / 12) * 12 : 48;
+    const int rows12 = ((rows + 11) / 12) * 12;
+    R = std::min(std::min(R, rows12), 252);
+    for (; R >= 12; R -= 12) {
+        const int NQ = 3 * R / 4;
+        if (NQ > NTC) continue;
+        const int NFL = NTC / NQ;
+        int FC = env_fc ? atoi(env_fc) : 2 * NFL;
+        FC = std::max(1, std::min(FC, std::min(n, 256)));
+        int NS = env_ns ? atoi(env_ns) : 6;
+        while (NS >= 3 && ss_smem_bytes(n, R, FC, NS, NTC) > SS_SMEM_CAP) --NS;
+        if (NS < 3) continue;
+        p.R = R; p.P = 3 * R; p.FC = FC; p.NS = NS; p.NCW = NCW;
+        p.bufstride = (int)(((size_t)FC * p.P + 31) / 32 * 32);
+        p.smem_bytes = ss_smem_bytes(n, R, FC, NS, NTC);
+        p.nchunkf = (n + FC - 1) / FC;
+        p.ntile_r = (rows + R - 1) / R;
+        p.ntile_c = (cols + 2) / 3;
+        p.ntiles = (long long)p.ntile_r * p.ntile_c;
+        p.grid = (int)std::min<long long>(num_sms, p.ntiles);
+        p.nparts = p.grid;
+        *out = p;
+        return true;
+    }
+    return false;
+}
+
+int make_shrink_stream_maps(const ShrinkStreamPlan& p, const float* D, float* S, float* Y, float* U, ShrinkTmaMaps* m) {
+    const uint64_t dims[3] = {(uint64_t)p.rows, (uint64_t)p.cols, (uint64_t)p.n};
+    const uint64_t strides[2] = {(uint64_t)p.rows * sizeof(float), (uint64_t)p.ld * sizeof(float)};
+    const uint32_t box[3] = {(uint32_t)p.R, 3u, (uint32_t)p.FC};
+    if (make_tensor_map_f32(&m->D, D, 3, dims, strides, box) != 0) return -1;
+    if (make_tensor_map_f32(&m->S, S, 3, dims, strides, box) != 0) return -1;
+    if (make_tensor_map_f32(&m->Y, Y, 3, dims, strides, box) != 0) return -1;
+    m->has_U = false;
+    if (U != nullptr) { if (make_tensor_map_f32(&m->U, U, 3, dims, strides, box) != 0) return -1; m->has_U = true; }
+    else m->U = m->S;
+    return 0;
+}
+
+template <int NCW>
+static int launch_ss(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, const ShrinkStreamArgs& a, int mode, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        BSUB_CUDA_CHECK(cudaFuncSetAttribute(shrink_stream_kernel<NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM_CAP));
+        attr_set = true;
+    }
+    const CUtensorMap& outmap = (mode == SHRINK_SPILL) ? maps.U : maps.S;
+    shrink_stream_kernel<NCW><<<p.grid, 32 * (NCW + 2), p.smem_bytes, stream>>>(maps.D, maps.S, maps.Y, outmap, a);
+    BSUB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, ShrinkBuffers b, const DevState* st, int mode,
+                         cudaStream_t stream) {
+    if (mode == SHRINK_SPILL && !maps.has_U) { set_error("shrink_stream: spill buffer map missing"); return -1; }
+    ShrinkStreamArgs a;
+    a.T = b.T; a.Vr = b.Vr; a.VC = b.VC; a.vstride = b.vstride; a.ld = p.ld; a.n = p.n; a.rows = p.rows; a.cols = p.cols;
+    a.R = p.R; a.P = p.P; a.NQ = p.P / 4; a.NFL = (32 * p.NCW) / a.NQ; a.FC = p.FC; a.NS = p.NS; a.BS = p.bufstride;
+    a.nchunkf = p.nchunkf; a.ntile_r = p.ntile_r; a.ntiles = p.ntiles; a.st = st; a.part_zz = b.part_zz; a.part_nnz = b.part_nnz;
+    a.part_max = b.part_max; a.mode = mode;
+    if (p.NCW == 16) return launch_ss<16>(p, maps, a, mode, stream);
+    return launch_ss<8>(p, maps, a, mode, stream);
+}
+
+}  // namespace bsub

@@ -8,6 +8,7 @@
 // host only limits how far ahead it enqueues by watching a mapped status word.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include <algorithm>
@@ -47,7 +48,9 @@ struct bsub_solver {
     double* comm_max = nullptr;         // [8]
     GramPlan gp; GramMaps gmaps; int2* tasks_dev = nullptr; double* gram_partial = nullptr;
     EigPlan ep; EigBuffers eb;
-    ShrinkPlan sp; float* tpart = nullptr; double* part_zz = nullptr; unsigned long long* part_nnz = nullptr;
+    ShrinkPlan sp; ShrinkTmaPlan stp; ShrinkTmaMaps stmaps; bool use_tma = false, stmaps_ready = false;
+    ShrinkStreamPlan ssp; ShrinkTmaMaps ssmaps; bool use_stream = false;
+    float* tpart = nullptr; double* part_zz = nullptr; unsigned long long* part_nnz = nullptr;
     float* part_max = nullptr;
     int shrink_mode = SHRINK_FLAT3;
     // generic flat groups
@@ -168,8 +171,12 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
                 if (s->m % r == 0) { rows = r; cols = (int)(s->m / r); break; }
         }
         s->sp = make_shrink_plan(s->n, rows, cols, s->ld, s->num_sms, cfg->tile_rows, cfg->cluster_frames);
-        ALLOC(s->tpart, sizeof(float) * s->sp.tpart_floats);
-        int nparts = std::max(s->sp.nparts, s->num_sms * 8);
+        s->use_tma = (getenv("BSUB_NO_TMA") == nullptr) &&
+                     make_shrink_tma_plan(s->n, rows, cols, s->ld, s->num_sms, cfg->tile_rows, cfg->cluster_frames, &s->stp);
+        s->use_stream = s->use_tma && (getenv("BSUB_NO_STREAM") == nullptr) &&
+                        make_shrink_stream_plan(s->n, rows, cols, s->ld, s->num_sms, cfg->tile_rows, &s->ssp);
+        ALLOC(s->tpart, sizeof(float) * std::max(s->sp.tpart_floats, s->use_tma ? s->stp.tpart_floats : (size_t)0));
+        int nparts = std::max(std::max(s->sp.nparts, (s->use_tma ? s->stp.nparts : 0) + (s->use_stream ? s->ssp.nparts : 0)), s->num_sms * 8);
         ALLOC(s->part_zz, sizeof(double) * nparts); ALLOC(s->part_nnz, sizeof(unsigned long long) * nparts);
         ALLOC(s->part_max, sizeof(float) * nparts);
         cudaMemset(s->part_zz, 0, sizeof(double) * nparts); cudaMemset(s->part_nnz, 0, sizeof(unsigned long long) * nparts);
@@ -227,6 +234,7 @@ int bsub_set_flat_groups(bsub_solver* s, const int32_t* g) {
     CK(cudaMemcpy(s->gidx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
     s->ngroups = gmax;
     s->shrink_mode = SHRINK_SPILL;
+    s->stmaps_ready = false;
     const size_t mat = sizeof(float) * (size_t)s->ld * s->n;
     if (!s->U) { CK(cudaMalloc((void**)&s->U, mat)); CK(cudaMemset(s->U, 0, mat)); }
     if (!s->L) { CK(cudaMalloc((void**)&s->L, mat)); CK(cudaMemset(s->L, 0, mat)); }
@@ -411,8 +419,25 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
     ShrinkBuffers b;
     b.D = s->D; b.S = s->S; b.Y = s->Y; b.T = s->T; b.U = s->U; b.tpart = s->tpart; b.Vr = s->eb.Vr; b.VC = s->eb.VC;
     b.vstride = s->eb.vstride; b.part_zz = s->part_zz; b.part_nnz = s->part_nnz; b.part_max = s->part_max; b.part_wmax = nullptr;
-    RET_IF(launch_shrink(s->sp, b, s->st, s->shrink_mode, st));
     int nparts = s->sp.nparts;
+    if (s->use_tma) {
+        if (!s->stmaps_ready) {
+            RET_IF(make_shrink_tma_maps(s->stp, s->D, s->S, s->Y, s->U, &s->stmaps));
+            if (s->use_stream) RET_IF(make_shrink_stream_maps(s->ssp, s->D, s->S, s->Y, s->U, &s->ssmaps));
+            s->stmaps_ready = true;
+        }
+        int off = 0, min_rank = 0;
+        if (s->use_stream) {          // rank <= 16: streamed kernel; larger ranks fall through to the cluster kernel
+            RET_IF(launch_shrink_stream(s->ssp, s->ssmaps, b, s->st, s->shrink_mode, st));
+            off = s->ssp.nparts; min_rank = kStreamMaxRank + 1;
+        }
+        ShrinkBuffers b2 = b;
+        b2.part_zz += off; b2.part_nnz += off; b2.part_max += off;
+        RET_IF(launch_shrink_tma(s->stp, s->stmaps, b2, s->st, s->shrink_mode, min_rank, st));
+        nparts = off + s->stp.nparts;
+    } else {
+        RET_IF(launch_shrink(s->sp, b, s->st, s->shrink_mode, st));
+    }
     if (s->shrink_mode == SHRINK_SPILL) {
         // two-phase: U = G_S -> prox -> S_new (written over S) -> dual update
         if (s->cfg.prox == BSUB_PROX_FLAT_LINF) {
