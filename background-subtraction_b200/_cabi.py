@@ -83,6 +83,7 @@ SIGNATURES = {
                                              ctypes.c_double, ctypes.c_double, vp]),
     "bsub_gram_dev": (ctypes.c_int, [vp, vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, c_double_p, vp]),
     "bsub_eig_topk": (ctypes.c_int, [c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p, c_double_p]),
+    "bsub_gram_i8_test": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int64, vp]),
 }
 
 _lib = None

@@ -39,6 +39,13 @@ struct DevState {
     int max_iter, round005d, d, use_sv_prediction, break_on_rank0;
     int eig_info;           // diagnostics of the eigen solver (bisection rounds etc.)
     long long eig_clk[8];   // clock64() at the phase boundaries of the last eig_kernel (CTA 0)
+    // int8 (tcgen05) Gram path: W of the NEXT iteration is written by the shrink pass as 32-bit fixed point
+    double wq_scale;        // S: q = rint(W * 2^31 / S), power of two
+    double wq_scale_next;   // S for the slices the coming shrink pass writes
+    double wmax;            // max |W| seen by the last shrink pass (over the W it produced)
+    int gram_mode;          // 0: fp64 DMMA Gram from D,S,Y   1: int8 tcgen05 Gram from the slices
+    int wq_saturated;       // the last shrink pass clipped a slice -> fall back to the DMMA Gram once
+    int use_i8;             // configuration: int8 path enabled
 };
 
 struct IterLog {

@@ -18,6 +18,7 @@
 //      Vr and VC = Vr * diag(1 - 1/(mu sigma)) written in fp32 for the shrink pass.
 #include <cooperative_groups.h>
 #include <float.h>
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -40,7 +41,7 @@ struct EigArgs {
     double* ee;                // [n]
     double* pbuf;              // [2][n]
     double* dotbuf;            // [2][16]
-    double* iw;                // inverse-iteration workspace [6][n][kcap]
+    size_t iw_smem_doubles;    // shared-memory doubles available to the inverse-iteration workspace (aliases zs)
     double* lam;               // [n]
     double* Z;                 // [n][n]
     float* Vr; float* VC; int vstride;
@@ -49,15 +50,24 @@ struct EigArgs {
 
 __device__ __forceinline__ double ldcg_d(const double* p) { return __ldcg(p); }
 
-// number of eigenvalues of the tridiagonal (d, e2 = e^2) that are < x   (LAPACK dlaebz-style pivmin guard)
+// number of eigenvalues of the tridiagonal (d, e2 = e^2) that are < x: sign changes of the Sturm sequence
+//   p_0 = 1, p_1 = d_0 - x, p_i = (d_{i-1} - x) p_{i-1} - e2_{i-2} p_{i-2}
+// evaluated in product form (one DFMA on the critical path per step instead of a division) with power-of-two
+// rescaling; an exact zero is given the sign opposite to its predecessor (the pivmin rule of LAPACK dlaebz).
 __device__ __forceinline__ int sturm_negcount(const double* d, const double* e2, int n, double x, double pivmin) {
-    double q = d[0] - x;
-    if (fabs(q) < pivmin) q = -pivmin;
-    int c = (q < 0.0);
+    (void)pivmin;
+    double pm = 1.0, p = d[0] - x;
+    if (p == 0.0) p = -1e-300;
+    int c = (p < 0.0);
     for (int i = 1; i < n; ++i) {
-        q = d[i] - x - e2[i - 1] / q;
-        if (fabs(q) < pivmin) q = -pivmin;
-        c += (q < 0.0);
+        const double t = e2[i - 1] * pm;
+        double pn = fma(d[i] - x, p, -t);
+        if (pn == 0.0) pn = -p * 0x1p-200;
+        c += ((pn < 0.0) != (p < 0.0));
+        pm = p; p = pn;
+        const double ap = fabs(p);
+        if (ap > 0x1p200) { p *= 0x1p-400; pm *= 0x1p-400; }
+        else if (ap < 0x1p-200) { p *= 0x1p400; pm *= 0x1p400; }
     }
     return c;
 }
@@ -248,62 +258,72 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
     if (tid == 0) st->eig_clk[2] = clock64();
 
     // ---- 3. eigenvectors of the tridiagonal matrix: inverse iteration, one thread per vector ---------------------
-    const int kcap = a.kcap;
-    for (int k = tid; k < K; k += EIG_THREADS) {
-        double lamk = a.lam[k];
-        double* Up = a.iw + (size_t)0 * n * kcap + k;
-        double* Uq = a.iw + (size_t)1 * n * kcap + k;
-        double* Ur = a.iw + (size_t)2 * n * kcap + k;
-        double* Mm = a.iw + (size_t)3 * n * kcap + k;
-        double* Sw = a.iw + (size_t)4 * n * kcap + k;
-        double* Bz = a.iw + (size_t)5 * n * kcap + k;
-        const double ptol = fmax(DBL_EPSILON * tnorm, pivmin);
-        // factor T - lam I = P L U  (partial pivoting; U has two super-diagonals)
-        double p = d_s[0] - lamk, q = (n > 1) ? e_s[0] : 0.0, rr = 0.0;
-        for (int i = 0; i + 1 < n; ++i) {
-            const double sub = e_s[i];
-            const double an = d_s[i + 1] - lamk;
-            const double en = (i + 2 < n) ? e_s[i + 1] : 0.0;
-            if (fabs(p) >= fabs(sub)) {
-                if (fabs(p) < ptol) p = copysign(ptol, p);
-                const double mlt = sub / p;
-                Up[(size_t)i * kcap] = p; Uq[(size_t)i * kcap] = q; Ur[(size_t)i * kcap] = rr;
-                Mm[(size_t)i * kcap] = mlt; Sw[(size_t)i * kcap] = 0.0;
-                p = an - mlt * q; q = en - mlt * rr; rr = 0.0;
-            } else {
-                const double mlt = p / sub;
-                Up[(size_t)i * kcap] = sub; Uq[(size_t)i * kcap] = an; Ur[(size_t)i * kcap] = en;
-                Mm[(size_t)i * kcap] = mlt; Sw[(size_t)i * kcap] = 1.0;
-                p = q - mlt * an; q = rr - mlt * en; rr = 0.0;
-            }
-        }
-        if (fabs(p) < ptol) p = copysign(ptol, p);
-        Up[(size_t)(n - 1) * kcap] = p; Uq[(size_t)(n - 1) * kcap] = 0.0; Ur[(size_t)(n - 1) * kcap] = 0.0;
-        for (int i = 0; i < n; ++i) Bz[(size_t)i * kcap] = hash_unit((unsigned)i, (unsigned)k);
-        for (int itn = 0; itn < 3; ++itn) {
-            // forward: apply P L^{-1}
+    // The six work arrays of a vector live in shared memory ([array][i][slot], slot fastest -> conflict-free), so the
+    // sequential recurrences run at shared-memory latency; vectors are processed in batches of `kbcap`.
+    double* iw_s = zs;                                   // aliases the back-transformation scratch (later phase)
+    const int kbcap = max(1, min(EIG_THREADS, (int)(a.iw_smem_doubles / ((size_t)6 * n))));
+    for (int kb0 = 0; kb0 < K; kb0 += kbcap) {
+        const int k = kb0 + tid;
+        if (tid < kbcap && k < K) {
+            const double lamk = a.lam[k];
+            double* Up = iw_s + (size_t)0 * n * kbcap + tid;
+            double* Uq = iw_s + (size_t)1 * n * kbcap + tid;
+            double* Ur = iw_s + (size_t)2 * n * kbcap + tid;
+            double* Mm = iw_s + (size_t)3 * n * kbcap + tid;
+            double* Sw = iw_s + (size_t)4 * n * kbcap + tid;
+            double* Bz = iw_s + (size_t)5 * n * kbcap + tid;
+            const double ptol = fmax(DBL_EPSILON * tnorm, pivmin);
+            // factor T - lam I = P L U  (partial pivoting; U has two super-diagonals)
+            double p = d_s[0] - lamk, q = (n > 1) ? e_s[0] : 0.0, rr = 0.0;
             for (int i = 0; i + 1 < n; ++i) {
-                double bi = Bz[(size_t)i * kcap], bn = Bz[(size_t)(i + 1) * kcap];
-                if (Sw[(size_t)i * kcap] != 0.0) { double t = bi; bi = bn; bn = t; }
-                bn -= Mm[(size_t)i * kcap] * bi;
-                Bz[(size_t)i * kcap] = bi; Bz[(size_t)(i + 1) * kcap] = bn;
+                const double sub = e_s[i];
+                const double an = d_s[i + 1] - lamk;
+                const double en = (i + 2 < n) ? e_s[i + 1] : 0.0;
+                if (fabs(p) >= fabs(sub)) {
+                    if (fabs(p) < ptol) p = copysign(ptol, p);
+                    const double mlt = sub / p;
+                    Up[(size_t)i * kbcap] = p; Uq[(size_t)i * kbcap] = q; Ur[(size_t)i * kbcap] = rr;
+                    Mm[(size_t)i * kbcap] = mlt; Sw[(size_t)i * kbcap] = 0.0;
+                    p = an - mlt * q; q = en - mlt * rr; rr = 0.0;
+                } else {
+                    const double mlt = p / sub;
+                    Up[(size_t)i * kbcap] = sub; Uq[(size_t)i * kbcap] = an; Ur[(size_t)i * kbcap] = en;
+                    Mm[(size_t)i * kbcap] = mlt; Sw[(size_t)i * kbcap] = 1.0;
+                    p = q - mlt * an; q = rr - mlt * en; rr = 0.0;
+                }
             }
-            // backward: solve U z = b
-            double z1 = 0.0, z2 = 0.0, zmax = 0.0;
-            for (int i = n - 1; i >= 0; --i) {
-                double z = (Bz[(size_t)i * kcap] - Uq[(size_t)i * kcap] * z1 - Ur[(size_t)i * kcap] * z2) / Up[(size_t)i * kcap];
-                Bz[(size_t)i * kcap] = z;
-                z2 = z1; z1 = z;
-                zmax = fmax(zmax, fabs(z));
+            if (fabs(p) < ptol) p = copysign(ptol, p);
+            Up[(size_t)(n - 1) * kbcap] = p; Uq[(size_t)(n - 1) * kbcap] = 0.0; Ur[(size_t)(n - 1) * kbcap] = 0.0;
+            for (int i = 0; i < n; ++i) Bz[(size_t)i * kbcap] = hash_unit((unsigned)i, (unsigned)k);
+            for (int itn = 0; itn < 3; ++itn) {
+                // forward: apply P L^{-1}
+                double bi = Bz[0];
+                for (int i = 0; i + 1 < n; ++i) {
+                    double bn = Bz[(size_t)(i + 1) * kbcap];
+                    if (Sw[(size_t)i * kbcap] != 0.0) { double t = bi; bi = bn; bn = t; }
+                    bn -= Mm[(size_t)i * kbcap] * bi;
+                    Bz[(size_t)i * kbcap] = bi;
+                    bi = bn;
+                }
+                Bz[(size_t)(n - 1) * kbcap] = bi;
+                // backward: solve U z = b
+                double z1 = 0.0, z2 = 0.0, zmax = 0.0;
+                for (int i = n - 1; i >= 0; --i) {
+                    double z = (Bz[(size_t)i * kbcap] - Uq[(size_t)i * kbcap] * z1 - Ur[(size_t)i * kbcap] * z2) / Up[(size_t)i * kbcap];
+                    Bz[(size_t)i * kbcap] = z;
+                    z2 = z1; z1 = z;
+                    zmax = fmax(zmax, fabs(z));
+                }
+                const double sc = (zmax > 0.0) ? 1.0 / zmax : 1.0;
+                for (int i = 0; i < n; ++i) Bz[(size_t)i * kbcap] *= sc;
             }
-            const double sc = (zmax > 0.0) ? 1.0 / zmax : 1.0;
-            for (int i = 0; i < n; ++i) Bz[(size_t)i * kcap] *= sc;
+            double nn = 0.0;
+            for (int i = 0; i < n; ++i) { double z = Bz[(size_t)i * kbcap]; nn += z * z; }
+            const double sc = 1.0 / sqrt(nn);
+            double* zrow = a.Z + (size_t)k * n;
+            for (int i = 0; i < n; ++i) zrow[i] = Bz[(size_t)i * kbcap] * sc;
         }
-        double nn = 0.0;
-        for (int i = 0; i < n; ++i) { double z = Bz[(size_t)i * kcap]; nn += z * z; }
-        const double sc = 1.0 / sqrt(nn);
-        double* zrow = a.Z + (size_t)k * n;
-        for (int i = 0; i < n; ++i) zrow[i] = Bz[(size_t)i * kcap] * sc;
+        __syncthreads();
     }
     __threadfence_block();
     __syncthreads();
@@ -353,6 +373,12 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
 
     if (tid == 0) st->eig_clk[4] = clock64();
     // ---- 4. back-transformation z <- H_0 H_1 ... H_{n-3} z, one warp per vector ---------------------------------
+    // tau is staged in shared memory and the next reflector row is prefetched into registers while the current one
+    // is applied, so the chain of n dependent steps does not pay an L2 round trip per step.
+    double* tau_s = d_s;                                  // d_s / e_s / e2_s are dead now
+    for (int i = tid; i < n; i += EIG_THREADS) tau_s[i] = a.tau[i];
+    __syncthreads();
+    constexpr int VHR = 20;                               // register prefetch covers n <= 32 * VHR
     for (int kb = 0; kb < K; kb += EIG_BT) {
         const int k = kb + warp;
         if (warp < EIG_BT && k < K) {
@@ -360,15 +386,44 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
             const double* zrow = a.Z + (size_t)k * n;
             for (int i = lane; i < n; i += 32) z[i] = zrow[i];
             __syncwarp();
-            for (int j = n - 3; j >= 0; --j) {
-                const double tau = a.tau[j];
-                if (tau == 0.0) continue;
-                const double* vh = a.Vh + (size_t)j * n;
-                double s = 0.0;
-                for (int i = j + 1 + lane; i < n; i += 32) s += vh[i] * z[i];
-                s = warp_sum(s) * tau;
-                for (int i = j + 1 + lane; i < n; i += 32) z[i] -= s * vh[i];
-                __syncwarp();
+            if (n <= 32 * VHR) {
+                double vcur[VHR], vnxt[VHR];
+                {
+                    const int j = n - 3;
+                    const double* vh = a.Vh + (size_t)(j < 0 ? 0 : j) * n;
+#pragma unroll
+                    for (int t = 0; t < VHR; ++t) { const int i = j + 1 + lane + 32 * t; vcur[t] = (j >= 0 && i < n) ? vh[i] : 0.0; }
+                }
+                for (int j = n - 3; j >= 0; --j) {
+                    if (j > 0) {
+                        const double* vh = a.Vh + (size_t)(j - 1) * n;
+#pragma unroll
+                        for (int t = 0; t < VHR; ++t) { const int i = j + lane + 32 * t; vnxt[t] = (i < n) ? vh[i] : 0.0; }
+                    }
+                    const double tau = tau_s[j];
+                    if (tau != 0.0) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int t = 0; t < VHR; ++t) { const int i = j + 1 + lane + 32 * t; if (i < n) s = fma(vcur[t], z[i], s); }
+                        s = warp_sum(s) * tau;
+#pragma unroll
+                        for (int t = 0; t < VHR; ++t) { const int i = j + 1 + lane + 32 * t; if (i < n) z[i] -= s * vcur[t]; }
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int t = 0; t < VHR; ++t) vcur[t] = vnxt[t];
+                }
+            } else {
+                for (int j = n - 3; j >= 0; --j) {
+                    const double tau = tau_s[j];
+                    if (tau == 0.0) continue;
+                    const double* vh = a.Vh + (size_t)j * n;
+                    double s = 0.0;
+                    for (int i = j + 1 + lane; i < n; i += 32) s += vh[i] * z[i];
+                    s = warp_sum(s) * tau;
+                    for (int i = j + 1 + lane; i < n; i += 32) z[i] -= s * vh[i];
+                    __syncwarp();
+                }
             }
             double* zout = a.Z + (size_t)k * n;
             for (int i = lane; i < n; i += 32) zout[i] = z[i];
@@ -452,10 +507,10 @@ EigPlan make_eig_plan(int n, int npad) {
     if (bytes_for(C, true) > cap) p.in_smem = 0;
     p.C = C;
     p.rows_per = (n + C - 1) / C;
-    p.smem_bytes = bytes_for(C, p.in_smem != 0);
+    p.smem_bytes = std::max(bytes_for(C, p.in_smem != 0), cap);      // CTA 0 uses the slack for the inverse iteration
     p.kcap = n;
     // workspace: Aglob + Vh + tau + dd + ee + pbuf + dotbuf + iw
-    p.work_doubles = (size_t)C * p.rows_per * n + (size_t)n * n + 3 * (size_t)n + 2 * (size_t)n + 32 + (size_t)6 * n * p.kcap;
+    p.work_doubles = (size_t)C * p.rows_per * n + (size_t)n * n + 3 * (size_t)n + 2 * (size_t)n + 32;
     return p;
 }
 
@@ -479,7 +534,7 @@ int launch_eig(const EigPlan& p, const double* G, const double* comm_max, EigBuf
     a.ee = w;    w += p.n;
     a.pbuf = w;  w += 2 * (size_t)p.n;
     a.dotbuf = w; w += 32;
-    a.iw = w;
+    a.iw_smem_doubles = (p.smem_bytes / sizeof(double)) - (2 * (size_t)p.n + 64) - (3 * (size_t)p.n + 4 * EIG_THREADS + EIG_THREADS / 2);
     a.lam = b.lam; a.Z = b.Z; a.Vr = b.Vr; a.VC = b.VC; a.vstride = b.vstride; a.st = st;
 
     cudaLaunchConfig_t cfg = {};

@@ -254,8 +254,23 @@ typedef CUresult (*PFN_tmap_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static int make_tensor_map_any(CUtensorMap* map, const void* base, CUtensorMapDataType dtype, int rank, const uint64_t* dims,
+                               const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz);
+
 int make_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                         const uint32_t* box) {
+    return make_tensor_map_any(map, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+int make_tensor_map_u8(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, int swizzle_bytes) {
+    const CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B :
+                                   swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    return make_tensor_map_any(map, base, CU_TENSOR_MAP_DATA_TYPE_UINT8, rank, dims, strides_bytes, box, swz);
+}
+
+static int make_tensor_map_any(CUtensorMap* map, const void* base, CUtensorMapDataType dtype, int rank, const uint64_t* dims,
+                               const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
     static PFN_tmap_encode fn = nullptr;
     if (fn == nullptr) {
         void* p = nullptr;
@@ -270,8 +285,8 @@ int make_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint
     cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bx[5]; cuuint32_t es[5];
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    CUresult r = fn(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu box %u,%u,%u", (int)r, rank,

@@ -1,0 +1,298 @@
+// gram_i8.cu -- the frames x frames Gram on the 5th-generation tensor cores (tcgen05, sm_100a), exact in integers.
+//
+// W (fp32) is written by the shrink pass as 32-bit fixed point q = rint(W * 2^31 / S) split into four balanced base-256
+// digits (int8 "slices" d0..d3, q = sum d_k 256^k).  Then
+//     q_f . q_g = sum_{i,j} 256^{i+j} (d_i(f) . d_j(g))
+// and every slice-pair product is an int8 GEMM with exact int32 accumulation (tcgen05.mma.kind::i8, accumulators in
+// TMEM).  Pairs of equal weight i+j share one TMEM accumulator ("class"); classes 3..6 are kept (the dropped ones sit
+// below 2^-32 of the top class), i.e. 10 MMAs per 32-pixel k-step.  Accumulators are flushed to a global int64 matrix
+// with atomics before int32 could overflow -- integer adds commute, so the result is exact AND deterministic.
+// This replaces the fp64 DMMA Gram (gram.cu, FP64-pipe bound at ~6.4 ms for 1080p x 300) wherever the slices exist.
+//
+// Kernel anatomy (one CTA = one 128 x N output tile of the upper block triangle x a range of pixels):
+//   warp 0     TMA producer: K-major SWIZZLE_64B boxes {64 B pixels, 128 frames} of the A block and the B block (4 slices)
+//   warp 1     MMA issuer (one elected thread): tcgen05.mma, tcgen05.commit -> mbarriers
+//   warp 2     TMEM allocator (512 columns = 4 classes x 128)
+//   warps 4-7  epilogue: tcgen05.ld of the four class accumulators, recombination into int64, atomicAdd to global
+#include <algorithm>
+#include <vector>
+#include "common.cuh"
+#include "kernels.h"
+#include "tma.cuh"
+
+namespace bsub {
+
+constexpr int GI_THREADS = 256;
+constexpr int GI_KB = 64;                 // pixels (bytes) per K block = one SWIZZLE_64B row
+constexpr int GI_STAGES = 3;
+constexpr int GI_FLUSH_KB = 448;          // K blocks between flushes: 4 pairs * 448*64 px * 2^14 < 2^31
+constexpr int GI_TILE_BYTES = 128 * GI_KB;            // one slice of one 128-frame block
+constexpr int GI_STAGE_BYTES = 8 * GI_TILE_BYTES;     // A (4 slices) + B (4 slices)
+
+struct GramI8Args {
+    int n, nblk;
+    const int4* cta_info;                 // per CTA: (bi, bj, kb_begin, kb_end)
+    const int* blk_n;                     // MMA N of each frame block (multiple of 16, <= 128)
+    unsigned long long* Gint;             // [nblk*128][nblk*128] int64 accumulators (zeroed by the caller)
+    const DevState* st;
+    int require_mode;                     // kernel is a no-op unless st->gram_mode == require_mode (when st != nullptr)
+};
+
+__device__ __forceinline__ void gi_mbar_wait(uint64_t* bar, uint32_t parity) {
+    unsigned long long spins = 0;
+    while (!mbar_try_wait(bar, parity)) { if (++spins > (1ull << 31)) __trap(); }     // watchdog: never hang the GPU
+}
+__device__ __forceinline__ void gi_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint64_t gi_smem_desc(uint32_t saddr) {
+    // K-major, SWIZZLE_64B: rows of 64 B, 8-row groups 512 B apart (SBO), LBO = 1 (ignored for swizzled K-major),
+    // descriptor version 1 (Blackwell), layout type 4 = SWIZZLE_64B
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t gi_instr_desc(int N) {
+    // kind::i8: c_format S32 (2) at [4,6); a_format / b_format signed 8-bit (1) at [7,10) / [10,13); K-major A and B;
+    // n_dim = N >> 3 at [17,23); m_dim = 128 >> 4 at [24,29)
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void gi_mma(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void gi_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void gi_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+
+__global__ void __launch_bounds__(GI_THREADS, 1)
+gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8Args a) {
+    if (a.st != nullptr && (a.st->done || a.st->gram_mode != a.require_mode)) return;
+    extern __shared__ __align__(1024) unsigned char gi_smem[];
+    unsigned char* stages = gi_smem;                                             // [GI_STAGES][8][128][64]
+    uint64_t* full = reinterpret_cast<uint64_t*>(gi_smem + (size_t)GI_STAGES * GI_STAGE_BYTES);   // [GI_STAGES]
+    uint64_t* empty = full + GI_STAGES;                                          // [GI_STAGES]
+    uint64_t* tmem_full = empty + GI_STAGES;                                     // accumulators ready for the epilogue
+    uint64_t* tmem_empty = tmem_full + 1;                                        // accumulators drained
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int4 info = a.cta_info[blockIdx.x];
+    const int bi = info.x, bj = info.y, kb0 = info.z, kb1 = info.w;
+    const bool diag = (bi == bj);
+    const int Nj = a.blk_n[bj];
+    const int nkb = kb1 - kb0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GI_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 128);
+        mbar_fence_init();
+        tma_prefetch_desc(&mapQ);
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint32_t tx = (uint32_t)((diag ? 4 : 8) * GI_TILE_BYTES);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % GI_STAGES;
+                const int u = kb / GI_STAGES;
+                if (u > 0) gi_mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));
+                unsigned char* base = stages + (size_t)s * GI_STAGE_BYTES;
+                mbar_expect_tx(&full[s], tx);
+                const int x = (kb0 + kb) * GI_KB;
+                for (int sl = 0; sl < 4; ++sl) {
+                    tma_load_3d(base + (size_t)sl * GI_TILE_BYTES, &mapQ, &full[s], x, bi * 128, sl);
+                    if (!diag) tma_load_3d(base + (size_t)(4 + sl) * GI_TILE_BYTES, &mapQ, &full[s], x, bj * 128, sl);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = gi_instr_desc(Nj);
+            int since_flush = 0, nflush = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % GI_STAGES;
+                const int u = kb / GI_STAGES;
+                if (since_flush == 0 && nflush > 0) {
+                    gi_mbar_wait(tmem_empty, (uint32_t)((nflush - 1) & 1));          // epilogue has drained TMEM
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                gi_mbar_wait(&full[s], (uint32_t)(u & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sbase = smem_u32(stages + (size_t)s * GI_STAGE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < GI_KB / 32; ++ks) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int cls = i + j - 3;
+                            if (cls < 0) continue;
+                            const uint64_t da = gi_smem_desc(sbase + (uint32_t)(i * GI_TILE_BYTES) + ks * 32);
+                            const uint64_t db = gi_smem_desc(sbase + (uint32_t)(((diag ? 0 : 4) + j) * GI_TILE_BYTES) + ks * 32);
+                            // first pair of a class right after a flush overwrites the accumulator
+                            const bool first = (since_flush == 0 && ks == 0 && j == 3);   // (i, 3) is the first pair of class i
+                            gi_mma(tmem_base + (uint32_t)(cls * 128), da, db, idesc, first ? 0u : 1u);
+                        }
+                }
+                gi_commit(&empty[s]);                                            // smem stage reusable when these MMAs finish
+                ++since_flush;
+                if (since_flush == GI_FLUSH_KB || kb == nkb - 1) {
+                    gi_commit(tmem_full);                                        // accumulators complete -> epilogue
+                    since_flush = 0; ++nflush;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;                                                 // TMEM lanes 32*ew .. 32*ew+31
+        const int nflush_total = (nkb + GI_FLUSH_KB - 1) / GI_FLUSH_KB;
+        const int row = bi * 128 + ew * 32 + lane;
+        const size_t ldg = (size_t)a.nblk * 128;
+        for (int fl = 0; fl < nflush_total; ++fl) {
+            gi_mbar_wait(tmem_full, (uint32_t)(fl & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int c0 = 0; c0 < Nj; c0 += 16) {
+                uint32_t v3[16], v4[16], v5[16], v6[16];
+                const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0;
+                gi_tmem_ld16(ta + 0 * 128, v3);
+                gi_tmem_ld16(ta + 1 * 128, v4);
+                gi_tmem_ld16(ta + 2 * 128, v5);
+                gi_tmem_ld16(ta + 3 * 128, v6);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < a.n) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int col = bj * 128 + c0 + e;
+                        if (col < a.n) {
+                            const long long val = (long long)(int)v3[e] + ((long long)(int)v4[e] << 8) + ((long long)(int)v5[e] << 16) +
+                                                  ((long long)(int)v6[e] << 24);
+                            if (val != 0) atomicAdd(a.Gint + (size_t)row * ldg + col, (unsigned long long)val);
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            gi_mbar_arrive(tmem_empty);
+        }
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// G[i][j] (double, [npad][npad], symmetric) = Gint * scale   with  scale = S^2 * 2^-38
+__global__ void gram_i8_finish_kernel(const unsigned long long* __restrict__ Gint, int nblk, int n, int npad, double* __restrict__ G,
+                                      const DevState* st, double scale_override, int require_mode) {
+    if (st != nullptr && (st->done || st->gram_mode != require_mode)) return;
+    const double scale = (st != nullptr) ? st->wq_scale * st->wq_scale * 0x1p-38 : scale_override;
+    const size_t ldg = (size_t)nblk * 128;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < npad * npad; idx += gridDim.x * blockDim.x) {
+        const int i = idx / npad, j = idx - i * npad;
+        double v = 0.0;
+        if (i < n && j < n) {
+            const int r = (i / 128 <= j / 128) ? i : j, c = (i / 128 <= j / 128) ? j : i;     // upper block triangle holds the data
+            v = (double)(long long)Gint[(size_t)r * ldg + c] * scale;
+        }
+        G[idx] = v;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+GramI8Plan make_gram_i8_plan(int n, long long ldq, int num_sms) {
+    GramI8Plan p;
+    p.n = n; p.ldq = ldq;
+    p.nblk = (n + 127) / 128;
+    p.nkb = (int)(ldq / GI_KB);
+    p.smem_bytes = (size_t)GI_STAGES * GI_STAGE_BYTES + 256 + 1024;
+    p.grid = num_sms;
+    return p;
+}
+
+void fill_gram_i8_tables(const GramI8Plan& p, std::vector<int4>& cta_info, std::vector<int>& blk_n) {
+    blk_n.assign(p.nblk, 128);
+    const int last = p.n - (p.nblk - 1) * 128;
+    blk_n[p.nblk - 1] = std::min(128, ((last + 15) / 16) * 16);
+    // CTAs per output tile proportional to its MMA cost (N of the column block); every tile gets at least one
+    std::vector<std::pair<int, int>> tiles;
+    std::vector<double> w;
+    double wsum = 0.0;
+    for (int bi = 0; bi < p.nblk; ++bi)
+        for (int bj = bi; bj < p.nblk; ++bj) { tiles.push_back({bi, bj}); w.push_back(blk_n[bj]); wsum += blk_n[bj]; }
+    std::vector<int> cnt(tiles.size(), 1);
+    int left = p.grid - (int)tiles.size();
+    if (left < 0) left = 0;
+    // largest-remainder apportionment
+    std::vector<double> want(tiles.size());
+    int given = 0;
+    for (size_t t = 0; t < tiles.size(); ++t) { want[t] = w[t] / wsum * left; cnt[t] += (int)want[t]; given += (int)want[t]; }
+    while (given < left) {
+        size_t best = 0; double br = -1.0;
+        for (size_t t = 0; t < tiles.size(); ++t) { double r = want[t] - (int)want[t]; if (r > br) { br = r; best = t; } }
+        cnt[best]++; want[best] = (int)want[best]; ++given;
+    }
+    cta_info.clear();
+    for (size_t t = 0; t < tiles.size(); ++t) {
+        const int c = std::min(cnt[t], std::max(1, p.nkb));
+        for (int k = 0; k < c; ++k) {
+            const int kb0 = (int)((long long)p.nkb * k / c), kb1 = (int)((long long)p.nkb * (k + 1) / c);
+            if (kb1 > kb0) cta_info.push_back(make_int4(tiles[t].first, tiles[t].second, kb0, kb1));
+        }
+    }
+}
+
+int make_gram_i8_map(const GramI8Plan& p, const signed char* Wq, CUtensorMap* map) {
+    // u8 tensor {ldq bytes, n frames, 4 slices}; K-major SWIZZLE_64B boxes {64, 128, 1}; frames beyond n read as zero
+    const uint64_t dims[3] = {(uint64_t)p.ldq, (uint64_t)p.n, 4};
+    const uint64_t strides[2] = {(uint64_t)p.ldq, (uint64_t)p.ldq * (uint64_t)p.n};
+    const uint32_t box[3] = {GI_KB, 128, 1};
+    return make_tensor_map_u8(map, Wq, 3, dims, strides, box, 64);
+}
+
+int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const int4* cta_info_dev, int ncta, const int* blk_n_dev,
+                   unsigned long long* Gint, double* G, int npad, const DevState* st, double scale_override, int require_mode,
+                   cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        BSUB_CUDA_CHECK(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
+        attr_set = true;
+    }
+    const size_t gbytes = sizeof(unsigned long long) * (size_t)p.nblk * 128 * p.nblk * 128;
+    BSUB_CUDA_CHECK(cudaMemsetAsync(Gint, 0, gbytes, stream));
+    GramI8Args a;
+    a.n = p.n; a.nblk = p.nblk; a.cta_info = cta_info_dev; a.blk_n = blk_n_dev; a.Gint = Gint; a.st = st; a.require_mode = require_mode;
+    gram_i8_kernel<<<ncta, GI_THREADS, p.smem_bytes, stream>>>(map, a);
+    BSUB_CUDA_CHECK(cudaGetLastError());
+    gram_i8_finish_kernel<<<64, 256, 0, stream>>>(Gint, p.nblk, p.n, npad, G, st, scale_override, require_mode);
+    BSUB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace bsub

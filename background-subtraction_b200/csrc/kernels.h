@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <vector>
 #include "common.cuh"
 
 namespace bsub {
@@ -21,6 +22,15 @@ int make_gram_maps(const GramPlan& p, const float* D, const float* S, const floa
 // combo: W = D - S + Y/mu (needs the S/Y maps); otherwise W = D
 int launch_gram(const GramPlan& p, const GramMaps& maps, bool combo, const int2* dev_tasks, const DevState* st,
                 float inv_mu_override, double* partial, double* G, cudaStream_t stream);
+
+// ---------------------------------------------------------------- gram_i8.cu (tcgen05 int8 Gram from the W slices)
+struct GramI8Plan { int n, nblk, nkb, grid; long long ldq; size_t smem_bytes; };
+GramI8Plan make_gram_i8_plan(int n, long long ldq, int num_sms);
+void fill_gram_i8_tables(const GramI8Plan& p, std::vector<int4>& cta_info, std::vector<int>& blk_n);
+int make_gram_i8_map(const GramI8Plan& p, const signed char* Wq, CUtensorMap* map);
+int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const int4* cta_info_dev, int ncta, const int* blk_n_dev,
+                   unsigned long long* Gint, double* G, int npad, const DevState* st, double scale_override, int require_mode,
+                   cudaStream_t stream);
 
 // ---------------------------------------------------------------- eig.cu
 struct EigPlan {

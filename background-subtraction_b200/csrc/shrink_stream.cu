@@ -247,6 +247,8 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
     if (warp == 0) {
         // ===================== loader =====================
         if (lane == 0) {
+            // D and Y of a tile are read again in phase B: keep them in L2; everything else is streamed once
+            const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
             long long q = 0;
             for (long long tl = blockIdx.x; tl < a.ntiles; tl += gridDim.x) {
                 int j0, i0;
@@ -259,9 +261,10 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                     const bool isA = phaseA && c < ncf;
                     const int fbase = (isA ? c : c - (phaseA ? ncf : 0)) * FC;
                     mbar_expect_tx(&full[s], (uint32_t)((isA ? 3 : 2) * (size_t)FC * P * sizeof(float)));
-                    tma_load_3d(b, &mapD, &full[s], i0, j0, fbase);
-                    tma_load_3d(b + (size_t)2 * a.BS, &mapY, &full[s], i0, j0, fbase);
-                    if (isA) tma_load_3d(b + (size_t)a.BS, &mapS, &full[s], i0, j0, fbase);
+                    const uint64_t pol = (isA && phaseA) ? pol_keep : pol_stream;
+                    tma_load_3d_hint(b, &mapD, &full[s], i0, j0, fbase, pol);
+                    tma_load_3d_hint(b + (size_t)2 * a.BS, &mapY, &full[s], i0, j0, fbase, pol);
+                    if (isA) tma_load_3d_hint(b + (size_t)a.BS, &mapS, &full[s], i0, j0, fbase, pol_stream);
                 }
             }
         }
@@ -269,6 +272,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
     } else if (warp == 1) {
         // ===================== storer: TMA stores of finished phase-B stages, stage recycling =====================
         if (lane == 0) {
+            const uint64_t pol_stream = l2_policy_evict_first();
             long long q = 0;
             for (long long tl = blockIdx.x; tl < a.ntiles; tl += gridDim.x) {
                 int j0, i0;
@@ -281,8 +285,8 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                     if (!isA) {
                         float* b = ring + (size_t)s * stage_floats;
                         const int fbase = (c - (phaseA ? ncf : 0)) * FC;
-                        tma_store_3d(&mapOut, b, i0, j0, fbase);                                   // S_new (or G_S)
-                        if (a.mode != SHRINK_SPILL) tma_store_3d(&mapY, b + (size_t)2 * a.BS, i0, j0, fbase);
+                        tma_store_3d_hint(&mapOut, b, i0, j0, fbase, pol_stream);                  // S_new (or G_S)
+                        if (a.mode != SHRINK_SPILL) tma_store_3d_hint(&mapY, b + (size_t)2 * a.BS, i0, j0, fbase, pol_stream);
                         tma_store_commit();
                         tma_store_wait_read<0>();                                                  // stage may be overwritten
                     }
@@ -398,7 +402,7 @@ bool make_shrink_stream_plan(int n, int rows, int cols, long long ld, int num_sm
         const int NQ = 3 * R / 4;
         if (NQ > NTC) continue;
         const int NFL = NTC / NQ;
-        int FC = env_fc ? atoi(env_fc) : 2 * NFL;
+        int FC = env_fc ? atoi(env_fc) : 4 * NFL;
         FC = std::max(1, std::min(FC, std::min(n, 256)));
         int NS = env_ns ? atoi(env_ns) : 6;
         while (NS >= 3 && ss_smem_bytes(n, R, FC, NS, NTC) > SS_SMEM_CAP) --NS;

@@ -741,6 +741,44 @@ int bsub_gram_dev(const float* D, const float* S, const float* Y, int64_t ld, in
     return rc;
 }
 
+int bsub_gram_i8_test(const int8_t* slices_host, int32_t n, int64_t ldq, int64_t* G_host) {
+    // slices_host: int8 [4][n][ldq] (ldq a multiple of 64); G_host: int64 [n][n] = sum over pixels and slice pairs (i + j >= 3)
+    // of 256^(i+j-3) d_i(f) d_j(g)  -- exact integers; exercises the tcgen05 kernel on its own
+    if (!slices_host || !G_host || n <= 0 || ldq <= 0 || (ldq % 64) != 0) { set_error("bsub_gram_i8_test: bad argument"); return -1; }
+    int dev = 0, sms = 148;
+    CK(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    GramI8Plan gp = make_gram_i8_plan(n, ldq, sms);
+    std::vector<int4> info; std::vector<int> blkn;
+    fill_gram_i8_tables(gp, info, blkn);
+    signed char* q = nullptr; int4* info_d = nullptr; int* blkn_d = nullptr; unsigned long long* Gint = nullptr; double* G = nullptr;
+    const size_t qbytes = (size_t)4 * n * ldq, gn = (size_t)gp.nblk * 128;
+    const int npad = ((n + 31) / 32) * 32;
+    CK(cudaMalloc((void**)&q, qbytes));
+    CK(cudaMalloc((void**)&info_d, sizeof(int4) * info.size()));
+    CK(cudaMalloc((void**)&blkn_d, sizeof(int) * blkn.size()));
+    CK(cudaMalloc((void**)&Gint, sizeof(unsigned long long) * gn * gn));
+    CK(cudaMalloc((void**)&G, sizeof(double) * (size_t)npad * npad));
+    CK(cudaMemcpy(q, slices_host, qbytes, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(info_d, info.data(), sizeof(int4) * info.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(blkn_d, blkn.data(), sizeof(int) * blkn.size(), cudaMemcpyHostToDevice));
+    CUtensorMap map;
+    int rc = make_gram_i8_map(gp, q, &map);
+    if (rc == 0) rc = launch_gram_i8(gp, map, info_d, (int)info.size(), blkn_d, Gint, G, npad, nullptr, 1.0, 1, 0);
+    if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) { set_error("bsub_gram_i8_test: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    if (rc == 0) {
+        std::vector<long long> tmp(gn * gn);
+        cudaMemcpy(tmp.data(), Gint, sizeof(long long) * gn * gn, cudaMemcpyDeviceToHost);
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                const int r = (i / 128 <= j / 128) ? i : j, c = (i / 128 <= j / 128) ? j : i;
+                G_host[(size_t)i * n + j] = tmp[(size_t)r * gn + c];
+            }
+    }
+    cudaFree(q); cudaFree(info_d); cudaFree(blkn_d); cudaFree(Gint); cudaFree(G);
+    return rc;
+}
+
 int bsub_eig_topk(const double* G_host, int32_t n, int32_t k, double* lam_host, double* vec_host) {
     if (!G_host || n <= 0 || k <= 0 || k > n || !lam_host) { set_error("bsub_eig_topk: bad argument"); return -1; }
     const int npad = ((n + 31) / 32) * 32;

@@ -154,6 +154,8 @@ int bsub_gram_dev(const float* D, const float* S, const float* Y, int64_t ld, in
 /* top-k eigenpairs of a symmetric double[n][n] host matrix: svd_k_largest's n x n core (utils.py:204-212).
  * lam_host double[k] descending, vec_host double[k][n] (row i = eigenvector i). */
 int bsub_eig_topk(const double* G_host, int32_t n, int32_t k, double* lam_host, double* vec_host);
+/* the tcgen05 int8 Gram on its own: slices int8[4][n][ldq] (host), G int64[n][n] = sum_p sum_{i+j>=3} 256^(i+j-3) d_i(f,p) d_j(g,p) */
+int bsub_gram_i8_test(const int8_t* slices_host, int32_t n, int64_t ldq, int64_t* G_host);
 
 #ifdef __cplusplus
 }

@@ -152,3 +152,21 @@ def test_svd_k_largest(B):
     s_ref = np.linalg.svd(A, compute_uv=False)[:6]
     assert np.abs(s - s_ref).max() <= 1e-9 * s_ref[0]
     assert rel_fro((u * s) @ vh, (lambda U, S, V: (U[:, :6] * S[:6]) @ V[:6])(*np.linalg.svd(A, full_matrices=False))) <= 1e-8
+
+
+@pytest.mark.parametrize("n,ldq", [(44, 256), (128, 64 * 7), (130, 64 * 40), (300, 64 * 33), (300, 64 * 1000)])
+def test_gram_i8_exact(B, n, ldq):
+    """tcgen05 int8 slice Gram: exact integer equality with NumPy (classes i + j >= 3 of the 4x4 slice pairs)."""
+    import ctypes
+    from background_subtraction_b200 import _cabi as C
+    rng = np.random.default_rng(n + ldq)
+    sl = rng.integers(-128, 128, size=(4, n, ldq), dtype=np.int8)
+    G = np.empty((n, n), dtype=np.int64)
+    C.check(C.load().bsub_gram_i8_test(sl.ctypes.data_as(ctypes.c_void_p), n, ldq, G.ctypes.data_as(ctypes.c_void_p)))
+    ref = np.zeros((n, n), dtype=np.int64)
+    s64 = sl.astype(np.int64)
+    for i in range(4):
+        for j in range(4):
+            if i + j >= 3:
+                ref += (s64[i] @ s64[j].T) << (8 * (i + j - 3))
+    assert np.array_equal(G, ref), (np.abs(G - ref).max(), np.argwhere(G != ref)[:5])
