@@ -451,6 +451,10 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
             st->thresh = 1.0 / st->mu;
             st->iter = 0; st->svp = 0; st->done = 0; st->converged = 0; st->zz = 0.0; st->err = 0.0;
             st->maxS = 0.f; st->nnzS = 0ull;
+            // int8 Gram path: iteration 1 uses the fp64 DMMA Gram; |W_1| <= 1.08 max|D| (Y0/mu0 <= D/12.5)
+            st->gram_mode = 0; st->wq_saturated = 0; st->wmax = 1.08 * a.comm_max[2];
+            st->wq_scale = 0.0;
+            st->wq_scale_next = (a.comm_max[2] > 0.0) ? exp2(ceil(log2(4.0 * 1.08 * a.comm_max[2]))) : 1.0;
             if (!(norm_two > 0.0)) { st->done = 4; }       // all-zero input
         }
         return;

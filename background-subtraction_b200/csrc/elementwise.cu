@@ -18,7 +18,7 @@ static inline int ew_grid(long long work, int per_block, int cap = 148 * 8) {
 //      SURVEY Q1).  comm_max[0] must be zero on entry; non-negative doubles order like their bit patterns.
 __global__ void rowsum_max_kernel(const float* __restrict__ D, long long ld, long long m, int n, double* comm_max) {
     __shared__ double red[32];
-    double best = 0.0;
+    double best = 0.0, dmax = 0.0;
     const long long nq = ld / 4;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -26,6 +26,7 @@ __global__ void rowsum_max_kernel(const float* __restrict__ D, long long ld, lon
         for (int f = 0; f < n; ++f) {
             const float4 d = ldg4_stream(D + (size_t)f * ld + 4 * q);
             acc.x += fabsf(d.x); acc.y += fabsf(d.y); acc.z += fabsf(d.z); acc.w += fabsf(d.w);
+            dmax = fmax(dmax, (double)fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w))));
             if ((f & 63) == 63) { a0 += acc.x; a1 += acc.y; a2 += acc.z; a3 += acc.w; acc = make_float4(0.f, 0.f, 0.f, 0.f); }
         }
         a0 += acc.x; a1 += acc.y; a2 += acc.z; a3 += acc.w;
@@ -33,6 +34,8 @@ __global__ void rowsum_max_kernel(const float* __restrict__ D, long long ld, lon
     }
     best = block_max(best, red);
     if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(comm_max), (unsigned long long)__double_as_longlong(best));
+    dmax = block_max(dmax, red);
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(comm_max + 2), (unsigned long long)__double_as_longlong(dmax));
 }
 
 int launch_rowsum_max(const float* D, long long ld, long long m, int n, double* comm_max, cudaStream_t s) {
@@ -68,13 +71,20 @@ int launch_init_Y(const float* D, float* Y, float* S, long long ld, int n, const
 // phase bit 2: finish the iteration from the (all-reduced) communication buffer.
 __global__ void control_post_kernel(DevState* st, const double* part_zz, const unsigned long long* part_nnz,
                                     const float* part_max, int nparts, double* comm_tail, IterLog* log,
-                                    HostMirror* mirror, int phase) {
+                                    HostMirror* mirror, int phase, const float* part_wmax, int nwmax) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (!st->done) {
         if (phase & 1) {
             double zz = 0.0, nz = 0.0; float mx = 0.f;
             for (int i = 0; i < nparts; ++i) { zz += part_zz[i]; nz += (double)part_nnz[i]; mx = fmaxf(mx, part_max[i]); }
             comm_tail[0] = zz; comm_tail[1] = nz; comm_tail[2] = (double)mx;
+            // int8 Gram bookkeeping: were slices of the next W written, and with head-room?
+            float wm = -1.f;
+            if (st->use_i8 && part_wmax != nullptr && nwmax > 0) {
+                wm = 0.f;
+                for (int i = 0; i < nwmax; ++i) { const float v = part_wmax[i]; if (v < 0.f) { wm = -1.f; break; } wm = fmaxf(wm, v); }
+            }
+            comm_tail[3] = (double)wm;
         }
         if (phase & 2) {
             const double zz = comm_tail[0];
@@ -89,6 +99,18 @@ __global__ void control_post_kernel(DevState* st, const double* part_zz, const u
                 l.iter = it; l.svp = st->svp; l.sv = st->sv_used; l.pad = 0; l.err = err; l.mu = st->mu; l.nnz = st->nnzS;
             }
             st->mu = fmin(st->mu * st->rho, st->mu * 1e7);
+            if (st->use_i8) {
+                const double wm = comm_tail[3];
+                if (wm >= 0.0 && wm < 1.0e38 && wm > 0.0) {          // slices written, nothing clipped
+                    st->gram_mode = 1; st->wq_saturated = 0;
+                    st->wq_scale = st->wq_scale_next;              // scale of the slices that now exist
+                    st->wq_scale_next = exp2(ceil(log2(4.0 * wm))); // head-room x4 for the W of the following pass
+                    st->wmax = wm;
+                } else {
+                    st->gram_mode = 0; st->wq_saturated = (wm >= 1.0e38);
+                    if (wm >= 1.0e38) st->wq_scale_next = st->wq_scale_next * 16.0;
+                }
+            }
             if (err < st->tol) { st->done = 1; st->converged = 1; }
             else if (it >= st->max_iter) { st->done = 2; }
         }
@@ -102,8 +124,9 @@ __global__ void control_post_kernel(DevState* st, const double* part_zz, const u
 }
 
 int launch_control_post(DevState* st, const double* part_zz, const unsigned long long* part_nnz, const float* part_max,
-                        int nparts, double* comm_tail, IterLog* log, HostMirror* mirror, int phase, cudaStream_t s) {
-    control_post_kernel<<<1, 32, 0, s>>>(st, part_zz, part_nnz, part_max, nparts, comm_tail, log, mirror, phase);
+                        int nparts, double* comm_tail, IterLog* log, HostMirror* mirror, int phase, const float* part_wmax, int nwmax,
+                        cudaStream_t s) {
+    control_post_kernel<<<1, 32, 0, s>>>(st, part_zz, part_nnz, part_max, nparts, comm_tail, log, mirror, phase, part_wmax, nwmax);
     BSUB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -44,7 +44,7 @@ struct GramArgs {
 __global__ void __launch_bounds__(GR_THREADS, 1)
 gram_dmma_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_constant__ CUtensorMap mapS,
                  const __grid_constant__ CUtensorMap mapY, GramArgs a) {
-    if (a.st != nullptr && a.st->done) return;
+    if (a.st != nullptr && (a.st->done || a.st->gram_mode != 0)) return;      // gram_mode 1: gram_i8.cu does this iteration
     extern __shared__ __align__(128) unsigned char gram_smem_raw[];
     const int kc = a.kc, lds = kc + 4;
     const int rawrows = a.nbox * a.boxrows;
@@ -165,7 +165,7 @@ gram_dmma_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_constant
 // Sum the k-slot partials in a fixed order and scatter the symmetric result into G[npad][npad].
 __global__ void gram_reduce_kernel(const double* __restrict__ partial, const int2* __restrict__ tasks, int ntasks,
                                    int gridK, int npad, double* __restrict__ G, const DevState* st) {
-    if (st != nullptr && st->done) return;
+    if (st != nullptr && (st->done || st->gram_mode != 0)) return;
     const int task = blockIdx.x;
     const int2 t = tasks[task];
     for (int e = threadIdx.x; e < 1024; e += blockDim.x) {

@@ -73,7 +73,7 @@ struct ShrinkBuffers {
     double* part_zz;           // [nparts]
     unsigned long long* part_nnz;
     float* part_max;
-    float* part_wmax;          // [nparts][?] reserved
+    float* part_wmax;          // [stream grid] max |W_next| written with the int8 slices (nullptr: slices off)
 };
 int launch_shrink(const ShrinkPlan& p, ShrinkBuffers b, const DevState* st, int mode, cudaStream_t stream);
 
@@ -83,7 +83,7 @@ struct ShrinkTmaPlan {
     long long ld, ntiles;
     size_t smem_bytes, tpart_floats;
 };
-struct ShrinkTmaMaps { CUtensorMap D, S, Y, U; bool has_U; };
+struct ShrinkTmaMaps { CUtensorMap D, S, Y, U, Q; bool has_U, has_Q; };
 bool make_shrink_tma_plan(int n, int rows, int cols, long long ld, int num_sms, int R_hint, int Cf_hint, ShrinkTmaPlan* out);
 int make_shrink_tma_maps(const ShrinkTmaPlan& p, const float* D, float* S, float* Y, float* U, ShrinkTmaMaps* m);
 int launch_shrink_tma(const ShrinkTmaPlan& p, const ShrinkTmaMaps& maps, ShrinkBuffers b, const DevState* st, int mode,
@@ -98,6 +98,8 @@ struct ShrinkStreamPlan {
 constexpr int kStreamMaxRank = 16;
 bool make_shrink_stream_plan(int n, int rows, int cols, long long ld, int num_sms, int R_hint, ShrinkStreamPlan* out);
 int make_shrink_stream_maps(const ShrinkStreamPlan& p, const float* D, float* S, float* Y, float* U, ShrinkTmaMaps* m);
+long long shrink_stream_ldq(const ShrinkStreamPlan& p);
+int make_shrink_stream_qmap(const ShrinkStreamPlan& p, signed char* Wq, ShrinkTmaMaps* m);
 int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, ShrinkBuffers b, const DevState* st, int mode,
                          cudaStream_t stream);
 
@@ -106,7 +108,7 @@ int launch_rowsum_max(const float* D, long long ld, long long m, int n, double* 
 int launch_init_Y(const float* D, float* Y, float* S, long long ld, int n, const DevState* st, cudaStream_t s);
 int launch_control_post(DevState* st, const double* part_zz, const unsigned long long* part_nnz,
                         const float* part_max, int nparts, double* comm_sum_tail, IterLog* log, HostMirror* mirror,
-                        int phase, cudaStream_t s);
+                        int phase, const float* part_wmax, int nwmax, cudaStream_t s);
 int launch_convert_f64(const double* src, long long src_ld, float* dst, long long ld, long long m, int n,
                        cudaStream_t s);
 int launch_export_f64(const float* src, long long ld, double* dst, long long dst_ld, long long m, int n,

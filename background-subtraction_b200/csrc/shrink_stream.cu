@@ -33,7 +33,11 @@ struct ShrinkStreamArgs {
     int ntile_r; long long ntiles;
     const DevState* st;
     double* part_zz; unsigned long long* part_nnz; float* part_max;
+    float* part_wmax;                      // [grid] max |W_next| (negative: this kernel did not run -> no slices)
     int mode;
+    int wq;                                // write the int8 slices of W_next (gram_i8.cu)
+    int QS;                                // bytes per slice sub-buffer of a stage (FC*Pq rounded up to 128)
+    int Pq;                                // bytes per frame row of a tile in the slice matrix (P rounded up to 16: TMA box rule)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -99,14 +103,15 @@ __device__ __forceinline__ void ss_accumulate(float (&acc)[SS_KC][4], const floa
 // phase B, one 3x3 group of one frame: L from T, prox, dual update, in place in the stage
 template <int KCNT>
 __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg, const float* vc, int R, int P, float inv_mu,
-                                         float mu_f, float lamq, int mode, double& zz_acc, unsigned int& nnz_acc, float& max_acc) {
+                                         float mu_f, float lamq, int mode, double& zz_acc, unsigned int& nnz_acc, float& max_acc,
+                                         unsigned char* qb, int QS, int qpad, float inv_mu_next, float Qf, float& wmax_acc, int& sat_acc) {
     float vv[SS_KC];
 #pragma unroll
     for (int k4 = 0; k4 < (KCNT + 3) / 4; ++k4) {
         const float4 v = *reinterpret_cast<const float4*>(vc + 4 * k4);
         vv[4 * k4] = v.x; vv[4 * k4 + 1] = v.y; vv[4 * k4 + 2] = v.z; vv[4 * k4 + 3] = v.w;
     }
-    float av[9], yv[9], x[9], ax[9];
+    float av[9], yv[9], x[9], ax[9], dv[9];
     float sabs = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -116,7 +121,8 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
             float l = 0.f;
 #pragma unroll
             for (int k = 0; k < KCNT; ++k) l = fmaf(vv[k], Tg[(size_t)k * P + o], l);
-            av[e] = dsp[o] - l;                           // a = D - L
+            dv[e] = dsp[o];
+            av[e] = dv[e] - l;                            // a = D - L
             yv[e] = ysp[o];
             x[e] = fmaf(yv[e], inv_mu, av[e]);            // G_S
             ax[e] = fabsf(x[e]);
@@ -170,6 +176,26 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
 #pragma unroll
         for (int e = 0; e < 9; ++e) dsp[(e / 3) * R + (e % 3)] = x[e];
     }
+    if (qb != nullptr) {
+        // W of the next iteration, exactly as the next pass will form it from the stored S and Y, as 32-bit fixed point
+        // q = rint(W * Q) split into four balanced base-256 digits (one byte plane each)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dr = 0; dr < 3; ++dr) {
+                const int e = c * 3 + dr, o = c * R + dr;
+                const float wn = fmaf(ysp[o], inv_mu_next, dv[e] - dsp[o]);
+                wmax_acc = fmaxf(wmax_acc, fabsf(wn));
+                float wq = wn * Qf;
+                if (!(fabsf(wq) < 2130706432.f)) { sat_acc = 1; wq = fminf(fmaxf(wq, -2130706432.f), 2130706432.f); }   // |q| <= 2^31 - 2^24
+                int q = __float2int_rn(wq);
+                const int d0 = (q << 24) >> 24; q = (q - d0) >> 8;
+                const int d1 = (q << 24) >> 24; q = (q - d1) >> 8;
+                const int d2 = (q << 24) >> 24; q = (q - d2) >> 8;
+                qb[o] = (unsigned char)d0; qb[QS + o] = (unsigned char)d1; qb[2 * QS + o] = (unsigned char)d2; qb[3 * QS + o] = (unsigned char)q;
+            }
+        (void)qpad;
+    }
 }
 
 #define SS_DISPATCH_K(kcnt, CALL)                         \
@@ -191,13 +217,14 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
 template <int NCW>      // number of consumer warps; block = 32 * (NCW + 2)
 __global__ void __launch_bounds__(32 * (NCW + 2), 1)
 shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_constant__ CUtensorMap mapS,
-                     const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapOut, ShrinkStreamArgs a) {
+                     const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapOut,
+                     const __grid_constant__ CUtensorMap mapQ, ShrinkStreamArgs a) {
     constexpr int NTC = 32 * NCW;
     const DevState* st = a.st;
     if (st->done) return;
     const int r = st->svp;
     if (r > SS_KC) {                                       // large ranks take the fallback kernel launched next
-        if (threadIdx.x == 0) { a.part_zz[blockIdx.x] = 0.0; a.part_nnz[blockIdx.x] = 0ull; a.part_max[blockIdx.x] = 0.f; }
+        if (threadIdx.x == 0) { a.part_zz[blockIdx.x] = 0.0; a.part_nnz[blockIdx.x] = 0ull; a.part_max[blockIdx.x] = 0.f; if (a.part_wmax != nullptr) a.part_wmax[blockIdx.x] = -1.f; }
         return;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -205,6 +232,12 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
     const double mu_d = st->mu;
     const float inv_mu = (float)(1.0 / mu_d), mu_f = (float)mu_d;
     const float lamq = (float)(st->lambda / mu_d);
+    const bool wq = (a.wq != 0) && (a.mode != SHRINK_SPILL);
+    // the next pass uses mu_next = min(mu rho, mu 1e7) (control_post_kernel): same double arithmetic here
+    const float inv_mu_next = (float)(1.0 / fmin(mu_d * st->rho, mu_d * 1e7));
+    const float Qf = wq ? (float)(2147483648.0 / st->wq_scale_next) : 0.f;
+    float wmax_acc = 0.f;
+    int sat_acc = 0;
 
     extern __shared__ __align__(128) unsigned char ss_smem_raw[];
     const size_t stage_floats = (size_t)3 * a.BS;
@@ -287,6 +320,10 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                         const int fbase = (c - (phaseA ? ncf : 0)) * FC;
                         tma_store_3d_hint(&mapOut, b, i0, j0, fbase, pol_stream);                  // S_new (or G_S)
                         if (a.mode != SHRINK_SPILL) tma_store_3d_hint(&mapY, b + (size_t)2 * a.BS, i0, j0, fbase, pol_stream);
+                        if (wq) {                      // four byte planes of W_next, pixel order = tile-major (gram_i8.cu does not care)
+                            const unsigned char* qbase = reinterpret_cast<const unsigned char*>(b + (size_t)a.BS);
+                            for (int sl = 0; sl < 4; ++sl) tma_store_3d(&mapQ, qbase + (size_t)sl * a.QS, (int)(tl * a.Pq), fbase, sl);
+                        }
                         tma_store_commit();
                         tma_store_wait_read<0>();                                                  // stage may be overwritten
                     }
@@ -359,8 +396,13 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                     if (fg >= a.n) continue;
                     float* dsp = b + (size_t)f * P + 3 * g;
                     float* ysp = b + (size_t)2 * a.BS + (size_t)f * P + 3 * g;
+                    unsigned char* qrow = reinterpret_cast<unsigned char*>(b + (size_t)a.BS) + (size_t)f * a.Pq;
+                    unsigned char* qb = wq ? (qrow + 3 * g) : nullptr;
+                    if (wq && g == NG - 1) {           // pad bytes P .. Pq of this frame row are zero in all four planes
+                        for (int o = P; o < a.Pq; ++o) { qrow[o] = 0; qrow[a.QS + o] = 0; qrow[2 * a.QS + o] = 0; qrow[3 * a.QS + o] = 0; }
+                    }
                     SS_DISPATCH_K(r, (ss_group<K_>(dsp, ysp, Tp + 3 * g, VC_s + (size_t)fg * SS_KC, R, P, inv_mu, mu_f, lamq, a.mode,
-                                                   zz_acc, nnz_acc, max_acc)));
+                                                   zz_acc, nnz_acc, max_acc, qb, a.QS, 0, inv_mu_next, Qf, wmax_acc, sat_acc)));
                 }
                 fence_proxy_async_smem();                   // my writes -> visible to the storer's TMA stores
                 __syncwarp();
@@ -375,12 +417,15 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
     if (threadIdx.x == 0) a.part_nnz[blockIdx.x] = (unsigned long long)(nt + 0.5);
     double mt = block_max((double)max_acc, redd);
     if (threadIdx.x == 0) a.part_max[blockIdx.x] = (float)mt;
+    // max |W_next| (+ a large sentinel if a slice was clipped) for the fixed-point scale of the following pass
+    double wt = block_max((double)(sat_acc ? 3.0e38f : wmax_acc), redd);
+    if (threadIdx.x == 0 && a.part_wmax != nullptr) a.part_wmax[blockIdx.x] = wq ? (float)wt : -1.f;
 }
 
 // -------------------------------------------------------------------------------------------------------------
 static size_t ss_smem_bytes(int n, int R, int FC, int NS, int NTC) {
     const int P = 3 * R, NQ = P / 4, NFL = NTC / NQ;
-    const size_t bs = ((size_t)FC * P + 31) / 32 * 32;
+    const size_t bs = ((size_t)FC * ((P + 15) / 16 * 16) + 127) / 128 * 128;
     size_t fl = (size_t)NS * 3 * bs + (size_t)NFL * SS_KRED * P + (size_t)SS_KC * P + (size_t)2 * n * SS_KC;
     return fl * sizeof(float) + (size_t)3 * NS * sizeof(uint64_t) + 64;
 }
@@ -408,7 +453,7 @@ bool make_shrink_stream_plan(int n, int rows, int cols, long long ld, int num_sm
         while (NS >= 3 && ss_smem_bytes(n, R, FC, NS, NTC) > SS_SMEM_CAP) --NS;
         if (NS < 3) continue;
         p.R = R; p.P = 3 * R; p.FC = FC; p.NS = NS; p.NCW = NCW;
-        p.bufstride = (int)(((size_t)FC * p.P + 31) / 32 * 32);
+        p.bufstride = (int)(((size_t)FC * ((p.P + 15) / 16 * 16) + 127) / 128 * 128);
         p.smem_bytes = ss_smem_bytes(n, R, FC, NS, NTC);
         p.nchunkf = (n + FC - 1) / FC;
         p.ntile_r = (rows + R - 1) / R;
@@ -432,6 +477,20 @@ int make_shrink_stream_maps(const ShrinkStreamPlan& p, const float* D, float* S,
     m->has_U = false;
     if (U != nullptr) { if (make_tensor_map_f32(&m->U, U, 3, dims, strides, box) != 0) return -1; m->has_U = true; }
     else m->U = m->S;
+    m->has_Q = false; m->Q = m->S;
+    return 0;
+}
+
+// slice matrix Wq: int8 [4][n][ldq], pixel order tile-major (tile tl of the shrink pass owns bytes [tl*P, tl*P + P) of every row)
+long long shrink_stream_ldq(const ShrinkStreamPlan& p) { return ((p.ntiles * (long long)((p.P + 15) / 16 * 16)) + 63) / 64 * 64; }
+
+int make_shrink_stream_qmap(const ShrinkStreamPlan& p, signed char* Wq, ShrinkTmaMaps* m) {
+    const long long ldq = shrink_stream_ldq(p);
+    const uint64_t dims[3] = {(uint64_t)ldq, (uint64_t)p.n, 4};
+    const uint64_t strides[2] = {(uint64_t)ldq, (uint64_t)ldq * (uint64_t)p.n};
+    const uint32_t box[3] = {(uint32_t)((p.P + 15) / 16 * 16), (uint32_t)p.FC, 1};
+    if (make_tensor_map_u8(&m->Q, Wq, 3, dims, strides, box, 0) != 0) return -1;
+    m->has_Q = true;
     return 0;
 }
 
@@ -443,7 +502,7 @@ static int launch_ss(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, const
         attr_set = true;
     }
     const CUtensorMap& outmap = (mode == SHRINK_SPILL) ? maps.U : maps.S;
-    shrink_stream_kernel<NCW><<<p.grid, 32 * (NCW + 2), p.smem_bytes, stream>>>(maps.D, maps.S, maps.Y, outmap, a);
+    shrink_stream_kernel<NCW><<<p.grid, 32 * (NCW + 2), p.smem_bytes, stream>>>(maps.D, maps.S, maps.Y, outmap, maps.Q, a);
     BSUB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -455,7 +514,9 @@ int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, S
     a.T = b.T; a.Vr = b.Vr; a.VC = b.VC; a.vstride = b.vstride; a.ld = p.ld; a.n = p.n; a.rows = p.rows; a.cols = p.cols;
     a.R = p.R; a.P = p.P; a.NQ = p.P / 4; a.NFL = (32 * p.NCW) / a.NQ; a.FC = p.FC; a.NS = p.NS; a.BS = p.bufstride;
     a.nchunkf = p.nchunkf; a.ntile_r = p.ntile_r; a.ntiles = p.ntiles; a.st = st; a.part_zz = b.part_zz; a.part_nnz = b.part_nnz;
-    a.part_max = b.part_max; a.mode = mode;
+    a.part_max = b.part_max; a.part_wmax = b.part_wmax; a.mode = mode;
+    a.wq = (maps.has_Q && b.part_wmax != nullptr) ? 1 : 0; a.Pq = (p.P + 15) / 16 * 16;
+    a.QS = (int)(((size_t)p.FC * a.Pq + 127) / 128 * 128);
     if (p.NCW == 16) return launch_ss<16>(p, maps, a, mode, stream);
     return launch_ss<8>(p, maps, a, mode, stream);
 }

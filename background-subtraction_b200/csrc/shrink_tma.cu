@@ -444,6 +444,7 @@ int make_shrink_tma_maps(const ShrinkTmaPlan& p, const float* D, float* S, float
     m->has_U = false;
     if (U != nullptr) { if (make_tensor_map_f32(&m->U, U, 3, dims, strides, box) != 0) return -1; m->has_U = true; }
     else m->U = m->S;
+    m->has_Q = false; m->Q = m->S;
     return 0;
 }
 

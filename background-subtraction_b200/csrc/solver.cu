@@ -50,6 +50,9 @@ struct bsub_solver {
     EigPlan ep; EigBuffers eb;
     ShrinkPlan sp; ShrinkTmaPlan stp; ShrinkTmaMaps stmaps; bool use_tma = false, stmaps_ready = false;
     ShrinkStreamPlan ssp; ShrinkTmaMaps ssmaps; bool use_stream = false;
+    // int8 tcgen05 Gram from the W slices written by the streamed shrink pass
+    bool use_i8 = false; signed char* Wq = nullptr; unsigned long long* Gint = nullptr; GramI8Plan gip; CUtensorMap gimap;
+    int4* gi_info = nullptr; int* gi_blkn = nullptr; int gi_ncta = 0; float* part_wmax = nullptr;
     float* tpart = nullptr; double* part_zz = nullptr; unsigned long long* part_nnz = nullptr;
     float* part_max = nullptr;
     int shrink_mode = SHRINK_FLAT3;
@@ -93,7 +96,8 @@ int bsub_destroy(bsub_solver* s) {
     cudaDeviceSynchronize();
     void* ptrs[] = {s->D, s->S, s->Y, s->T, s->L, s->U, s->st, s->log, s->comm_sum, s->comm_max, s->tasks_dev, s->gram_partial,
                     s->eb.work, s->eb.lam, s->eb.Z, s->eb.Vr, s->eb.VC, s->tpart, s->part_zz, s->part_nnz, s->part_max, s->gptr,
-                    s->gidx, s->eta_dev, s->xi, s->tot, s->sweeps_dev, s->labels_dev, s->lam_table, s->bsums};
+                    s->gidx, s->eta_dev, s->xi, s->tot, s->sweeps_dev, s->labels_dev, s->lam_table, s->bsums, s->Wq, s->Gint,
+                    s->gi_info, s->gi_blkn, s->part_wmax};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->mirror) cudaFreeHost((void*)s->mirror);
     for (int i = 0; i <= kRunAhead; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -181,6 +185,25 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
         ALLOC(s->part_max, sizeof(float) * nparts);
         cudaMemset(s->part_zz, 0, sizeof(double) * nparts); cudaMemset(s->part_nnz, 0, sizeof(unsigned long long) * nparts);
         cudaMemset(s->part_max, 0, sizeof(float) * nparts);
+        s->use_i8 = s->use_stream && (getenv("BSUB_NO_I8") == nullptr) && (s->cfg.m_global == s->m) &&
+                    (cfg->prox == BSUB_PROX_FLAT_LINF || cfg->prox == BSUB_PROX_L1);
+        if (s->use_i8) {
+            const long long ldq = shrink_stream_ldq(s->ssp);
+            s->gip = make_gram_i8_plan(s->n, ldq, s->num_sms);
+            std::vector<int4> info; std::vector<int> blkn;
+            fill_gram_i8_tables(s->gip, info, blkn);
+            s->gi_ncta = (int)info.size();
+            ALLOC(s->Wq, (size_t)4 * s->n * ldq);
+            cudaMemset(s->Wq, 0, (size_t)4 * s->n * ldq);                     // the row tails (ldq padding) stay zero
+            ALLOC(s->Gint, sizeof(unsigned long long) * (size_t)s->gip.nblk * 128 * s->gip.nblk * 128);
+            ALLOC(s->gi_info, sizeof(int4) * info.size());
+            ALLOC(s->gi_blkn, sizeof(int) * blkn.size());
+            ALLOC(s->part_wmax, sizeof(float) * s->ssp.grid);
+            cudaMemcpy(s->gi_info, info.data(), sizeof(int4) * info.size(), cudaMemcpyHostToDevice);
+            cudaMemcpy(s->gi_blkn, blkn.data(), sizeof(int) * blkn.size(), cudaMemcpyHostToDevice);
+            cudaMemset(s->part_wmax, 0, sizeof(float) * s->ssp.grid);
+            if (make_gram_i8_map(s->gip, s->Wq, &s->gimap) != 0) { rc = -1; break; }
+        }
         for (int i = 0; i <= kRunAhead; ++i)
             if (cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming) != cudaSuccess) { set_error("bsub_create: event"); rc = -1; break; }
         if (rc) break;
@@ -357,6 +380,7 @@ static int upload_state(bsub_solver* s, cudaStream_t st) {
     h.use_sv_prediction = c.use_sv_prediction;
     h.break_on_rank0 = c.break_on_rank0;
     h.sv = c.use_sv_prediction ? c.sv0 : h.d;
+    h.use_i8 = s->use_i8 ? 1 : 0;
     CK(cudaMemcpyAsync(s->st, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));     // h is a stack object
     memset((void*)s->mirror, 0, sizeof(HostMirror));
@@ -405,7 +429,12 @@ int bsub_step_init_finish(bsub_solver* s, void* stream) {
 
 int bsub_step_gram(bsub_solver* s, void* stream) {
     if (!s || !s->initialised) { set_error("bsub_step_gram: solver not initialised"); return -1; }
-    return launch_gram(s->gp, s->gmaps, true, s->tasks_dev, s->st, 0.f, s->gram_partial, s->comm_sum, as_stream(stream));
+    // both Gram kernels are enqueued; DevState.gram_mode (set on the device) decides which one does the work
+    RET_IF(launch_gram(s->gp, s->gmaps, true, s->tasks_dev, s->st, 0.f, s->gram_partial, s->comm_sum, as_stream(stream)));
+    if (s->use_i8)
+        RET_IF(launch_gram_i8(s->gip, s->gimap, s->gi_info, s->gi_ncta, s->gi_blkn, s->Gint, s->comm_sum, s->npad, s->st, 0.0, 1,
+                              as_stream(stream)));
+    return 0;
 }
 
 int bsub_step_solve(bsub_solver* s, void* stream) {
@@ -418,12 +447,14 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
     cudaStream_t st = as_stream(stream);
     ShrinkBuffers b;
     b.D = s->D; b.S = s->S; b.Y = s->Y; b.T = s->T; b.U = s->U; b.tpart = s->tpart; b.Vr = s->eb.Vr; b.VC = s->eb.VC;
-    b.vstride = s->eb.vstride; b.part_zz = s->part_zz; b.part_nnz = s->part_nnz; b.part_max = s->part_max; b.part_wmax = nullptr;
+    b.vstride = s->eb.vstride; b.part_zz = s->part_zz; b.part_nnz = s->part_nnz; b.part_max = s->part_max;
+    b.part_wmax = s->use_i8 ? s->part_wmax : nullptr;
     int nparts = s->sp.nparts;
     if (s->use_tma) {
         if (!s->stmaps_ready) {
             RET_IF(make_shrink_tma_maps(s->stp, s->D, s->S, s->Y, s->U, &s->stmaps));
             if (s->use_stream) RET_IF(make_shrink_stream_maps(s->ssp, s->D, s->S, s->Y, s->U, &s->ssmaps));
+            if (s->use_stream && s->use_i8) RET_IF(make_shrink_stream_qmap(s->ssp, s->Wq, &s->ssmaps));
             s->stmaps_ready = true;
         }
         int off = 0, min_rank = 0;
@@ -455,7 +486,7 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
                                   s->part_nnz, s->part_max, nparts, st));
     }
     RET_IF(launch_control_post(s->st, s->part_zz, s->part_nnz, s->part_max, nparts, s->comm_sum + (size_t)s->npad * s->npad, s->log,
-                               s->mirror_dev, 1, st));
+                               s->mirror_dev, 1, (s->use_i8 && s->use_stream) ? s->part_wmax : nullptr, s->use_i8 ? s->ssp.grid : 0, st));
     return 0;
 }
 
@@ -463,7 +494,7 @@ int bsub_step_finish_iter(bsub_solver* s, void* stream) {
     if (!s || !s->initialised) { set_error("bsub_step_finish_iter: solver not initialised"); return -1; }
     cudaStream_t st = as_stream(stream);
     RET_IF(launch_control_post(s->st, s->part_zz, s->part_nnz, s->part_max, 0, s->comm_sum + (size_t)s->npad * s->npad, s->log,
-                               s->mirror_dev, 2, st));
+                               s->mirror_dev, 2, nullptr, 0, st));
     CK(cudaEventRecord(s->ev[s->iters_enqueued % (kRunAhead + 1)], st));
     s->iters_enqueued++;
     return 0;
