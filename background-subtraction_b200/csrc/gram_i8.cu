@@ -10,7 +10,9 @@
 // This replaces the fp64 DMMA Gram (gram.cu, FP64-pipe bound at ~6.4 ms for 1080p x 300) wherever the slices exist.
 //
 // Kernel anatomy (one CTA = one 128 x N output tile of the upper block triangle x a range of pixels):
-//   warp 0     TMA producer: K-major SWIZZLE_64B boxes {64 B pixels, 128 frames} of the A block and the B block (4 slices)
+//   warp 0     TMA producer: one 8 KB box {16 B, 128 frames, 4 k-blocks} per slice and frame block -- the slice matrix is
+//              stored k-block-major ([slice][k16][frame][16 B]) so every box is four contiguous 2 KB runs and lands in
+//              shared memory directly in the canonical K-major no-swizzle UMMA layout (8x16 B core matrices)
 //   warp 1     MMA issuer (one elected thread): tcgen05.mma, tcgen05.commit -> mbarriers
 //   warp 2     TMEM allocator (512 columns = 4 classes x 128)
 //   warps 4-7  epilogue: tcgen05.ld of the four class accumulators, recombination into int64, atomicAdd to global
@@ -23,7 +25,7 @@
 namespace bsub {
 
 constexpr int GI_THREADS = 256;
-constexpr int GI_KB = 64;                 // pixels (bytes) per K block = one SWIZZLE_64B row
+constexpr int GI_KB = 64;                 // pixels (bytes) per pipeline stage = 4 k16 blocks = 2 MMA k-steps
 constexpr int GI_STAGES = 3;
 constexpr int GI_FLUSH_KB = 448;          // K blocks between flushes: 4 pairs * 448*64 px * 2^14 < 2^31
 constexpr int GI_TILE_BYTES = 128 * GI_KB;            // one slice of one 128-frame block
@@ -31,7 +33,8 @@ constexpr int GI_STAGE_BYTES = 8 * GI_TILE_BYTES;     // A (4 slices) + B (4 sli
 
 struct GramI8Args {
     int n, nblk;
-    const int4* cta_info;                 // per CTA: (bi, bj, kb_begin, kb_end)
+    const int4* cta_info;                 // per CTA: (bi, bj, first stage index, stage stride); stages are 64-pixel blocks
+    int nkb;                              // number of 64-pixel stages in the slice matrix
     const int* blk_n;                     // MMA N of each frame block (multiple of 16, <= 128)
     unsigned long long* Gint;             // [nblk*128][nblk*128] int64 accumulators (zeroed by the caller)
     const DevState* st;
@@ -45,15 +48,14 @@ __device__ __forceinline__ void gi_mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void gi_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ uint64_t gi_smem_desc(uint32_t saddr) {
-    // K-major, SWIZZLE_64B: rows of 64 B, 8-row groups 512 B apart (SBO), LBO = 1 (ignored for swizzled K-major),
-    // descriptor version 1 (Blackwell), layout type 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t gi_smem_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    // K-major, no swizzle ("interleave"): 8 x 16 B core matrices; the two core matrices of one K = 32 MMA are 2048 B
+    // apart (LBO: next k16 block of the stage), consecutive 8-frame groups 128 B apart (SBO); descriptor version 1
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(128 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)4 << 61;
     return d;
 }
 __device__ __forceinline__ uint32_t gi_instr_desc(int N) {
@@ -79,7 +81,7 @@ __device__ __forceinline__ void gi_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) 
 }
 
 __global__ void __launch_bounds__(GI_THREADS, 1)
-gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8Args a) {
+gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapQlast, GramI8Args a) {
     if (a.st != nullptr && (a.st->done || a.st->gram_mode != a.require_mode)) return;
     extern __shared__ __align__(1024) unsigned char gi_smem[];
     unsigned char* stages = gi_smem;                                             // [GI_STAGES][8][128][64]
@@ -91,10 +93,12 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8Args a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int4 info = a.cta_info[blockIdx.x];
-    const int bi = info.x, bj = info.y, kb0 = info.z, kb1 = info.w;
+    const int bi = info.x, bj = info.y, kb0 = info.z, kstride = info.w;
     const bool diag = (bi == bj);
     const int Nj = a.blk_n[bj];
-    const int nkb = kb1 - kb0;
+    // stages kb0, kb0 + kstride, ...: all CTAs sweep the pixels front to back together, so a frame block fetched for one
+    // output tile is still in L2 when the other tiles need it
+    const int nkb = (a.nkb > kb0) ? (a.nkb - kb0 + kstride - 1) / kstride : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < GI_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -115,17 +119,19 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8Args a) {
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            const uint32_t tx = (uint32_t)((diag ? 4 : 8) * GI_TILE_BYTES);
+            // the B block of the last frame block only needs its Nj (< 128) frames: narrower box, fewer bytes
+            const bool narrowB = (!diag && Nj < 128);
+            const uint32_t tx = (uint32_t)(4 * GI_TILE_BYTES + (diag ? 0 : 4 * Nj * GI_KB));
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % GI_STAGES;
                 const int u = kb / GI_STAGES;
                 if (u > 0) gi_mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));
                 unsigned char* base = stages + (size_t)s * GI_STAGE_BYTES;
                 mbar_expect_tx(&full[s], tx);
-                const int x = (kb0 + kb) * GI_KB;
+                const int k16 = (kb0 + kb * kstride) * (GI_KB / 16);
                 for (int sl = 0; sl < 4; ++sl) {
-                    tma_load_3d(base + (size_t)sl * GI_TILE_BYTES, &mapQ, &full[s], x, bi * 128, sl);
-                    if (!diag) tma_load_3d(base + (size_t)(4 + sl) * GI_TILE_BYTES, &mapQ, &full[s], x, bj * 128, sl);
+                    tma_load_4d(base + (size_t)sl * GI_TILE_BYTES, &mapQ, &full[s], 0, bi * 128, k16, sl);
+                    if (!diag) tma_load_4d(base + (size_t)(4 + sl) * GI_TILE_BYTES, narrowB ? &mapQlast : &mapQ, &full[s], 0, bj * 128, k16, sl);
                 }
             }
         }
@@ -153,8 +159,9 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8Args a) {
                         for (int j = 0; j < 4; ++j) {
                             const int cls = i + j - 3;
                             if (cls < 0) continue;
-                            const uint64_t da = gi_smem_desc(sbase + (uint32_t)(i * GI_TILE_BYTES) + ks * 32);
-                            const uint64_t db = gi_smem_desc(sbase + (uint32_t)(((diag ? 0 : 4) + j) * GI_TILE_BYTES) + ks * 32);
+                            const uint32_t lboB = (diag || Nj == 128) ? 2048u : (uint32_t)(Nj * 16);
+                            const uint64_t da = gi_smem_desc(sbase + (uint32_t)(i * GI_TILE_BYTES) + ks * 4096, 2048u);
+                            const uint64_t db = gi_smem_desc(sbase + (uint32_t)(((diag ? 0 : 4) + j) * GI_TILE_BYTES) + ks * 2 * lboB, lboB);
                             // first pair of a class right after a flush overwrites the accumulator
                             const bool first = (since_flush == 0 && ks == 0 && j == 3);   // (i, 3) is the first pair of class i
                             gi_mma(tmem_base + (uint32_t)(cls * 128), da, db, idesc, first ? 0u : 1u);
@@ -230,7 +237,7 @@ GramI8Plan make_gram_i8_plan(int n, long long ldq, int num_sms) {
     GramI8Plan p;
     p.n = n; p.ldq = ldq;
     p.nblk = (n + 127) / 128;
-    p.nkb = (int)(ldq / GI_KB);
+    p.nkb = (int)(ldq / GI_KB);          // ldq = pixels per frame in the slice matrix, a multiple of 64
     p.smem_bytes = (size_t)GI_STAGES * GI_STAGE_BYTES + 256 + 1024;
     p.grid = num_sms;
     return p;
@@ -245,7 +252,11 @@ void fill_gram_i8_tables(const GramI8Plan& p, std::vector<int4>& cta_info, std::
     std::vector<double> w;
     double wsum = 0.0;
     for (int bi = 0; bi < p.nblk; ++bi)
-        for (int bj = bi; bj < p.nblk; ++bj) { tiles.push_back({bi, bj}); w.push_back(blk_n[bj]); wsum += blk_n[bj]; }
+        for (int bj = bi; bj < p.nblk; ++bj) {
+            // the kernel is bound by operand bytes per 64-pixel stage (L2 -> SM), not by the MMAs: balance on bytes
+            const double cost = 128.0 + (bi == bj ? 0.0 : (double)blk_n[bj]);
+            tiles.push_back({bi, bj}); w.push_back(cost); wsum += cost;
+        }
     std::vector<int> cnt(tiles.size(), 1);
     int left = p.grid - (int)tiles.size();
     if (left < 0) left = 0;
@@ -261,22 +272,25 @@ void fill_gram_i8_tables(const GramI8Plan& p, std::vector<int4>& cta_info, std::
     cta_info.clear();
     for (size_t t = 0; t < tiles.size(); ++t) {
         const int c = std::min(cnt[t], std::max(1, p.nkb));
-        for (int k = 0; k < c; ++k) {
-            const int kb0 = (int)((long long)p.nkb * k / c), kb1 = (int)((long long)p.nkb * (k + 1) / c);
-            if (kb1 > kb0) cta_info.push_back(make_int4(tiles[t].first, tiles[t].second, kb0, kb1));
-        }
+        for (int k = 0; k < c; ++k) cta_info.push_back(make_int4(tiles[t].first, tiles[t].second, k, c));
     }
 }
 
-int make_gram_i8_map(const GramI8Plan& p, const signed char* Wq, CUtensorMap* map) {
-    // u8 tensor {ldq bytes, n frames, 4 slices}; K-major SWIZZLE_64B boxes {64, 128, 1}; frames beyond n read as zero
-    const uint64_t dims[3] = {(uint64_t)p.ldq, (uint64_t)p.n, 4};
-    const uint64_t strides[2] = {(uint64_t)p.ldq, (uint64_t)p.ldq * (uint64_t)p.n};
-    const uint32_t box[3] = {GI_KB, 128, 1};
-    return make_tensor_map_u8(map, Wq, 3, dims, strides, box, 64);
+int gram_i8_last_block_n(const GramI8Plan& p) {
+    const int last = p.n - (p.nblk - 1) * 128;
+    return std::min(128, ((last + 15) / 16) * 16);
 }
 
-int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const int4* cta_info_dev, int ncta, const int* blk_n_dev,
+int make_gram_i8_map(const GramI8Plan& p, const signed char* Wq, CUtensorMap* map, int box_frames) {
+    // u8 tensor {16 B, n frames, ldq/16 k-blocks, 4 slices} (k-block-major slice matrix); boxes {16, 128, 4, 1};
+    // frames beyond n read as zero
+    const uint64_t dims[4] = {16, (uint64_t)p.n, (uint64_t)(p.ldq / 16), 4};
+    const uint64_t strides[3] = {16, (uint64_t)16 * p.n, (uint64_t)p.ldq * (uint64_t)p.n};
+    const uint32_t box[4] = {16, (uint32_t)box_frames, 4, 1};
+    return make_tensor_map_u8(map, Wq, 4, dims, strides, box, 0);
+}
+
+int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const CUtensorMap& map_last, const int4* cta_info_dev, int ncta, const int* blk_n_dev,
                    unsigned long long* Gint, double* G, int npad, const DevState* st, double scale_override, int require_mode,
                    cudaStream_t stream) {
     static bool attr_set = false;
@@ -287,8 +301,8 @@ int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const int4* cta_
     const size_t gbytes = sizeof(unsigned long long) * (size_t)p.nblk * 128 * p.nblk * 128;
     BSUB_CUDA_CHECK(cudaMemsetAsync(Gint, 0, gbytes, stream));
     GramI8Args a;
-    a.n = p.n; a.nblk = p.nblk; a.cta_info = cta_info_dev; a.blk_n = blk_n_dev; a.Gint = Gint; a.st = st; a.require_mode = require_mode;
-    gram_i8_kernel<<<ncta, GI_THREADS, p.smem_bytes, stream>>>(map, a);
+    a.n = p.n; a.nblk = p.nblk; a.nkb = p.nkb; a.cta_info = cta_info_dev; a.blk_n = blk_n_dev; a.Gint = Gint; a.st = st; a.require_mode = require_mode;
+    gram_i8_kernel<<<ncta, GI_THREADS, p.smem_bytes, stream>>>(map, map_last, a);
     BSUB_CUDA_CHECK(cudaGetLastError());
     gram_i8_finish_kernel<<<64, 256, 0, stream>>>(Gint, p.nblk, p.n, npad, G, st, scale_override, require_mode);
     BSUB_CUDA_CHECK(cudaGetLastError());

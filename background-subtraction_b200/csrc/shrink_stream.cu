@@ -37,7 +37,7 @@ struct ShrinkStreamArgs {
     int mode;
     int wq;                                // write the int8 slices of W_next (gram_i8.cu)
     int QS;                                // bytes per slice sub-buffer of a stage (FC*Pq rounded up to 128)
-    int Pq;                                // bytes per frame row of a tile in the slice matrix (P rounded up to 16: TMA box rule)
+    int Pq;                                // = P (a multiple of 16 when the slices are on): bytes per frame of a tile
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -104,7 +104,8 @@ __device__ __forceinline__ void ss_accumulate(float (&acc)[SS_KC][4], const floa
 template <int KCNT>
 __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg, const float* vc, int R, int P, float inv_mu,
                                          float mu_f, float lamq, int mode, double& zz_acc, unsigned int& nnz_acc, float& max_acc,
-                                         unsigned char* qb, int QS, int qpad, float inv_mu_next, float Qf, float& wmax_acc, int& sat_acc) {
+                                         unsigned char* qb, int QS, int o0, int kstep, float inv_mu_next, float Qf, float& wmax_acc,
+                                         int& sat_acc) {
     float vv[SS_KC];
 #pragma unroll
     for (int k4 = 0; k4 < (KCNT + 3) / 4; ++k4) {
@@ -192,9 +193,10 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
                 const int d0 = (q << 24) >> 24; q = (q - d0) >> 8;
                 const int d1 = (q << 24) >> 24; q = (q - d1) >> 8;
                 const int d2 = (q << 24) >> 24; q = (q - d2) >> 8;
-                qb[o] = (unsigned char)d0; qb[QS + o] = (unsigned char)d1; qb[2 * QS + o] = (unsigned char)d2; qb[3 * QS + o] = (unsigned char)q;
+                // stage layout per plane: [k16 block of the tile][frame][16 B]  (k-block-major, see gram_i8.cu)
+                const int po = ((o0 + o) >> 4) * kstep + ((o0 + o) & 15);
+                qb[po] = (unsigned char)d0; qb[QS + po] = (unsigned char)d1; qb[2 * QS + po] = (unsigned char)d2; qb[3 * QS + po] = (unsigned char)q;
             }
-        (void)qpad;
     }
 }
 
@@ -322,7 +324,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                         if (a.mode != SHRINK_SPILL) tma_store_3d_hint(&mapY, b + (size_t)2 * a.BS, i0, j0, fbase, pol_stream);
                         if (wq) {                      // four byte planes of W_next, pixel order = tile-major (gram_i8.cu does not care)
                             const unsigned char* qbase = reinterpret_cast<const unsigned char*>(b + (size_t)a.BS);
-                            for (int sl = 0; sl < 4; ++sl) tma_store_3d(&mapQ, qbase + (size_t)sl * a.QS, (int)(tl * a.Pq), fbase, sl);
+                            for (int sl = 0; sl < 4; ++sl) tma_store_4d(&mapQ, qbase + (size_t)sl * a.QS, 0, fbase, (int)(tl * (P / 16)), sl);
                         }
                         tma_store_commit();
                         tma_store_wait_read<0>();                                                  // stage may be overwritten
@@ -396,13 +398,9 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                     if (fg >= a.n) continue;
                     float* dsp = b + (size_t)f * P + 3 * g;
                     float* ysp = b + (size_t)2 * a.BS + (size_t)f * P + 3 * g;
-                    unsigned char* qrow = reinterpret_cast<unsigned char*>(b + (size_t)a.BS) + (size_t)f * a.Pq;
-                    unsigned char* qb = wq ? (qrow + 3 * g) : nullptr;
-                    if (wq && g == NG - 1) {           // pad bytes P .. Pq of this frame row are zero in all four planes
-                        for (int o = P; o < a.Pq; ++o) { qrow[o] = 0; qrow[a.QS + o] = 0; qrow[2 * a.QS + o] = 0; qrow[3 * a.QS + o] = 0; }
-                    }
+                    unsigned char* qb = wq ? (reinterpret_cast<unsigned char*>(b + (size_t)a.BS) + (size_t)f * 16) : nullptr;
                     SS_DISPATCH_K(r, (ss_group<K_>(dsp, ysp, Tp + 3 * g, VC_s + (size_t)fg * SS_KC, R, P, inv_mu, mu_f, lamq, a.mode,
-                                                   zz_acc, nnz_acc, max_acc, qb, a.QS, 0, inv_mu_next, Qf, wmax_acc, sat_acc)));
+                                                   zz_acc, nnz_acc, max_acc, qb, a.QS, 3 * g, FC * 16, inv_mu_next, Qf, wmax_acc, sat_acc)));
                 }
                 fence_proxy_async_smem();                   // my writes -> visible to the storer's TMA stores
                 __syncwarp();
@@ -425,7 +423,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
 // -------------------------------------------------------------------------------------------------------------
 static size_t ss_smem_bytes(int n, int R, int FC, int NS, int NTC) {
     const int P = 3 * R, NQ = P / 4, NFL = NTC / NQ;
-    const size_t bs = ((size_t)FC * ((P + 15) / 16 * 16) + 127) / 128 * 128;
+    const size_t bs = ((size_t)FC * P + 127) / 128 * 128;
     size_t fl = (size_t)NS * 3 * bs + (size_t)NFL * SS_KRED * P + (size_t)SS_KC * P + (size_t)2 * n * SS_KC;
     return fl * sizeof(float) + (size_t)3 * NS * sizeof(uint64_t) + 64;
 }
@@ -453,7 +451,7 @@ bool make_shrink_stream_plan(int n, int rows, int cols, long long ld, int num_sm
         while (NS >= 3 && ss_smem_bytes(n, R, FC, NS, NTC) > SS_SMEM_CAP) --NS;
         if (NS < 3) continue;
         p.R = R; p.P = 3 * R; p.FC = FC; p.NS = NS; p.NCW = NCW;
-        p.bufstride = (int)(((size_t)FC * ((p.P + 15) / 16 * 16) + 127) / 128 * 128);
+        p.bufstride = (int)(((size_t)FC * p.P + 127) / 128 * 128);
         p.smem_bytes = ss_smem_bytes(n, R, FC, NS, NTC);
         p.nchunkf = (n + FC - 1) / FC;
         p.ntile_r = (rows + R - 1) / R;
@@ -482,14 +480,16 @@ int make_shrink_stream_maps(const ShrinkStreamPlan& p, const float* D, float* S,
 }
 
 // slice matrix Wq: int8 [4][n][ldq], pixel order tile-major (tile tl of the shrink pass owns bytes [tl*P, tl*P + P) of every row)
-long long shrink_stream_ldq(const ShrinkStreamPlan& p) { return ((p.ntiles * (long long)((p.P + 15) / 16 * 16)) + 63) / 64 * 64; }
+// pixels per frame in the slice matrix (tile-major pixel order); 0 when the tile width does not split into 16-byte k-blocks
+long long shrink_stream_ldq(const ShrinkStreamPlan& p) { return (p.P % 16 == 0) ? ((p.ntiles * (long long)p.P) + 63) / 64 * 64 : 0; }
 
 int make_shrink_stream_qmap(const ShrinkStreamPlan& p, signed char* Wq, ShrinkTmaMaps* m) {
     const long long ldq = shrink_stream_ldq(p);
-    const uint64_t dims[3] = {(uint64_t)ldq, (uint64_t)p.n, 4};
-    const uint64_t strides[2] = {(uint64_t)ldq, (uint64_t)ldq * (uint64_t)p.n};
-    const uint32_t box[3] = {(uint32_t)((p.P + 15) / 16 * 16), (uint32_t)p.FC, 1};
-    if (make_tensor_map_u8(&m->Q, Wq, 3, dims, strides, box, 0) != 0) return -1;
+    // [slice][k16][frame][16 B]; a tile's chunk of FC frames is one box {16, FC, P/16, 1} per plane
+    const uint64_t dims[4] = {16, (uint64_t)p.n, (uint64_t)(ldq / 16), 4};
+    const uint64_t strides[3] = {16, (uint64_t)16 * p.n, (uint64_t)ldq * (uint64_t)p.n};
+    const uint32_t box[4] = {16, (uint32_t)p.FC, (uint32_t)(p.P / 16), 1};
+    if (make_tensor_map_u8(&m->Q, Wq, 4, dims, strides, box, 0) != 0) return -1;
     m->has_Q = true;
     return 0;
 }
@@ -515,8 +515,8 @@ int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, S
     a.R = p.R; a.P = p.P; a.NQ = p.P / 4; a.NFL = (32 * p.NCW) / a.NQ; a.FC = p.FC; a.NS = p.NS; a.BS = p.bufstride;
     a.nchunkf = p.nchunkf; a.ntile_r = p.ntile_r; a.ntiles = p.ntiles; a.st = st; a.part_zz = b.part_zz; a.part_nnz = b.part_nnz;
     a.part_max = b.part_max; a.part_wmax = b.part_wmax; a.mode = mode;
-    a.wq = (maps.has_Q && b.part_wmax != nullptr) ? 1 : 0; a.Pq = (p.P + 15) / 16 * 16;
-    a.QS = (int)(((size_t)p.FC * a.Pq + 127) / 128 * 128);
+    a.wq = (maps.has_Q && b.part_wmax != nullptr) ? 1 : 0; a.Pq = p.P;
+    a.QS = (int)(((size_t)p.FC * p.P + 127) / 128 * 128);
     if (p.NCW == 16) return launch_ss<16>(p, maps, a, mode, stream);
     return launch_ss<8>(p, maps, a, mode, stream);
 }

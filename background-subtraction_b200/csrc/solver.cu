@@ -51,7 +51,7 @@ struct bsub_solver {
     ShrinkPlan sp; ShrinkTmaPlan stp; ShrinkTmaMaps stmaps; bool use_tma = false, stmaps_ready = false;
     ShrinkStreamPlan ssp; ShrinkTmaMaps ssmaps; bool use_stream = false;
     // int8 tcgen05 Gram from the W slices written by the streamed shrink pass
-    bool use_i8 = false; signed char* Wq = nullptr; unsigned long long* Gint = nullptr; GramI8Plan gip; CUtensorMap gimap;
+    bool use_i8 = false; signed char* Wq = nullptr; unsigned long long* Gint = nullptr; GramI8Plan gip; CUtensorMap gimap, gimap_last;
     int4* gi_info = nullptr; int* gi_blkn = nullptr; int gi_ncta = 0; float* part_wmax = nullptr;
     float* tpart = nullptr; double* part_zz = nullptr; unsigned long long* part_nnz = nullptr;
     float* part_max = nullptr;
@@ -185,7 +185,7 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
         ALLOC(s->part_max, sizeof(float) * nparts);
         cudaMemset(s->part_zz, 0, sizeof(double) * nparts); cudaMemset(s->part_nnz, 0, sizeof(unsigned long long) * nparts);
         cudaMemset(s->part_max, 0, sizeof(float) * nparts);
-        s->use_i8 = s->use_stream && (getenv("BSUB_NO_I8") == nullptr) && (s->cfg.m_global == s->m) &&
+        s->use_i8 = s->use_stream && (shrink_stream_ldq(s->ssp) > 0) && (getenv("BSUB_NO_I8") == nullptr) && (s->cfg.m_global == s->m) &&
                     (cfg->prox == BSUB_PROX_FLAT_LINF || cfg->prox == BSUB_PROX_L1);
         if (s->use_i8) {
             const long long ldq = shrink_stream_ldq(s->ssp);
@@ -202,7 +202,8 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
             cudaMemcpy(s->gi_info, info.data(), sizeof(int4) * info.size(), cudaMemcpyHostToDevice);
             cudaMemcpy(s->gi_blkn, blkn.data(), sizeof(int) * blkn.size(), cudaMemcpyHostToDevice);
             cudaMemset(s->part_wmax, 0, sizeof(float) * s->ssp.grid);
-            if (make_gram_i8_map(s->gip, s->Wq, &s->gimap) != 0) { rc = -1; break; }
+            if (make_gram_i8_map(s->gip, s->Wq, &s->gimap, 128) != 0) { rc = -1; break; }
+            if (make_gram_i8_map(s->gip, s->Wq, &s->gimap_last, gram_i8_last_block_n(s->gip)) != 0) { rc = -1; break; }
         }
         for (int i = 0; i <= kRunAhead; ++i)
             if (cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming) != cudaSuccess) { set_error("bsub_create: event"); rc = -1; break; }
@@ -432,7 +433,7 @@ int bsub_step_gram(bsub_solver* s, void* stream) {
     // both Gram kernels are enqueued; DevState.gram_mode (set on the device) decides which one does the work
     RET_IF(launch_gram(s->gp, s->gmaps, true, s->tasks_dev, s->st, 0.f, s->gram_partial, s->comm_sum, as_stream(stream)));
     if (s->use_i8)
-        RET_IF(launch_gram_i8(s->gip, s->gimap, s->gi_info, s->gi_ncta, s->gi_blkn, s->Gint, s->comm_sum, s->npad, s->st, 0.0, 1,
+        RET_IF(launch_gram_i8(s->gip, s->gimap, s->gimap_last, s->gi_info, s->gi_ncta, s->gi_blkn, s->Gint, s->comm_sum, s->npad, s->st, 0.0, 1,
                               as_stream(stream)));
     return 0;
 }
@@ -790,12 +791,20 @@ int bsub_gram_i8_test(const int8_t* slices_host, int32_t n, int64_t ldq, int64_t
     CK(cudaMalloc((void**)&blkn_d, sizeof(int) * blkn.size()));
     CK(cudaMalloc((void**)&Gint, sizeof(unsigned long long) * gn * gn));
     CK(cudaMalloc((void**)&G, sizeof(double) * (size_t)npad * npad));
-    CK(cudaMemcpy(q, slices_host, qbytes, cudaMemcpyHostToDevice));
+    {   // repack [4][n][ldq] (row-major, as the caller gives it) into the k-block-major layout [4][ldq/16][n][16]
+        std::vector<signed char> packed(qbytes);
+        for (int sl = 0; sl < 4; ++sl)
+            for (int f = 0; f < n; ++f)
+                for (long long k = 0; k < ldq / 16; ++k)
+                    memcpy(&packed[(((size_t)sl * (ldq / 16) + k) * n + f) * 16], &slices_host[((size_t)sl * n + f) * ldq + k * 16], 16);
+        CK(cudaMemcpy(q, packed.data(), qbytes, cudaMemcpyHostToDevice));
+    }
     CK(cudaMemcpy(info_d, info.data(), sizeof(int4) * info.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(blkn_d, blkn.data(), sizeof(int) * blkn.size(), cudaMemcpyHostToDevice));
-    CUtensorMap map;
-    int rc = make_gram_i8_map(gp, q, &map);
-    if (rc == 0) rc = launch_gram_i8(gp, map, info_d, (int)info.size(), blkn_d, Gint, G, npad, nullptr, 1.0, 1, 0);
+    CUtensorMap map, map_last;
+    int rc = make_gram_i8_map(gp, q, &map, 128);
+    if (rc == 0) rc = make_gram_i8_map(gp, q, &map_last, gram_i8_last_block_n(gp));
+    if (rc == 0) rc = launch_gram_i8(gp, map, map_last, info_d, (int)info.size(), blkn_d, Gint, G, npad, nullptr, 1.0, 1, 0);
     if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) { set_error("bsub_gram_i8_test: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
     if (rc == 0) {
         std::vector<long long> tmp(gn * gn);
