@@ -187,15 +187,14 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
                 const int e = c * 3 + dr, o = c * R + dr;
                 const float wn = fmaf(ysp[o], inv_mu_next, dv[e] - dsp[o]);
                 wmax_acc = fmaxf(wmax_acc, fabsf(wn));
-                float wq = wn * Qf;
-                if (!(fabsf(wq) < 2130706432.f)) { sat_acc = 1; wq = fminf(fmaxf(wq, -2130706432.f), 2130706432.f); }   // |q| <= 2^31 - 2^24
-                int q = __float2int_rn(wq);
-                const int d0 = (q << 24) >> 24; q = (q - d0) >> 8;
-                const int d1 = (q << 24) >> 24; q = (q - d1) >> 8;
-                const int d2 = (q << 24) >> 24; q = (q - d2) >> 8;
+                // cvt saturates; a clipped value is detected afterwards through wmax (the slices are then discarded)
+                const int q = __float2int_rn(wn * Qf);
+                // balanced base-256 digits in one go: byte k of ((q + 0x808080) ^ 0x808080) is d_k as a signed byte
+                const unsigned int u = ((unsigned int)q + 0x00808080u) ^ 0x00808080u;
                 // stage layout per plane: [k16 block of the tile][frame][16 B]  (k-block-major, see gram_i8.cu)
                 const int po = ((o0 + o) >> 4) * kstep + ((o0 + o) & 15);
-                qb[po] = (unsigned char)d0; qb[QS + po] = (unsigned char)d1; qb[2 * QS + po] = (unsigned char)d2; qb[3 * QS + po] = (unsigned char)q;
+                qb[po] = (unsigned char)u; qb[QS + po] = (unsigned char)(u >> 8); qb[2 * QS + po] = (unsigned char)(u >> 16);
+                qb[3 * QS + po] = (unsigned char)(u >> 24);
             }
     }
 }
@@ -416,6 +415,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
     double mt = block_max((double)max_acc, redd);
     if (threadIdx.x == 0) a.part_max[blockIdx.x] = (float)mt;
     // max |W_next| (+ a large sentinel if a slice was clipped) for the fixed-point scale of the following pass
+    if (wq && !(wmax_acc * Qf < 2130706432.f)) sat_acc = 1;              // |q| must stay <= 2^31 - 2^24
     double wt = block_max((double)(sat_acc ? 3.0e38f : wmax_acc), redd);
     if (threadIdx.x == 0 && a.part_wmax != nullptr) a.part_wmax[blockIdx.x] = wq ? (float)wt : -1.f;
 }

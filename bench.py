@@ -229,9 +229,23 @@ def main():
         else:
             ev[name].append((pending.pop(name), e))
 
+    marks = []
+
+    def mark(tag):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        marks.append((tag, e))
+
     def one_step(timed):
+        if timed:
+            mark('start')
         driver.solve(hooks if timed else None)
-        return driver.finish(2.0, want_mask=True)
+        if timed:
+            mark('solved')
+        out = driver.finish(2.0, want_mask=True)
+        if timed:
+            mark('finished')
+        return out
 
     def barrier():
         if world > 1:
@@ -264,6 +278,12 @@ def main():
         v = [a.elapsed_time(b) for a, b in ev[name]]
         return (float(np.mean(v)) if v else 0.0), len(v)
 
+    # coarse breakdown of a step: solve (init + loop) vs finish (L + mask)
+    seg = {}
+    for (t0, e_0), (t1, e_1) in zip(marks[:-1], marks[1:]):
+        if t0 != 'finished':
+            seg.setdefault(t0 + '->' + t1, []).append(e_0.elapsed_time(e_1))
+    breakdown = {k: float(np.mean(v)) for k, v in seg.items()}
     gram_ms, n_gram = phase_ms("gram")
     solve_ms, n_solve = phase_ms("solve")
     shrink_ms, n_shrink = phase_ms("shrink")
@@ -350,7 +370,8 @@ def main():
            "alm_iters": iters, "converged": bool(st.converged), "rank_L": int(st.svp), "err": float(st.err),
            "mask_fraction": float(mask.float().mean().item()),
            "kernels": kern, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
-           "clocks": clocks, "datagen_s": t_gen}
+           "clocks": clocks, "datagen_s": t_gen, "breakdown_ms": breakdown,
+           "iters_enqueued": driver.iters_enqueued}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
