@@ -273,6 +273,14 @@ class Decomposition:
         C.check(self.lib.bsub_poll(self.h, ctypes.byref(st)))
         return st
 
+    def debug_info(self):
+        """Which kernel paths this solver uses (TMA / streamed shrink / int8 tcgen05 Gram) and their tile shapes."""
+        out = (ctypes.c_int32 * 12)()
+        C.check(self.lib.bsub_debug_info(self.h, out))
+        keys = ["use_tma", "use_stream", "use_i8", "stream_R", "stream_FC", "stream_NS", "gram_types", "gram_kc", "eig_cluster",
+                "tma_R", "tma_Cf", "ld"]
+        return dict(zip(keys, [int(v) for v in out]))
+
     def log(self):
         buf = (C.IterLog * 512)()
         cnt = ctypes.c_int32(0)

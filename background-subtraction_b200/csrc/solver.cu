@@ -599,6 +599,14 @@ int bsub_download_f64(bsub_solver* s, int which, double* dst, int64_t ld, void* 
     return rc;
 }
 
+int bsub_debug_info(bsub_solver* s, int32_t* o) {
+    if (!s || !o) { set_error("bsub_debug_info: null argument"); return -1; }
+    o[0] = s->use_tma; o[1] = s->use_stream; o[2] = s->use_i8; o[3] = s->use_stream ? s->ssp.R : 0; o[4] = s->use_stream ? s->ssp.FC : 0;
+    o[5] = s->use_stream ? s->ssp.NS : 0; o[6] = s->gp.ntype; o[7] = s->gp.kc; o[8] = s->ep.C; o[9] = s->use_tma ? s->stp.R : s->sp.R;
+    o[10] = s->use_tma ? s->stp.Cf : s->sp.Cf; o[11] = (int32_t)s->ld;
+    return 0;
+}
+
 int bsub_debug_eig_cycles(bsub_solver* s, int64_t* out8) {
     if (!s || !out8) { set_error("bsub_debug_eig_cycles: null argument"); return -1; }
     DevState h;

@@ -227,7 +227,7 @@ def main():
         if phase == 'begin':
             pending[name] = e
         else:
-            ev[name].append((pending.pop(name), e))
+            ev[name][-1].append((pending.pop(name), e))
 
     marks = []
 
@@ -239,6 +239,8 @@ def main():
     def one_step(timed):
         if timed:
             mark('start')
+            for k in ev:
+                ev[k].append([])                      # one event list per timed step
         driver.solve(hooks if timed else None)
         if timed:
             mark('solved')
@@ -274,8 +276,11 @@ def main():
     st = solver.status()
     iters = int(st.iter)
 
-    def phase_ms(name):
-        v = [a.elapsed_time(b) for a, b in ev[name]]
+    info = solver.dec.debug_info()
+
+    def phase_ms(name, first=0):
+        # only the `iters` real ALM iterations of every step (the host enqueues up to run_ahead extra ones, which exit at once)
+        v = [a.elapsed_time(b) for step in ev[name] for a, b in step[first:iters]]
         return (float(np.mean(v)) if v else 0.0), len(v)
 
     # coarse breakdown of a step: solve (init + loop) vs finish (L + mask)
@@ -284,11 +289,16 @@ def main():
         if t0 != 'finished':
             seg.setdefault(t0 + '->' + t1, []).append(e_0.elapsed_time(e_1))
     breakdown = {k: float(np.mean(v)) for k, v in seg.items()}
-    gram_ms, n_gram = phase_ms("gram")
+    use_i8 = bool(info["use_i8"])
+    gram_first_ms = float(np.mean([s[0][0].elapsed_time(s[0][1]) for s in ev["gram"] if s])) if ev["gram"] else 0.0
+    gram_ms, n_gram = phase_ms("gram", 1 if use_i8 else 0)      # with the int8 path the first iteration is the fp64 DMMA Gram
     solve_ms, n_solve = phase_ms("solve")
     shrink_ms, n_shrink = phase_ms("shrink")
-    launches_per_iter = 2 + 1 + 1 + 2          # gram + reduce, eig, shrink, control x2
-    gpu_launches = int(args.steps * (iters * launches_per_iter + 2 + 1 + 1 + 1 + 1 + 2 + 1))
+    # kernels launched per enqueued iteration: gram_dmma, gram_reduce, (gram_i8, gram_i8_finish), eig, shrink_stream /
+    # shrink_tma / shrink (whichever exist), control_post x2; per step: rowsum, gram_dmma, gram_reduce, eig, init_Y, lowrank,
+    # absmax, mask_stats, mask_write
+    per_iter = 2 + (2 if use_i8 else 0) + 1 + (2 if info["use_stream"] else 1) + 2
+    gpu_launches = int(args.steps * (driver.iters_enqueued * per_iter + 9))
 
     # ---- end to end through the public host-buffer API (single GPU only) ----
     e2e = None
@@ -329,15 +339,23 @@ def main():
     # ---- roofline of the dominant kernel (per launch, algorithmic bytes) ----
     peak, peak_src = measured_peaks()
     elems_local = float(frames) * m_local
+    shrink_name = "shrink_stream_kernel" if info["use_stream"] else ("shrink_tma_kernel" if info["use_tma"] else "shrink_kernel")
+    gram_name = "gram_i8_kernel" if use_i8 else "gram_dmma_kernel"
+    # algorithmic bytes per matrix element: shrink reads D,S,Y and writes S,Y (20 B) plus the four
+    # int8 slices of the next W (4 B) when the tcgen05 Gram is on; the Gram then reads those 4 B instead of D,S,Y (12 B)
     kern = {
-        "shrink_kernel": {"ms": shrink_ms, "launches": n_shrink, "alg_bytes": 20.0 * elems_local, "bound": "hbm"},
-        "gram_dmma_kernel": {"ms": gram_ms, "launches": n_gram, "alg_bytes": 12.0 * elems_local, "bound": "hbm"},
+        shrink_name: {"ms": shrink_ms, "launches": n_shrink, "alg_bytes": (24.0 if use_i8 else 20.0) * elems_local, "bound": "hbm"},
+        gram_name: {"ms": gram_ms, "launches": n_gram, "alg_bytes": (4.0 if use_i8 else 12.0) * elems_local,
+                    "bound": "hbm" if use_i8 else "fp64 tensor pipe"},
         "eig_kernel": {"ms": solve_ms, "launches": n_solve, "alg_bytes": 8.0 * frames * frames, "bound": "latency"},
     }
+    if use_i8:
+        kern["gram_dmma_kernel (iteration 1 only)"] = {"ms": gram_first_ms, "launches": args.steps, "alg_bytes": 12.0 * elems_local,
+                                                      "bound": "fp64 tensor pipe"}
     for k in kern.values():
         k["gbs"] = (k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9) if k["ms"] > 0 else 0.0
         k["share"] = (k["ms"] * k["launches"]) / (ms_step * args.steps) if ms_step > 0 else 0.0
-    dom = max(("shrink_kernel", "gram_dmma_kernel"), key=lambda n: kern[n]["ms"] * kern[n]["launches"])
+    dom = max((shrink_name, gram_name), key=lambda n: kern[n]["ms"] * kern[n]["launches"])
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
@@ -363,10 +381,12 @@ def main():
 
     out = {"metric": "frames/s decomposed", "value": frames / (ms_step * 1e-3), "unit": "frames/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-           "scaling": "strong", "vs_baseline": None, "dtype": "f32 storage / f64 Gram+eigensolve", "data": "synthetic",
+           "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32 (state) / exact int8-slice Gram on tcgen05 + f64 eigensolve" if use_i8 else "f32 (state) / f64 Gram + eigensolve",
+           "data": "synthetic",
            "config": {"workload": args.workload, "rows": rows, "cols": cols, "frames": frames, "prox": "flat 3x3 l_inf (LSD)",
                       "delta": 10, "sharding": f"pixel columns over {world} GPU(s)", "l2": "inputs (2.5 GB/matrix) larger than L2",
-                      "tile_rows": solver.dec.cfg.tile_rows, "cluster_frames": solver.dec.cfg.cluster_frames},
+                      "tile_rows": info["stream_R"] if info["use_stream"] else solver.dec.cfg.tile_rows, "paths": info},
            "alm_iters": iters, "converged": bool(st.converged), "rank_L": int(st.svp), "err": float(st.err),
            "mask_fraction": float(mask.float().mean().item()),
            "kernels": kern, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,

@@ -128,6 +128,8 @@ int bsub_download_f32(bsub_solver* s, int which, float* dst_host, int64_t ld, vo
 int bsub_get_log(bsub_solver* s, bsub_iter_log* out, int32_t cap, int32_t* count);
 /* diagnostics: SM clock at the phase boundaries of the last eigensolve (load, tridiag, eigenvalues, vectors, reorth, back-transform) */
 int bsub_debug_eig_cycles(bsub_solver* s, int64_t* out8);
+/* diagnostics: kernel paths chosen for this solver: use_tma, use_stream, use_i8, stream R/FC/NS, gram types/kc, eig cluster, tma R/Cf, ld */
+int bsub_debug_info(bsub_solver* s, int32_t* out12);
 /* foreground_mask(D, L, S, sigmas) of utils.py:139-149 on the solver's own D, L, S; mask uint8[n][m] on the host */
 int bsub_mask_stats_local(bsub_solver* s, int phase /*0: max|S|, 1: count/sum/sumsq*/, void* stream);
 int bsub_mask_host(bsub_solver* s, double sigmas, uint8_t* mask_host, void* stream);
