@@ -38,7 +38,7 @@ struct DevState {
     int converged;
     int max_iter, round005d, d, use_sv_prediction, break_on_rank0;
     int eig_info;           // diagnostics of the eigen solver (bisection rounds etc.)
-    long long eig_clk[8];   // clock64() at the phase boundaries of the last eig_kernel (CTA 0)
+    long long eig_clk[16];  // [0..5] clock64() at the phase boundaries of the last eig_kernel (CTA 0); [8..13] cycles per tridiagonalisation sub-phase
     // int8 (tcgen05) Gram path: W of the NEXT iteration is written by the shrink pass as 32-bit fixed point
     double wq_scale;        // S: q = rint(W * 2^31 / S), power of two
     double wq_scale_next;   // S for the slices the coming shrink pass writes

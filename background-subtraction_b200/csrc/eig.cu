@@ -34,6 +34,7 @@ struct EigArgs {
     const double* G;           // [npad][npad]
     const double* comm_max;    // [0] = max row-sum of |D| (init mode)
     int n, npad, C, rows_per, in_smem, kcap, mode, k_override;
+    int tail_off;              // doubles from the start of dynamic shared memory to the [3][n] exchange buffers
     double* Aglob;             // [C][rows_per][n]  (only when !in_smem)
     double* Vh;                // [n][n] reflectors
     double* tau;               // [n]
@@ -49,6 +50,11 @@ struct EigArgs {
 };
 
 __device__ __forceinline__ double ldcg_d(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ double warp_allsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 
 // number of eigenvalues of the tridiagonal (d, e2 = e^2) that are < x: sign changes of the Sturm sequence
 //   p_0 = 1, p_1 = d_0 - x, p_i = (d_{i-1} - x) p_{i-1} - e2_{i-2} p_{i-2}
@@ -78,13 +84,74 @@ __device__ __forceinline__ double hash_unit(unsigned a, unsigned b) {
     return ((double)(x & 0xFFFFFFu) / (double)0x1000000u) * 2.0 - 1.0;
 }
 
+// ---- control that follows the eigensolve (runs in CTA 0).  lam_scale: the stored eigenvalues are those of G / lam_scale
+//      (first iteration of the int8 path: G_1 = c^2 Gram(D), whose eigenpairs the initialisation already produced).
+__device__ void eig_control(const EigArgs& a, DevState* st, int K, double mu, double lam_scale, double* red, double* bc) {
+    const int n = a.n, tid = threadIdx.x;
+    if (a.mode == 2) return;
+    if (a.mode == 0) {
+        double tr = 0.0;
+        for (int i = tid; i < n; i += EIG_THREADS) tr += a.G[(size_t)i * a.npad + i];
+        tr = block_sum(tr, red);
+        if (tid == 0) {
+            const double l0 = a.lam[0];
+            const double norm_two = sqrt(fmax(l0, 0.0));
+            st->norm_two = norm_two;
+            st->normD2 = tr;
+            st->norm_rowsum = a.comm_max[0];
+            st->dual_norm = fmax(norm_two, a.comm_max[0] / st->lambda);
+            st->mu = st->mu_scale / norm_two;
+            st->thresh = 1.0 / st->mu;
+            st->iter = 0; st->svp = 0; st->done = 0; st->converged = 0; st->zz = 0.0; st->err = 0.0;
+            st->maxS = 0.f; st->nnzS = 0ull;
+            // int8 Gram path: W_1 = c D, so iteration 1 reuses this eigen-decomposition (gram_mode 2);
+            // |W_1| <= 1.08 max|D| (Y0/mu0 <= D/12.5)
+            st->gram_mode = st->use_i8 ? 2 : 0; st->wq_saturated = 0; st->wmax = 1.08 * a.comm_max[2];
+            st->wq_scale = 0.0;
+            st->wq_scale_next = (a.comm_max[2] > 0.0) ? exp2(ceil(log2(4.0 * 1.08 * a.comm_max[2]))) : 1.0;
+            if (!(norm_two > 0.0)) { st->done = 4; }       // all-zero input
+        }
+        return;
+    }
+    // mode 1
+    const double thresh = 1.0 / mu;
+    if (tid == 0) {
+        int svp = 0;
+        for (int k = 0; k < K; ++k) {
+            double sig = sqrt(fmax((a.lam[k] * lam_scale), 0.0));
+            if (sig > thresh) svp = k + 1;               // last index with sigma > 1/mu (utils.py:215-217)
+        }
+        const int sv = K;
+        st->iter += 1;
+        st->sv_used = sv;                                // sv looked at this iteration
+        st->svp = svp;
+        st->thresh = thresh;
+        int svn = sv;
+        if (st->use_sv_prediction) svn = (svp < sv) ? svp + 1 : min(svp + st->round005d, st->d);
+        st->sv = svn;                                    // inexact_alm_lsd.py:145
+        if (st->break_on_rank0 && svp == 0) st->done = 3;  // group_sparse_RPCA.py:91-93
+        bc[0] = (double)svp;
+    }
+    __syncthreads();
+    const int svp = (int)bc[0];
+    for (int idx = tid; idx < n * svp; idx += EIG_THREADS) {
+        const int f = idx / svp, k = idx - f * svp;
+        const double sig = sqrt(fmax((a.lam[k] * lam_scale), 0.0));
+        const double z = a.Z[(size_t)k * n + f];
+        a.Vr[(size_t)f * a.vstride + k] = (float)z;
+        a.VC[(size_t)f * a.vstride + k] = (float)(z * (1.0 - thresh / sig));
+    }
+}
+
 __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
     DevState* st = a.st;
     if (a.mode == 1 && st->done) return;          // uniform over the cluster
     const int n = a.n, C = a.C, c = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int K = (a.mode == 0) ? 1 : ((a.mode == 1) ? st->sv : a.k_override);
+    // int8 path: the initialisation also produces the sv0 leading eigenpairs, which iteration 1 reuses (W_1 = c D)
+    int K = (a.mode == 0) ? (st->use_i8 ? st->sv : 1) : ((a.mode == 1) ? st->sv : a.k_override);
+    const bool reuse = (a.mode == 1) && (st->gram_mode == 2);
     if (K > n) K = n;
     if (K < 1) K = 1;
     const double mu = (a.mode == 1) ? st->mu : 0.0;
@@ -100,6 +167,13 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
         return a.in_smem ? (Asm + (size_t)li * n) : (a.Aglob + ((size_t)c * a.rows_per + li) * n);
     };
 
+    if (reuse) {
+        if (c != 0) return;
+        // W_1 = fma(Y0, 1/mu, D) with Y0 = D / dual_norm  ->  G_1 = c^2 Gram(D)
+        const double cc = 1.0 + (1.0 / st->dual_norm) * (double)(float)(1.0 / mu);
+        eig_control(a, st, K, mu, cc * cc, red, bc);
+        return;
+    }
     if (c == 0 && tid == 0) st->eig_clk[0] = clock64();
     // ---- load my rows -------------------------------------------------------------------------------------
     for (int li = warp; li < a.rows_per; li += EIG_WARPS) {
@@ -113,67 +187,164 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
     __syncthreads();
 
     // ---- 1. Householder tridiagonalisation ------------------------------------------------------------------
-    for (int j = 0; j + 2 < n; ++j) {
-        const int par = j & 1;
-        if (c == (j % C)) {
-            const double* r = Arow(j / C);
-            double ss = 0.0;
-            for (int i = j + 2 + tid; i < n; i += EIG_THREADS) ss += r[i] * r[i];
-            ss = block_sum(ss, red);
-            if (tid == 0) {
-                double alpha = r[j + 1];
-                double beta, tau, scale;
-                if (ss == 0.0) { tau = 0.0; beta = alpha; scale = 0.0; }
-                else {
-                    beta = -copysign(sqrt(alpha * alpha + ss), alpha);
-                    tau = (beta - alpha) / beta;
-                    scale = 1.0 / (alpha - beta);
-                }
-                bc[0] = scale;
-                a.tau[j] = tau; a.dd[j] = r[j]; a.ee[j] = beta;
-            }
-            __syncthreads();
-            const double scale = bc[0];
-            double* vh = a.Vh + (size_t)j * n;
-            for (int i = j + 1 + tid; i < n; i += EIG_THREADS) vh[i] = (i == j + 1) ? 1.0 : r[i] * scale;
+    if (a.in_smem) {
+        // Rows live in shared memory, dealt cyclically over the cluster.  Both exchanges of a step go through
+        // distributed shared memory: (1) after its rank-2 update every CTA pushes its entries of the next column
+        // into all CTAs, so everyone forms the reflector redundantly; (2) every CTA pushes its slice of p = tau A v
+        // into all CTAs.  Two hardware cluster barriers per step, no global-memory round trip on the critical path.
+        const int cshift = 31 - __clz(C), cmask = C - 1;      // C is a power of two (make_eig_plan)
+        double* xb = esm + a.tail_off;       // [2][n] column j of the current matrix, by parity of j
+        double* pb = xb + 2 * n;             // [n]    p = tau * A v
+        double* xb_rem = (lane < C) ? cluster.map_shared_rank(xb, lane) : nullptr;
+        double* pb_rem = (lane < C) ? cluster.map_shared_rank(pb, lane) : nullptr;
+        for (int li = warp; li < a.rows_per; li += EIG_WARPS) {
+            const int i = c + li * C;
+            if (i >= 1 && i < n) { const double val = Arow(li)[0]; if (lane < C) xb_rem[i] = val; }
         }
         cluster.sync();
-        const double tau = ldcg_d(a.tau + j);
-        if (tau != 0.0) {
-            const double* vh = a.Vh + (size_t)j * n;
-            for (int i = tid; i < n; i += EIG_THREADS) v_s[i] = (i > j) ? ldcg_d(vh + i) : 0.0;
+        long long tph[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();
+#define EIG_TICK(k) { const long long t_ = clock64(); tph[k] += t_ - tc; tc = t_; }
+        for (int j = 0; j + 2 < n; ++j) {
+            const int par = j & 1;
+            const double* x = xb + par * n;
+            // reflector from column j (every warp redundantly: no block-level reduction)
+            double ssl = 0.0;
+            for (int i = j + 2 + lane; i < n; i += 32) ssl = fma(x[i], x[i], ssl);
+            const double ss = warp_allsum(ssl);
+            const double alpha = x[j + 1];
+            double beta, tau, scale;
+            if (ss == 0.0) { tau = 0.0; beta = alpha; scale = 0.0; }
+            else {
+                beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
+                tau = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            for (int i = tid; i < n; i += EIG_THREADS) v_s[i] = (i > j) ? ((i == j + 1) ? 1.0 : x[i] * scale) : 0.0;
+            if (c == (j & cmask)) {
+                double* vh = a.Vh + (size_t)j * n;
+                for (int i = j + 1 + tid; i < n; i += EIG_THREADS) vh[i] = (i == j + 1) ? 1.0 : x[i] * scale;
+                if (tid == 0) { a.tau[j] = tau; a.dd[j] = Arow(j >> cshift)[j]; a.ee[j] = beta; }
+            }
             __syncthreads();
-            double pv = 0.0;
-            for (int li = warp; li < a.rows_per; li += EIG_WARPS) {
-                int i = c + li * C;
-                if (i > j && i < n) {
-                    const double* r = Arow(li);
-                    double s = 0.0;
-                    for (int col = j + 1 + lane; col < n; col += 32) s += r[col] * v_s[col];
-                    s = warp_sum(s);
-                    double p = tau * s;
-                    if (lane == 0) { a.pbuf[par * n + i] = p; pv += p * v_s[i]; }
+            EIG_TICK(0)
+            const int l0 = (j >= c) ? ((j - c) >> cshift) + 1 : 0;  // first local row with global index > j
+            for (int lb = l0 + warp; lb < a.rows_per; lb += 3 * EIG_WARPS) {
+                const int l1 = lb + EIG_WARPS, l2 = lb + 2 * EIG_WARPS;
+                const int i0 = c + lb * C, i1 = c + l1 * C, i2 = c + l2 * C;
+                const bool ok0 = i0 < n, ok1 = (l1 < a.rows_per) && i1 < n, ok2 = (l2 < a.rows_per) && i2 < n;
+                const double* r0 = Arow(lb);
+                const double* r1 = ok1 ? Arow(l1) : r0;
+                const double* r2 = ok2 ? Arow(l2) : r0;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+                for (int col = j + 1 + lane; col < n; col += 32) {
+                    const double vv = v_s[col];
+                    s0 = fma(r0[col], vv, s0); s1 = fma(r1[col], vv, s1); s2 = fma(r2[col], vv, s2);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                if (lane < C) {
+                    if (ok0) pb_rem[i0] = tau * s0;
+                    if (ok1) pb_rem[i1] = tau * s1;
+                    if (ok2) pb_rem[i2] = tau * s2;
                 }
             }
-            pv = block_sum(pv, red);
-            if (tid == 0) a.dotbuf[par * 16 + c] = pv;
-        }
-        cluster.sync();
-        if (tau != 0.0) {
-            double dot = 0.0;
-            for (int q = 0; q < C; ++q) dot += ldcg_d(a.dotbuf + par * 16 + q);
-            const double kc = -0.5 * tau * dot;
-            for (int i = tid; i < n; i += EIG_THREADS) w_s[i] = (i > j) ? (ldcg_d(a.pbuf + par * n + i) + kc * v_s[i]) : 0.0;
+            EIG_TICK(1)
+            cluster.sync();
+            EIG_TICK(2)
+            double dl = 0.0;
+            for (int i = j + 1 + lane; i < n; i += 32) dl = fma(pb[i], v_s[i], dl);
+            const double kc = -0.5 * tau * warp_allsum(dl);
+            for (int i = tid; i < n; i += EIG_THREADS) w_s[i] = (i > j) ? fma(kc, v_s[i], pb[i]) : 0.0;
             __syncthreads();
-            for (int li = warp; li < a.rows_per; li += EIG_WARPS) {
-                int i = c + li * C;
-                if (i > j && i < n) {
+            EIG_TICK(3)
+            double* xn = xb_rem + (par ^ 1) * n;
+            for (int li = l0 + warp; li < a.rows_per; li += EIG_WARPS) {
+                const int i = c + li * C;
+                if (i < n) {
                     double* r = Arow(li);
                     const double vi = v_s[i], wi = w_s[i];
-                    for (int col = j + 1 + lane; col < n; col += 32) r[col] -= vi * w_s[col] + wi * v_s[col];
+                    double first = 0.0;
+                    for (int col = j + 1 + lane; col < n; col += 32) {
+                        const double nv = r[col] - (vi * w_s[col] + wi * v_s[col]);
+                        r[col] = nv;
+                        if (col == j + 1) first = nv;
+                    }
+                    first = __shfl_sync(0xffffffffu, first, 0);    // new A[i][j+1] = this CTA's entry of the next column
+                    if (lane < C && i > j + 1) xn[i] = first;
                 }
             }
-            __syncthreads();
+            EIG_TICK(4)
+            cluster.sync();
+            EIG_TICK(5)
+        }
+        if (c == 0 && tid == 0) for (int k = 0; k < 6; ++k) st->eig_clk[8 + k] = tph[k];
+#undef EIG_TICK
+    } else {
+        for (int j = 0; j + 2 < n; ++j) {
+            const int par = j & 1;
+            if (c == (j % C)) {
+                const double* r = Arow(j / C);
+                double ss = 0.0;
+                for (int i = j + 2 + tid; i < n; i += EIG_THREADS) ss += r[i] * r[i];
+                ss = block_sum(ss, red);
+                if (tid == 0) {
+                    double alpha = r[j + 1];
+                    double beta, tau, scale;
+                    if (ss == 0.0) { tau = 0.0; beta = alpha; scale = 0.0; }
+                    else {
+                        beta = -copysign(sqrt(alpha * alpha + ss), alpha);
+                        tau = (beta - alpha) / beta;
+                        scale = 1.0 / (alpha - beta);
+                    }
+                    bc[0] = scale;
+                    a.tau[j] = tau; a.dd[j] = r[j]; a.ee[j] = beta;
+                }
+                __syncthreads();
+                const double scale = bc[0];
+                double* vh = a.Vh + (size_t)j * n;
+                for (int i = j + 1 + tid; i < n; i += EIG_THREADS) vh[i] = (i == j + 1) ? 1.0 : r[i] * scale;
+            }
+            cluster.sync();
+            const double tau = ldcg_d(a.tau + j);
+            if (tau != 0.0) {
+                const double* vh = a.Vh + (size_t)j * n;
+                for (int i = tid; i < n; i += EIG_THREADS) v_s[i] = (i > j) ? ldcg_d(vh + i) : 0.0;
+                __syncthreads();
+                double pv = 0.0;
+                for (int li = warp; li < a.rows_per; li += EIG_WARPS) {
+                    int i = c + li * C;
+                    if (i > j && i < n) {
+                        const double* r = Arow(li);
+                        double s = 0.0;
+                        for (int col = j + 1 + lane; col < n; col += 32) s += r[col] * v_s[col];
+                        s = warp_sum(s);
+                        double p = tau * s;
+                        if (lane == 0) { a.pbuf[par * n + i] = p; pv += p * v_s[i]; }
+                    }
+                }
+                pv = block_sum(pv, red);
+                if (tid == 0) a.dotbuf[par * 16 + c] = pv;
+            }
+            cluster.sync();
+            if (tau != 0.0) {
+                double dot = 0.0;
+                for (int q = 0; q < C; ++q) dot += ldcg_d(a.dotbuf + par * 16 + q);
+                const double kc = -0.5 * tau * dot;
+                for (int i = tid; i < n; i += EIG_THREADS) w_s[i] = (i > j) ? (ldcg_d(a.pbuf + par * n + i) + kc * v_s[i]) : 0.0;
+                __syncthreads();
+                for (int li = warp; li < a.rows_per; li += EIG_WARPS) {
+                    int i = c + li * C;
+                    if (i > j && i < n) {
+                        double* r = Arow(li);
+                        const double vi = v_s[i], wi = w_s[i];
+                        for (int col = j + 1 + lane; col < n; col += 32) r[col] -= vi * w_s[col] + wi * v_s[col];
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
     // trailing 2x2 (or smaller)
@@ -434,59 +605,7 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
     __syncthreads();
 
     if (tid == 0) st->eig_clk[5] = clock64();
-    // ---- 5. control ------------------------------------------------------------------------------------------
-    if (a.mode == 2) return;
-    if (a.mode == 0) {
-        double tr = 0.0;
-        for (int i = tid; i < n; i += EIG_THREADS) tr += a.G[(size_t)i * a.npad + i];
-        tr = block_sum(tr, red);
-        if (tid == 0) {
-            const double l0 = a.lam[0];
-            const double norm_two = sqrt(fmax(l0, 0.0));
-            st->norm_two = norm_two;
-            st->normD2 = tr;
-            st->norm_rowsum = a.comm_max[0];
-            st->dual_norm = fmax(norm_two, a.comm_max[0] / st->lambda);
-            st->mu = st->mu_scale / norm_two;
-            st->thresh = 1.0 / st->mu;
-            st->iter = 0; st->svp = 0; st->done = 0; st->converged = 0; st->zz = 0.0; st->err = 0.0;
-            st->maxS = 0.f; st->nnzS = 0ull;
-            // int8 Gram path: iteration 1 uses the fp64 DMMA Gram; |W_1| <= 1.08 max|D| (Y0/mu0 <= D/12.5)
-            st->gram_mode = 0; st->wq_saturated = 0; st->wmax = 1.08 * a.comm_max[2];
-            st->wq_scale = 0.0;
-            st->wq_scale_next = (a.comm_max[2] > 0.0) ? exp2(ceil(log2(4.0 * 1.08 * a.comm_max[2]))) : 1.0;
-            if (!(norm_two > 0.0)) { st->done = 4; }       // all-zero input
-        }
-        return;
-    }
-    // mode 1
-    const double thresh = 1.0 / mu;
-    if (tid == 0) {
-        int svp = 0;
-        for (int k = 0; k < K; ++k) {
-            double sig = sqrt(fmax(a.lam[k], 0.0));
-            if (sig > thresh) svp = k + 1;               // last index with sigma > 1/mu (utils.py:215-217)
-        }
-        const int sv = K;
-        st->iter += 1;
-        st->sv_used = sv;                                // sv looked at this iteration
-        st->svp = svp;
-        st->thresh = thresh;
-        int svn = sv;
-        if (st->use_sv_prediction) svn = (svp < sv) ? svp + 1 : min(svp + st->round005d, st->d);
-        st->sv = svn;                                    // inexact_alm_lsd.py:145
-        if (st->break_on_rank0 && svp == 0) st->done = 3;  // group_sparse_RPCA.py:91-93
-        bc[0] = (double)svp;
-    }
-    __syncthreads();
-    const int svp = (int)bc[0];
-    for (int idx = tid; idx < n * svp; idx += EIG_THREADS) {
-        const int f = idx / svp, k = idx - f * svp;
-        const double sig = sqrt(fmax(a.lam[k], 0.0));
-        const double z = a.Z[(size_t)k * n + f];
-        a.Vr[(size_t)f * a.vstride + k] = (float)z;
-        a.VC[(size_t)f * a.vstride + k] = (float)(z * (1.0 - thresh / sig));
-    }
+    eig_control(a, st, K, mu, 1.0, red, bc);
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -502,7 +621,7 @@ EigPlan make_eig_plan(int n, int npad) {
     const size_t cap = 200 * 1024;
     auto bytes_for = [&](int Cc, bool in_smem) {
         size_t rows = (size_t)(n + Cc - 1) / Cc;
-        size_t mat = in_smem ? rows * n : 0;
+        size_t mat = in_smem ? rows * n + 3 * (size_t)n : 0;     // + exchange buffers of the tridiagonalisation
         size_t ph = eig_phase_doubles(n);
         return (2 * (size_t)n + 64 + (mat > ph ? mat : ph)) * sizeof(double);
     };
@@ -530,6 +649,7 @@ int launch_eig(const EigPlan& p, const double* G, const double* comm_max, EigBuf
     EigArgs a;
     a.G = G; a.comm_max = comm_max; a.n = p.n; a.npad = p.npad; a.C = p.C; a.rows_per = p.rows_per;
     a.in_smem = p.in_smem; a.kcap = p.kcap; a.mode = mode; a.k_override = k_override;
+    a.tail_off = 2 * p.n + 64 + p.rows_per * p.n;
     double* w = b.work;
     a.Aglob = w; w += (size_t)p.C * p.rows_per * p.n;
     a.Vh = w;    w += (size_t)p.n * p.n;

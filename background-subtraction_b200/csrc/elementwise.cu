@@ -72,20 +72,30 @@ int launch_init_Y(const float* D, float* Y, float* S, long long ld, int n, const
 __global__ void control_post_kernel(DevState* st, const double* part_zz, const unsigned long long* part_nnz,
                                     const float* part_max, int nparts, double* comm_tail, IterLog* log,
                                     HostMirror* mirror, int phase, const float* part_wmax, int nwmax) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (!st->done) {
-        if (phase & 1) {
-            double zz = 0.0, nz = 0.0; float mx = 0.f;
-            for (int i = 0; i < nparts; ++i) { zz += part_zz[i]; nz += (double)part_nnz[i]; mx = fmaxf(mx, part_max[i]); }
-            comm_tail[0] = zz; comm_tail[1] = nz; comm_tail[2] = (double)mx;
-            // int8 Gram bookkeeping: were slices of the next W written, and with head-room?
-            float wm = -1.f;
-            if (st->use_i8 && part_wmax != nullptr && nwmax > 0) {
-                wm = 0.f;
-                for (int i = 0; i < nwmax; ++i) { const float v = part_wmax[i]; if (v < 0.f) { wm = -1.f; break; } wm = fmaxf(wm, v); }
-            }
-            comm_tail[3] = (double)wm;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    if (!st->done && (phase & 1)) {
+        // one warp: lane-strided partial sums, then a fixed shuffle tree (deterministic for a given launch geometry)
+        double zz = 0.0, nz = 0.0; float mx = 0.f;
+        for (int i = lane; i < nparts; i += 32) { zz += part_zz[i]; nz += (double)part_nnz[i]; mx = fmaxf(mx, part_max[i]); }
+        // int8 Gram bookkeeping: were slices of the next W written (no negative marker), and with head-room?
+        float wm = 0.f; int missing = 0;
+        const bool track = st->use_i8 && part_wmax != nullptr && nwmax > 0;
+        if (track)
+            for (int i = lane; i < nwmax; i += 32) { const float v = part_wmax[i]; missing |= (v < 0.f); wm = fmaxf(wm, v); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            zz += __shfl_xor_sync(0xffffffffu, zz, o); nz += __shfl_xor_sync(0xffffffffu, nz, o);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+            missing |= __shfl_xor_sync(0xffffffffu, missing, o);
         }
+        if (lane == 0) {
+            comm_tail[0] = zz; comm_tail[1] = nz; comm_tail[2] = (double)mx;
+            comm_tail[3] = (track && !missing) ? (double)wm : -1.0;
+        }
+    }
+    if (lane != 0) return;
+    if (!st->done) {
         if (phase & 2) {
             const double zz = comm_tail[0];
             const double err = sqrt(zz / st->normD2);

@@ -215,6 +215,71 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     }
 }
 
+// ---- D -> the four int8 digit planes (initialisation: Gram(D) runs on the tensor cores too).  The planes use the natural
+// pixel order here; the Gram is a sum over pixels and does not care as long as all frames agree.
+// scale S = 2^ceil(log2(2 max|D|)) is left in st->wq_scale for gram_i8_finish_kernel.
+__global__ void __launch_bounds__(256) quantize_D_kernel(const float* __restrict__ D, long long ld, int n, long long ldq,
+                                                         signed char* __restrict__ Wq, const double* __restrict__ dmax, DevState* st) {
+    // tile = QD_F frames x QD_KB k-blocks (16 pixels each): coalesced 1 KB row reads, digits staged in shared memory,
+    // then every plane is written as runs of QD_F * 16 contiguous bytes ([k16][frame][16 B] layout)
+    constexpr int QD_F = 32, QD_KB = 16;
+    __shared__ uint4 stage[4][QD_KB][QD_F + 1];
+    const double mx = *dmax;
+    const double S = (mx > 0.0) ? exp2(ceil(log2(2.0 * mx))) : 1.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->wq_scale = S;
+    const float Qf = (float)(2147483648.0 / S);
+    const long long nkb = ldq / 16, plane = ldq * (long long)n;
+    const long long ntk = (nkb + QD_KB - 1) / QD_KB;
+    const int ntf = (n + QD_F - 1) / QD_F;
+    const long long ntiles = ntk * ntf;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long kb0 = (tile / ntf) * QD_KB;
+        const int f0 = (int)(tile % ntf) * QD_F;
+        // read: a frame's share of the tile is 16 k-blocks x 16 floats = 64 float4 (1 KB contiguous)
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+            const int idx = pass * 256 + threadIdx.x;        // 0 .. 2047 = 32 frames x 64 float4
+            const int fl = idx >> 6, q4 = idx & 63;          // frame in tile, float4 index within the 256-pixel run
+            const int f = f0 + fl;
+            const long long p = kb0 * 16 + 4 * q4;
+            float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (f < n && p < ld) d = ldg4_stream(D + (size_t)f * ld + p);
+            // balanced base-256 digits: byte k of ((q + 0x808080) ^ 0x808080) is digit k as a signed byte (shrink_stream.cu)
+            const unsigned int u0 = ((unsigned int)__float2int_rn(d.x * Qf) + 0x00808080u) ^ 0x00808080u;
+            const unsigned int u1 = ((unsigned int)__float2int_rn(d.y * Qf) + 0x00808080u) ^ 0x00808080u;
+            const unsigned int u2 = ((unsigned int)__float2int_rn(d.z * Qf) + 0x00808080u) ^ 0x00808080u;
+            const unsigned int u3 = ((unsigned int)__float2int_rn(d.w * Qf) + 0x00808080u) ^ 0x00808080u;
+            const int kbl = q4 >> 2, wq = q4 & 3;             // k-block within tile, 32-bit word within its 16 bytes
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned int sel = (unsigned int)k | ((unsigned int)(4 + k) << 4);
+                reinterpret_cast<unsigned int*>(&stage[k][kbl][fl])[wq] =
+                    __byte_perm(__byte_perm(u0, u1, sel), __byte_perm(u2, u3, sel), 0x5410);
+            }
+        }
+        __syncthreads();
+        // write: per plane and k-block a run of QD_F x 16 B
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+            const int idx = pass * 256 + threadIdx.x;        // 0 .. 2047 = 4 planes x 16 k-blocks x 32 frames
+            const int fl = idx & 31, kbl = (idx >> 5) & 15, k = idx >> 9;
+            const int f = f0 + fl;
+            const long long kb = kb0 + kbl;
+            if (f < n && kb < nkb) *reinterpret_cast<uint4*>(Wq + (size_t)k * plane + ((size_t)kb * n + f) * 16) = stage[k][kbl][fl];
+        }
+        __syncthreads();
+    }
+}
+
+int launch_quantize_D(const float* D, long long ld, int n, long long ldq, signed char* Wq, const double* dmax, DevState* st,
+                      cudaStream_t stream) {
+    const long long ntiles = ((ldq / 16 + 15) / 16) * ((n + 31) / 32);
+    const int grid = (int)std::min<long long>(ntiles, 148LL * 8);
+    quantize_D_kernel<<<grid, 256, 0, stream>>>(D, ld, n, ldq, Wq, dmax, st);
+    BSUB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 // G[i][j] (double, [npad][npad], symmetric) = Gint * scale   with  scale = S^2 * 2^-38
 __global__ void gram_i8_finish_kernel(const unsigned long long* __restrict__ Gint, int nblk, int n, int npad, double* __restrict__ G,
                                       const DevState* st, double scale_override, int require_mode) {

@@ -62,6 +62,7 @@ struct bsub_solver {
     float* eta_dev = nullptr; float* xi = nullptr; float* tot = nullptr; int* sweeps_dev = nullptr; bool graph_set = false;
     // l2 blocks
     unsigned char* labels_dev = nullptr; double* lam_table = nullptr; double* bsums = nullptr; int nlab = 0; bool blocks_set = false;
+    unsigned char* mask_stage = nullptr;      // bsub_mask_host staging
     bool loaded = false, finalized = false, initialised = false;
     cudaEvent_t ev[kRunAhead + 1];
     int iters_enqueued = 0;
@@ -97,7 +98,7 @@ int bsub_destroy(bsub_solver* s) {
     void* ptrs[] = {s->D, s->S, s->Y, s->T, s->L, s->U, s->st, s->log, s->comm_sum, s->comm_max, s->tasks_dev, s->gram_partial,
                     s->eb.work, s->eb.lam, s->eb.Z, s->eb.Vr, s->eb.VC, s->tpart, s->part_zz, s->part_nnz, s->part_max, s->gptr,
                     s->gidx, s->eta_dev, s->xi, s->tot, s->sweeps_dev, s->labels_dev, s->lam_table, s->bsums, s->Wq, s->Gint,
-                    s->gi_info, s->gi_blkn, s->part_wmax};
+                    s->gi_info, s->gi_blkn, s->part_wmax, s->mask_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->mirror) cudaFreeHost((void*)s->mirror);
     for (int i = 0; i <= kRunAhead; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -319,7 +320,8 @@ int bsub_load_D_f32_host(bsub_solver* s, const float* D, int64_t ld, void* strea
     if (!s || !D || ld < s->m) { set_error("bsub_load_D_f32_host: bad argument"); return -1; }
     cudaStream_t st = as_stream(stream);
     if (s->ld != s->m) CK(cudaMemsetAsync(s->D, 0, sizeof(float) * (size_t)s->ld * s->n, st));
-    CK(cudaMemcpy2DAsync(s->D, sizeof(float) * s->ld, D, sizeof(float) * ld, sizeof(float) * s->m, s->n, cudaMemcpyHostToDevice, st));
+    if (ld == s->m && s->ld == s->m) CK(cudaMemcpyAsync(s->D, D, sizeof(float) * (size_t)s->m * s->n, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemcpy2DAsync(s->D, sizeof(float) * s->ld, D, sizeof(float) * ld, sizeof(float) * s->m, s->n, cudaMemcpyHostToDevice, st));
     return after_load(s);
 }
 
@@ -413,7 +415,14 @@ int bsub_step_init_local(bsub_solver* s, void* stream) {
     CK(cudaMemsetAsync(s->comm_max, 0, sizeof(double) * 8, st));
     CK(cudaMemsetAsync(s->comm_sum + (size_t)s->npad * s->npad, 0, sizeof(double) * kCommTail, st));
     RET_IF(launch_rowsum_max(s->D, s->ld, s->m, s->n, s->comm_max, st));
-    RET_IF(launch_gram(s->gp, s->gmaps, false, s->tasks_dev, nullptr, 0.f, s->gram_partial, s->comm_sum, st));
+    if (s->use_i8) {
+        // Gram(D) on the int8 tensor-core path: quantise D into the slice planes (scale from max|D|), then the exact Gram
+        RET_IF(launch_quantize_D(s->D, s->ld, s->n, s->gip.ldq, s->Wq, s->comm_max + 2, s->st, st));
+        RET_IF(launch_gram_i8(s->gip, s->gimap, s->gimap_last, s->gi_info, s->gi_ncta, s->gi_blkn, s->Gint, s->comm_sum, s->npad, s->st, 0.0, 0,
+                              st));
+    } else {
+        RET_IF(launch_gram(s->gp, s->gmaps, false, s->tasks_dev, nullptr, 0.f, s->gram_partial, s->comm_sum, st));
+    }
     s->iters_enqueued = 0;
     s->finalized = false;
     return 0;
@@ -571,8 +580,9 @@ int bsub_download_f32(bsub_solver* s, int which, float* dst, int64_t ld, void* s
     if (which == 0 && !s->finalized) RET_IF(bsub_finalize(s, stream));
     float* src = pick(s, which);
     if (!src) { set_error("bsub_download_f32: bad selector %d", which); return -1; }
-    CK(cudaMemcpy2DAsync(dst, sizeof(float) * ld, src, sizeof(float) * s->ld, sizeof(float) * s->m, s->n, cudaMemcpyDeviceToHost,
-                         as_stream(stream)));
+    if (ld == s->m && s->ld == s->m) CK(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)s->m * s->n, cudaMemcpyDeviceToHost, as_stream(stream)));
+    else CK(cudaMemcpy2DAsync(dst, sizeof(float) * ld, src, sizeof(float) * s->ld, sizeof(float) * s->m, s->n, cudaMemcpyDeviceToHost,
+                              as_stream(stream)));
     CK(cudaStreamSynchronize(as_stream(stream)));
     return 0;
 }
@@ -607,11 +617,11 @@ int bsub_debug_info(bsub_solver* s, int32_t* o) {
     return 0;
 }
 
-int bsub_debug_eig_cycles(bsub_solver* s, int64_t* out8) {
-    if (!s || !out8) { set_error("bsub_debug_eig_cycles: null argument"); return -1; }
+int bsub_debug_eig_cycles(bsub_solver* s, int64_t* out16) {
+    if (!s || !out16) { set_error("bsub_debug_eig_cycles: null argument"); return -1; }
     DevState h;
     CK(cudaMemcpy(&h, s->st, sizeof(h), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < 8; ++i) out8[i] = (int64_t)h.eig_clk[i];
+    for (int i = 0; i < 16; ++i) out16[i] = (int64_t)h.eig_clk[i];
     return 0;
 }
 
@@ -656,12 +666,12 @@ int bsub_mask_host(bsub_solver* s, double sigmas, uint8_t* mask_host, void* stre
     cudaStream_t st = as_stream(stream);
     RET_IF(bsub_mask_stats_local(s, 0, stream));
     RET_IF(bsub_mask_stats_local(s, 1, stream));
-    unsigned char* dev = nullptr;
-    CK(cudaMalloc((void**)&dev, (size_t)s->n * s->m));
+    // device staging buffer, allocated once (a cudaMalloc/cudaFree per call would synchronise the whole device)
+    if (!s->mask_stage) CK(cudaMalloc((void**)&s->mask_stage, (size_t)s->n * s->m));
+    unsigned char* dev = s->mask_stage;
     int rc = bsub_mask_dev(s, sigmas, dev, stream);
     if (rc == 0 && cudaMemcpyAsync(mask_host, dev, (size_t)s->n * s->m, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("bsub_mask_host: copy failed"); rc = -1; }
     if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_mask_host: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
-    cudaFree(dev);
     return rc;
 }
 

@@ -127,7 +127,7 @@ int bsub_download_f64(bsub_solver* s, int which /*0 L, 1 S, 2 D, 3 Y*/, double* 
 int bsub_download_f32(bsub_solver* s, int which, float* dst_host, int64_t ld, void* stream);
 int bsub_get_log(bsub_solver* s, bsub_iter_log* out, int32_t cap, int32_t* count);
 /* diagnostics: SM clock at the phase boundaries of the last eigensolve (load, tridiag, eigenvalues, vectors, reorth, back-transform) */
-int bsub_debug_eig_cycles(bsub_solver* s, int64_t* out8);
+int bsub_debug_eig_cycles(bsub_solver* s, int64_t* out16);
 /* diagnostics: kernel paths chosen for this solver: use_tma, use_stream, use_i8, stream R/FC/NS, gram types/kc, eig cluster, tma R/Cf, ld */
 int bsub_debug_info(bsub_solver* s, int32_t* out12);
 /* foreground_mask(D, L, S, sigmas) of utils.py:139-149 on the solver's own D, L, S; mask uint8[n][m] on the host */

@@ -18,9 +18,10 @@ for (rows, cols, n) in [(240, 320, 48), (240, 320, 200), (240, 320, 300), (120, 
     dec.load(D)
     dec.run()
     st = dec.status()
-    out = (ctypes.c_int64 * 8)()
+    out = (ctypes.c_int64 * 16)()
     C.check(dec.lib.bsub_debug_eig_cycles(dec.h, out))
     d = np.diff(np.array(list(out), dtype=np.float64)[:6]) / 1.965e3
     log = dec.log()
     print(f"n={n} iters={st.iter} sv_last={log[-1]['sv']} svp={log[-1]['svp']} us: tridiag={d[0]:.0f} eigval={d[1]:.0f} "
-          f"invit={d[2]:.0f} reorth={d[3]:.0f} backtr={d[4]:.0f} total={np.sum(d):.0f}")
+          f"invit={d[2]:.0f} reorth={d[3]:.0f} backtr={d[4]:.0f} total={np.sum(d):.0f}  tridiag sub-phases (us): "
+          + " ".join(f"{k}={v / 1.965e3:.0f}" for k, v in zip(["reflector", "matvec", "sync2", "dot_w", "update", "sync1"], list(out)[8:14])))
