@@ -143,6 +143,136 @@ __device__ void eig_control(const EigArgs& a, DevState* st, int K, double mu, do
     }
 }
 
+// ---- Householder tridiagonalisation with the matrix rows in shared memory, dealt cyclically over the cluster.
+// Both exchanges of a step go through distributed shared memory: (1) after its rank-2 update every CTA pushes its
+// entries of the next column into all CTAs, so every warp forms the reflector redundantly; (2) every CTA pushes its
+// slice of p = tau A v into all CTAs.  Two hardware cluster barriers per step and nothing else: every warp keeps the
+// reflector v and w = p + kc v in registers (lane owns columns lane + 32 t), so there is no block-level barrier or
+// reduction, and a row is always touched by the same warp.
+template <int NT>
+__device__ void eig_tridiag_dsmem(const EigArgs& a, double* Asm, double* xb, double* pb, DevState* st) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int n = a.n, C = a.C, c = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cshift = 31 - __clz(C), cmask = C - 1;      // C is a power of two (make_eig_plan)
+    double* xb_rem = (lane < C) ? cluster.map_shared_rank(xb, lane) : nullptr;
+    double* pb_rem = (lane < C) ? cluster.map_shared_rank(pb, lane) : nullptr;
+    for (int li = warp; li < a.rows_per; li += EIG_WARPS) {
+        const int i = c + li * C;
+        if (i >= 1 && i < n) { const double val = Asm[(size_t)li * n]; if (lane < C) xb_rem[i] = val; }
+    }
+    cluster.sync();
+    long long tph[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();
+#define EIG_TICK(k) { const long long t_ = clock64(); tph[k] += t_ - tc; tc = t_; }
+    for (int j = 0; j + 2 < n; ++j) {
+        const int par = j & 1;
+        const double* x = xb + par * n;
+        const int t0 = (j + 1) >> 5;                        // first 32-column block holding a column > j
+        // reflector from column j
+        double v[NT], w[NT];
+        double ssa = 0.0, ssb = 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int col = lane + 32 * t;
+            v[t] = (t >= t0 && col > j && col < n) ? x[col] : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int col = lane + 32 * t;
+            const double xv = (col >= j + 2) ? v[t] : 0.0;
+            if (t & 1) ssb = fma(xv, xv, ssb); else ssa = fma(xv, xv, ssa);
+        }
+        const double ss = warp_allsum(ssa + ssb);
+        const double alpha = x[j + 1];
+        double beta, tau, scale;
+        if (ss == 0.0) { tau = 0.0; beta = alpha; scale = 0.0; }
+        else {
+            // beta = -sgn(alpha) ||x||, tau = (beta - alpha) / beta = 1 + |alpha| / ||x||, scale = 1 / (alpha - beta):
+            // one reciprocal square root and one independent reciprocal instead of sqrt + two divisions
+            const double nrm2 = fma(alpha, alpha, ss), aa = fabs(alpha);
+            const double rn = rsqrt(nrm2), nrm = nrm2 * rn;
+            beta = -copysign(nrm, alpha);
+            tau = fma(aa, rn, 1.0);
+            scale = copysign(__drcp_rn(aa + nrm), alpha);
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) v[t] = (lane + 32 * t == j + 1) ? 1.0 : v[t] * scale;
+        if (c == (j & cmask) && warp == 0) {
+            double* vh = a.Vh + (size_t)j * n;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) { const int col = lane + 32 * t; if (t >= t0 && col > j && col < n) vh[col] = v[t]; }
+            if (lane == 0) { a.tau[j] = tau; a.dd[j] = Asm[(size_t)(j >> cshift) * n + j]; a.ee[j] = beta; }
+        }
+        EIG_TICK(0)
+        const int l0 = (j >= c) ? ((j - c) >> cshift) + 1 : 0;  // first local row with global index > j
+        for (int lb = l0 + warp; lb < a.rows_per; lb += 3 * EIG_WARPS) {
+            const int l1 = lb + EIG_WARPS, l2 = lb + 2 * EIG_WARPS;
+            const int i0 = c + lb * C, i1 = c + l1 * C, i2 = c + l2 * C;
+            const bool ok0 = i0 < n, ok1 = (l1 < a.rows_per) && i1 < n, ok2 = (l2 < a.rows_per) && i2 < n;
+            const double* r0 = Asm + (size_t)lb * n;
+            const double* r1 = ok1 ? Asm + (size_t)l1 * n : r0;
+            const double* r2 = ok2 ? Asm + (size_t)l2 * n : r0;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int col = lane + 32 * t;
+                if (t >= t0 && col < n) { s0 = fma(r0[col], v[t], s0); s1 = fma(r1[col], v[t], s1); s2 = fma(r2[col], v[t], s2); }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (lane < C) {
+                if (ok0) pb_rem[i0] = tau * s0;
+                if (ok1) pb_rem[i1] = tau * s1;
+                if (ok2) pb_rem[i2] = tau * s2;
+            }
+        }
+        EIG_TICK(1)
+        cluster.sync();
+        EIG_TICK(2)
+        double dla = 0.0, dlb = 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int col = lane + 32 * t;
+            w[t] = (t >= t0 && col > j && col < n) ? pb[col] : 0.0;
+            if (t & 1) dlb = fma(w[t], v[t], dlb); else dla = fma(w[t], v[t], dla);
+        }
+        const double kc = -0.5 * tau * warp_allsum(dla + dlb);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) w[t] = fma(kc, v[t], w[t]);
+        EIG_TICK(3)
+        double* xn = xb_rem + (par ^ 1) * n;
+        const int fl = (j + 1) & 31;                        // lane / block (t0) that hold column j + 1
+        for (int li = l0 + warp; li < a.rows_per; li += EIG_WARPS) {          // same rows per warp as in the product above
+            const int i = c + li * C;
+            if (i < n) {
+                double* r = Asm + (size_t)li * n;
+                const double vi = (i == j + 1) ? 1.0 : x[i] * scale;
+                const double wi = fma(kc, vi, pb[i]);
+                double first = 0.0;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const int col = lane + 32 * t;
+                    if (t >= t0 && col > j && col < n) {
+                        const double nv = r[col] - (vi * w[t] + wi * v[t]);
+                        r[col] = nv;
+                        if (t == t0) first = nv;
+                    }
+                }
+                first = __shfl_sync(0xffffffffu, first, fl);   // new A[i][j+1] = this CTA's entry of the next column
+                if (lane < C && i > j + 1) xn[i] = first;
+            }
+        }
+        EIG_TICK(4)
+        cluster.sync();
+        EIG_TICK(5)
+    }
+    if (c == 0 && tid == 0) for (int k = 0; k < 6; ++k) st->eig_clk[8 + k] = tph[k];
+#undef EIG_TICK
+}
+
 __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
     cg::cluster_group cluster = cg::this_cluster();
     DevState* st = a.st;
@@ -188,100 +318,14 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
 
     // ---- 1. Householder tridiagonalisation ------------------------------------------------------------------
     if (a.in_smem) {
-        // Rows live in shared memory, dealt cyclically over the cluster.  Both exchanges of a step go through
-        // distributed shared memory: (1) after its rank-2 update every CTA pushes its entries of the next column
-        // into all CTAs, so everyone forms the reflector redundantly; (2) every CTA pushes its slice of p = tau A v
-        // into all CTAs.  Two hardware cluster barriers per step, no global-memory round trip on the critical path.
-        const int cshift = 31 - __clz(C), cmask = C - 1;      // C is a power of two (make_eig_plan)
         double* xb = esm + a.tail_off;       // [2][n] column j of the current matrix, by parity of j
         double* pb = xb + 2 * n;             // [n]    p = tau * A v
-        double* xb_rem = (lane < C) ? cluster.map_shared_rank(xb, lane) : nullptr;
-        double* pb_rem = (lane < C) ? cluster.map_shared_rank(pb, lane) : nullptr;
-        for (int li = warp; li < a.rows_per; li += EIG_WARPS) {
-            const int i = c + li * C;
-            if (i >= 1 && i < n) { const double val = Arow(li)[0]; if (lane < C) xb_rem[i] = val; }
-        }
-        cluster.sync();
-        long long tph[6] = {0, 0, 0, 0, 0, 0}, tc = clock64();
-#define EIG_TICK(k) { const long long t_ = clock64(); tph[k] += t_ - tc; tc = t_; }
-        for (int j = 0; j + 2 < n; ++j) {
-            const int par = j & 1;
-            const double* x = xb + par * n;
-            // reflector from column j (every warp redundantly: no block-level reduction)
-            double ssl = 0.0;
-            for (int i = j + 2 + lane; i < n; i += 32) ssl = fma(x[i], x[i], ssl);
-            const double ss = warp_allsum(ssl);
-            const double alpha = x[j + 1];
-            double beta, tau, scale;
-            if (ss == 0.0) { tau = 0.0; beta = alpha; scale = 0.0; }
-            else {
-                beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
-                tau = (beta - alpha) / beta;
-                scale = 1.0 / (alpha - beta);
-            }
-            for (int i = tid; i < n; i += EIG_THREADS) v_s[i] = (i > j) ? ((i == j + 1) ? 1.0 : x[i] * scale) : 0.0;
-            if (c == (j & cmask)) {
-                double* vh = a.Vh + (size_t)j * n;
-                for (int i = j + 1 + tid; i < n; i += EIG_THREADS) vh[i] = (i == j + 1) ? 1.0 : x[i] * scale;
-                if (tid == 0) { a.tau[j] = tau; a.dd[j] = Arow(j >> cshift)[j]; a.ee[j] = beta; }
-            }
-            __syncthreads();
-            EIG_TICK(0)
-            const int l0 = (j >= c) ? ((j - c) >> cshift) + 1 : 0;  // first local row with global index > j
-            for (int lb = l0 + warp; lb < a.rows_per; lb += 3 * EIG_WARPS) {
-                const int l1 = lb + EIG_WARPS, l2 = lb + 2 * EIG_WARPS;
-                const int i0 = c + lb * C, i1 = c + l1 * C, i2 = c + l2 * C;
-                const bool ok0 = i0 < n, ok1 = (l1 < a.rows_per) && i1 < n, ok2 = (l2 < a.rows_per) && i2 < n;
-                const double* r0 = Arow(lb);
-                const double* r1 = ok1 ? Arow(l1) : r0;
-                const double* r2 = ok2 ? Arow(l2) : r0;
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-                for (int col = j + 1 + lane; col < n; col += 32) {
-                    const double vv = v_s[col];
-                    s0 = fma(r0[col], vv, s0); s1 = fma(r1[col], vv, s1); s2 = fma(r2[col], vv, s2);
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                }
-                if (lane < C) {
-                    if (ok0) pb_rem[i0] = tau * s0;
-                    if (ok1) pb_rem[i1] = tau * s1;
-                    if (ok2) pb_rem[i2] = tau * s2;
-                }
-            }
-            EIG_TICK(1)
-            cluster.sync();
-            EIG_TICK(2)
-            double dl = 0.0;
-            for (int i = j + 1 + lane; i < n; i += 32) dl = fma(pb[i], v_s[i], dl);
-            const double kc = -0.5 * tau * warp_allsum(dl);
-            for (int i = tid; i < n; i += EIG_THREADS) w_s[i] = (i > j) ? fma(kc, v_s[i], pb[i]) : 0.0;
-            __syncthreads();
-            EIG_TICK(3)
-            double* xn = xb_rem + (par ^ 1) * n;
-            for (int li = l0 + warp; li < a.rows_per; li += EIG_WARPS) {
-                const int i = c + li * C;
-                if (i < n) {
-                    double* r = Arow(li);
-                    const double vi = v_s[i], wi = w_s[i];
-                    double first = 0.0;
-                    for (int col = j + 1 + lane; col < n; col += 32) {
-                        const double nv = r[col] - (vi * w_s[col] + wi * v_s[col]);
-                        r[col] = nv;
-                        if (col == j + 1) first = nv;
-                    }
-                    first = __shfl_sync(0xffffffffu, first, 0);    // new A[i][j+1] = this CTA's entry of the next column
-                    if (lane < C && i > j + 1) xn[i] = first;
-                }
-            }
-            EIG_TICK(4)
-            cluster.sync();
-            EIG_TICK(5)
-        }
-        if (c == 0 && tid == 0) for (int k = 0; k < 6; ++k) st->eig_clk[8 + k] = tph[k];
-#undef EIG_TICK
+        if (n <= 64) eig_tridiag_dsmem<2>(a, Asm, xb, pb, st);
+        else if (n <= 128) eig_tridiag_dsmem<4>(a, Asm, xb, pb, st);
+        else if (n <= 224) eig_tridiag_dsmem<7>(a, Asm, xb, pb, st);
+        else if (n <= 320) eig_tridiag_dsmem<10>(a, Asm, xb, pb, st);
+        else if (n <= 448) eig_tridiag_dsmem<14>(a, Asm, xb, pb, st);
+        else eig_tridiag_dsmem<20>(a, Asm, xb, pb, st);
     } else {
         for (int j = 0; j + 2 < n; ++j) {
             const int par = j & 1;
@@ -618,7 +662,7 @@ EigPlan make_eig_plan(int n, int npad) {
     p.n = n; p.npad = npad;
     int C = 1;
     while (C < 16 && (n + C - 1) / C > 40) C *= 2;
-    const size_t cap = 200 * 1024;
+    const size_t cap = 225 * 1024;
     auto bytes_for = [&](int Cc, bool in_smem) {
         size_t rows = (size_t)(n + Cc - 1) / Cc;
         size_t mat = in_smem ? rows * n + 3 * (size_t)n : 0;     // + exchange buffers of the tridiagonalisation
@@ -641,11 +685,11 @@ int launch_eig(const EigPlan& p, const double* G, const double* comm_max, EigBuf
                int k_override, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        BSUB_CUDA_CHECK(cudaFuncSetAttribute(eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        BSUB_CUDA_CHECK(cudaFuncSetAttribute(eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
         BSUB_CUDA_CHECK(cudaFuncSetAttribute(eig_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         attr_set = true;
     }
-    if (p.smem_bytes > 200 * 1024) { set_error("eig: n=%d needs %zu B of shared memory", p.n, p.smem_bytes); return -1; }
+    if (p.smem_bytes > 225 * 1024) { set_error("eig: n=%d needs %zu B of shared memory", p.n, p.smem_bytes); return -1; }
     EigArgs a;
     a.G = G; a.comm_max = comm_max; a.n = p.n; a.npad = p.npad; a.C = p.C; a.rows_per = p.rows_per;
     a.in_smem = p.in_smem; a.kcap = p.kcap; a.mode = mode; a.k_override = k_override;
