@@ -43,6 +43,7 @@ struct DevState {
     double wq_scale;        // S: q = rint(W * 2^31 / S), power of two
     double wq_scale_next;   // S for the slices the coming shrink pass writes
     double wmax;            // max |W| seen by the last shrink pass (over the W it produced)
+    double wm_local;        // this rank's max |W_next| of the running iteration (-1: no slices written); never all-reduced
     int gram_mode;          // 0: fp64 DMMA Gram from D,S,Y   1: int8 tcgen05 Gram from the slices
     int wq_saturated;       // the last shrink pass clipped a slice -> fall back to the DMMA Gram once
     int use_i8;             // configuration: int8 path enabled

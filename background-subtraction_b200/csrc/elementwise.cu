@@ -91,7 +91,10 @@ __global__ void control_post_kernel(DevState* st, const double* part_zz, const u
         }
         if (lane == 0) {
             comm_tail[0] = zz; comm_tail[1] = nz; comm_tail[2] = (double)mx;
-            comm_tail[3] = (track && !missing) ? (double)wm : -1.0;
+            comm_tail[3] = 0.0;
+            // scale and validity of the slices are per rank (every rank turns its own partial Gram into doubles), so this
+            // stays out of the all-reduced tail
+            st->wm_local = (track && !missing) ? (double)wm : -1.0;
         }
     }
     if (lane != 0) return;
@@ -110,7 +113,7 @@ __global__ void control_post_kernel(DevState* st, const double* part_zz, const u
             }
             st->mu = fmin(st->mu * st->rho, st->mu * 1e7);
             if (st->use_i8) {
-                const double wm = comm_tail[3];
+                const double wm = st->wm_local;
                 if (wm >= 0.0 && wm < 1.0e38 && wm > 0.0) {          // slices written, nothing clipped
                     st->gram_mode = 1; st->wq_saturated = 0;
                     st->wq_scale = st->wq_scale_next;              // scale of the slices that now exist

@@ -186,7 +186,7 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
         ALLOC(s->part_max, sizeof(float) * nparts);
         cudaMemset(s->part_zz, 0, sizeof(double) * nparts); cudaMemset(s->part_nnz, 0, sizeof(unsigned long long) * nparts);
         cudaMemset(s->part_max, 0, sizeof(float) * nparts);
-        s->use_i8 = s->use_stream && (shrink_stream_ldq(s->ssp) > 0) && (getenv("BSUB_NO_I8") == nullptr) && (s->cfg.m_global == s->m) &&
+        s->use_i8 = s->use_stream && (shrink_stream_ldq(s->ssp) > 0) && (getenv("BSUB_NO_I8") == nullptr) &&
                     (cfg->prox == BSUB_PROX_FLAT_LINF || cfg->prox == BSUB_PROX_L1);
         if (s->use_i8) {
             const long long ldq = shrink_stream_ldq(s->ssp);

@@ -397,6 +397,11 @@ def main():
         e2e = {"value": None, "unit": "frames/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                "what": "not measured for N > 1"}
 
+    # foreground fraction over the whole frame (all shards)
+    mcount = torch.tensor([float(mask.sum(dtype=torch.float64).item()), float(mask.numel())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(mcount)
+    mask_fraction = float((mcount[0] / mcount[1]).item())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -454,7 +459,7 @@ def main():
                       "delta": 10, "sharding": f"pixel columns over {world} GPU(s)", "l2": "inputs (2.5 GB/matrix) larger than L2",
                       "tile_rows": info["stream_R"] if info["use_stream"] else solver.dec.cfg.tile_rows, "paths": info},
            "alm_iters": iters, "converged": bool(st.converged), "rank_L": int(st.svp), "err": float(st.err),
-           "mask_fraction": float(mask.float().mean().item()),
+           "mask_fraction": mask_fraction,
            "kernels": kern, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
            "clocks": clocks, "datagen_s": t_gen, "breakdown_ms": breakdown,
            "iters_enqueued": driver.iters_enqueued}

@@ -1,0 +1,64 @@
+"""Sharded solve (one process per GPU, NCCL) against the single-GPU solve of the same clip.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 scripts/check_sharded.py
+
+Every rank solves its column shard through ShardedLSD; rank 0 also solves the whole clip alone and compares iteration
+count, stop residual, rank and the foreground mask of its own columns.  Exit code 0 = agreement.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from background_subtraction_b200 import dist as bdist, synth  # noqa: E402
+
+
+def solve(rows, cols, c0, c1, frames, m_global, D_full, comm):
+    cl = c1 - c0
+    shard = np.ascontiguousarray(D_full.reshape(frames, cols, rows)[:, c0:c1, :].reshape(frames, rows * cl))
+    s = bdist.CudaStepSolver(rows, cl, frames, m_global)
+    s.load(shard)
+    drv = bdist.ShardedLSD(s, comm, fence=bdist.cuda_fence)
+    drv.solve()
+    mask = drv.finish(2.0, want_mask=True)
+    torch.cuda.synchronize()
+    st = s.status()
+    return st, mask.cpu().numpy().reshape(frames, cl, rows), s.dec.debug_info()
+
+
+def main():
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    rows, cols, frames = 240, 321, 96
+    video, _ = synth.make_clip(rows, cols, frames, seed=11, n_rect=3)
+    D = synth.preprocess_u8(video)                                   # float32 [frames][m]
+    m = rows * cols
+    c0, c1 = bdist.shard_columns(cols, world, rank)
+    st, mask, info = solve(rows, cols, c0, c1, frames, m, D, bdist.TorchComm())
+    ok = True
+    if rank == 0:
+        class Solo:
+            world, rank = 1, 0
+
+            def all_reduce_sum(self, t):
+                pass
+
+            def all_reduce_max(self, t):
+                pass
+        st1, mask1, _ = solve(rows, cols, 0, cols, frames, m, D, Solo())
+        same = float((mask1[:, c0:c1, :] == mask).mean())
+        print("sharded: iter=%d err=%.3e svp=%d use_i8=%d | single: iter=%d err=%.3e svp=%d | mask agreement on rank 0 columns %.6f"
+              % (st.iter, st.err, st.svp, info["use_i8"], st1.iter, st1.err, st1.svp, same), flush=True)
+        ok = abs(st.iter - st1.iter) <= 1 and st.svp == st1.svp and same >= 0.999 and bool(st.converged)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    return 0 if int(flag.item()) == 1 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
