@@ -101,8 +101,9 @@ __device__ __forceinline__ void ss_accumulate(float (&acc)[SS_KC][4], const floa
 }
 
 // phase B, one 3x3 group of one frame: L from T, prox, dual update, in place in the stage
+// Tg: this group's T entries, regrouped as [k][group][12] (9 used) so that they come in as three 16-byte loads per k
 template <int KCNT>
-__device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg, const float* vc, int R, int P, float inv_mu,
+__device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg, int tk_stride, const float* vc, int R, int P, float inv_mu,
                                          float mu_f, float lamq, int mode, double& zz_acc, unsigned int& nnz_acc, float& max_acc,
                                          unsigned char* qb, int QS, int o0, int kstep, float inv_mu_next, float Qf, float& wmax_acc,
                                          int& sat_acc) {
@@ -113,15 +114,24 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
         vv[4 * k4] = v.x; vv[4 * k4 + 1] = v.y; vv[4 * k4 + 2] = v.z; vv[4 * k4 + 3] = v.w;
     }
     float av[9], yv[9], x[9], ax[9], dv[9];
+    float lw[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) lw[e] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KCNT; ++k) {
+        const float4* tq = reinterpret_cast<const float4*>(Tg + (size_t)k * tk_stride);
+        const float4 t0 = tq[0], t1 = tq[1], t2 = tq[2];
+        lw[0] = fmaf(vv[k], t0.x, lw[0]); lw[1] = fmaf(vv[k], t0.y, lw[1]); lw[2] = fmaf(vv[k], t0.z, lw[2]);
+        lw[3] = fmaf(vv[k], t0.w, lw[3]); lw[4] = fmaf(vv[k], t1.x, lw[4]); lw[5] = fmaf(vv[k], t1.y, lw[5]);
+        lw[6] = fmaf(vv[k], t1.z, lw[6]); lw[7] = fmaf(vv[k], t1.w, lw[7]); lw[8] = fmaf(vv[k], t2.x, lw[8]);
+    }
     float sabs = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
         for (int dr = 0; dr < 3; ++dr) {
             const int e = c * 3 + dr, o = c * R + dr;
-            float l = 0.f;
-#pragma unroll
-            for (int k = 0; k < KCNT; ++k) l = fmaf(vv[k], Tg[(size_t)k * P + o], l);
+            const float l = lw[e];
             dv[e] = dsp[o];
             av[e] = dv[e] - l;                            // a = D - L
             yv[e] = ysp[o];
@@ -215,6 +225,34 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
         default: { constexpr int K_ = 16; CALL; } break;  \
     }
 
+// phase B of one tile: every stage = FC frames; thread item = one 3x3 group of one frame
+template <int KCNT, int NTC>
+__device__ __forceinline__ void ss_phase_b(const ShrinkStreamArgs& a, float* ring, size_t stage_floats, const float* Tp, const float* VC_s,
+                                           uint64_t* full, uint64_t* done, long long& q, int ct, int lane, int NG, int R, int P, int FC,
+                                           int NS, int ncf, bool wq, float inv_mu, float mu_f, float lamq, float inv_mu_next, float Qf,
+                                           double& zz_acc, unsigned int& nnz_acc, float& max_acc, float& wmax_acc, int& sat_acc) {
+    for (int c = 0; c < ncf; ++c, ++q) {
+        const int s = (int)(q % NS);
+        const long long u = q / NS;
+        mbar_wait(&full[s], (uint32_t)(u & 1));
+        float* b = ring + (size_t)s * stage_floats;
+        const int fbase = c * FC;
+        for (int itx = ct; itx < FC * NG; itx += NTC) {
+            const int f = itx / NG, g = itx - f * NG;
+            const int fg = fbase + f;
+            if (fg >= a.n) continue;
+            float* dsp = b + (size_t)f * P + 3 * g;
+            float* ysp = b + (size_t)2 * a.BS + (size_t)f * P + 3 * g;
+            unsigned char* qb = wq ? (reinterpret_cast<unsigned char*>(b + (size_t)a.BS) + (size_t)f * 16) : nullptr;
+            ss_group<KCNT>(dsp, ysp, Tp + 12 * g, 12 * NG, VC_s + (size_t)fg * SS_KC, R, P, inv_mu, mu_f, lamq, a.mode, zz_acc, nnz_acc,
+                           max_acc, qb, a.QS, 3 * g, FC * 16, inv_mu_next, Qf, wmax_acc, sat_acc);
+        }
+        fence_proxy_async_smem();                   // my writes -> visible to the storer's TMA stores
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[s]);
+    }
+}
+
 template <int NCW>      // number of consumer warps; block = 32 * (NCW + 2)
 __global__ void __launch_bounds__(32 * (NCW + 2), 1)
 shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_constant__ CUtensorMap mapS,
@@ -244,8 +282,8 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
     const size_t stage_floats = (size_t)3 * a.BS;
     float* ring = reinterpret_cast<float*>(ss_smem_raw);            // [NS][3][BS]
     float* scr = ring + (size_t)NS * stage_floats;                  // [NFL][SS_KRED][P]   (T reduction)
-    float* Tp = scr + (size_t)NFL * SS_KRED * P;                    // [SS_KC][P]
-    float* Vr_s = Tp + (size_t)SS_KC * P;                           // [n][SS_KC]
+    float* Tp = scr + (size_t)NFL * SS_KRED * P;                    // [SS_KC][R/3 groups][12]: T of the tile, 9 entries per 3x3 group
+    float* Vr_s = Tp + (size_t)SS_KC * (4 * R);                     // [n][SS_KC]
     float* VC_s = Vr_s + (size_t)a.n * SS_KC;                       // [n][SS_KC]
     uint64_t* full = reinterpret_cast<uint64_t*>(VC_s + (size_t)a.n * SS_KC);   // [NS]
     uint64_t* done = full + NS;                                     // [NS]
@@ -263,7 +301,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
         Vr_s[idx] = ok ? a.Vr[(size_t)f * a.vstride + k] : 0.f;
         VC_s[idx] = ok ? a.VC[(size_t)f * a.vstride + k] : 0.f;
     }
-    for (int idx = threadIdx.x; idx < SS_KC * P; idx += blockDim.x) Tp[idx] = 0.f;   // rows >= svp stay zero
+    for (int idx = threadIdx.x; idx < SS_KC * 4 * R; idx += blockDim.x) Tp[idx] = 0.f;   // rows >= svp stay zero
     __syncthreads();
 
     auto tile_origin = [&](long long tl, int& j0, int& i0) {
@@ -375,9 +413,14 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                             const float4 v = *reinterpret_cast<const float4*>(scr + ((size_t)(l * SS_KRED + k)) * P + 4 * qq);
                             sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
                         }
-                        *reinterpret_cast<float4*>(Tp + (size_t)(kr0 + k) * P + 4 * qq) = sum;
                         // keep T for the final materialisation of L (rows % 4 == 0 on this path)
                         const int c2 = qq / RQ, i2 = (qq - c2 * RQ) * 4;
+                        {   // regrouped copy for phase B: entry e = 3 c + dr of group g = row / 3
+                            float* tk = Tp + (size_t)(kr0 + k) * (4 * R);
+                            const float sv4[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) { const int ir = i2 + t; tk[(ir / 3) * 12 + c2 * 3 + (ir % 3)] = sv4[t]; }
+                        }
                         const int j2 = j0 + c2, row2 = i0 + i2;
                         if (j2 < a.cols && row2 < a.rows) stg4(a.T + (size_t)(kr0 + k) * a.ld + (long long)j2 * a.rows + row2, sum);
                     }
@@ -385,26 +428,8 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                 }
             }
             // phase B
-            for (int c = 0; c < ncf; ++c, ++q) {
-                const int s = (int)(q % NS);
-                const long long u = q / NS;
-                mbar_wait(&full[s], (uint32_t)(u & 1));
-                float* b = ring + (size_t)s * stage_floats;
-                const int fbase = c * FC;
-                for (int itx = ct; itx < FC * NG; itx += NTC) {
-                    const int f = itx / NG, g = itx - f * NG;
-                    const int fg = fbase + f;
-                    if (fg >= a.n) continue;
-                    float* dsp = b + (size_t)f * P + 3 * g;
-                    float* ysp = b + (size_t)2 * a.BS + (size_t)f * P + 3 * g;
-                    unsigned char* qb = wq ? (reinterpret_cast<unsigned char*>(b + (size_t)a.BS) + (size_t)f * 16) : nullptr;
-                    SS_DISPATCH_K(r, (ss_group<K_>(dsp, ysp, Tp + 3 * g, VC_s + (size_t)fg * SS_KC, R, P, inv_mu, mu_f, lamq, a.mode,
-                                                   zz_acc, nnz_acc, max_acc, qb, a.QS, 3 * g, FC * 16, inv_mu_next, Qf, wmax_acc, sat_acc)));
-                }
-                fence_proxy_async_smem();                   // my writes -> visible to the storer's TMA stores
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&done[s]);
-            }
+            SS_DISPATCH_K(r, (ss_phase_b<K_, NTC>(a, ring, stage_floats, Tp, VC_s, full, done, q, ct, lane, NG, R, P, FC, NS, ncf, wq, inv_mu,
+                                                  mu_f, lamq, inv_mu_next, Qf, zz_acc, nnz_acc, max_acc, wmax_acc, sat_acc)));
         }
     }
     __syncthreads();
@@ -424,7 +449,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
 static size_t ss_smem_bytes(int n, int R, int FC, int NS, int NTC) {
     const int P = 3 * R, NQ = P / 4, NFL = NTC / NQ;
     const size_t bs = ((size_t)FC * P + 127) / 128 * 128;
-    size_t fl = (size_t)NS * 3 * bs + (size_t)NFL * SS_KRED * P + (size_t)SS_KC * P + (size_t)2 * n * SS_KC;
+    size_t fl = (size_t)NS * 3 * bs + (size_t)NFL * SS_KRED * P + (size_t)SS_KC * 4 * R + (size_t)2 * n * SS_KC;
     return fl * sizeof(float) + (size_t)3 * NS * sizeof(uint64_t) + 64;
 }
 
