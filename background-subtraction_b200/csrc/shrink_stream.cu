@@ -101,6 +101,22 @@ __device__ __forceinline__ void ss_accumulate(float (&acc)[SS_KC][4], const floa
 }
 
 // phase B, one 3x3 group of one frame: L from T, prox, dual update, in place in the stage
+// W of the next iteration, exactly as the next pass will form it from the stored S and Y, as 32-bit fixed point
+// q = rint(W * Q) split into four balanced base-256 digits (one byte plane each).  Stage layout per plane:
+// [k16 block of the tile][frame][16 B]  (k-block-major, see gram_i8.cu)
+__device__ __forceinline__ void ss_emit_q(unsigned char* qb, int QS, int pix, int kstep, float d, float s_new, float y_new,
+                                          float inv_mu_next, float Qf, float& wmax_acc) {
+    const float wn = fmaf(y_new, inv_mu_next, d - s_new);
+    wmax_acc = fmaxf(wmax_acc, fabsf(wn));
+    // cvt saturates; a clipped value is detected afterwards through wmax (the slices are then discarded)
+    const int q = __float2int_rn(wn * Qf);
+    // balanced base-256 digits in one go: byte k of ((q + 0x808080) ^ 0x808080) is d_k as a signed byte
+    const unsigned int u = ((unsigned int)q + 0x00808080u) ^ 0x00808080u;
+    const int po = (pix >> 4) * kstep + (pix & 15);
+    qb[po] = (unsigned char)u; qb[QS + po] = (unsigned char)(u >> 8); qb[2 * QS + po] = (unsigned char)(u >> 16);
+    qb[3 * QS + po] = (unsigned char)(u >> 24);
+}
+
 // Tg: this group's T entries, regrouped as [k][group][12] (9 used) so that they come in as three 16-byte loads per k
 template <int KCNT>
 __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg, int tk_stride, const float* vc, int R, int P, float inv_mu,
@@ -147,9 +163,11 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
 #pragma unroll
                 for (int dr = 0; dr < 3; ++dr) {
                     const int e = c * 3 + dr, o = c * R + dr;
+                    const float yn = fmaf(mu_f, av[e], yv[e]);
                     dsp[o] = 0.f;
-                    ysp[o] = fmaf(mu_f, av[e], yv[e]);
+                    ysp[o] = yn;
                     zl = fmaf(av[e], av[e], zl);
+                    if (qb != nullptr) ss_emit_q(qb, QS, o0 + o, kstep, dv[e], 0.f, yn, inv_mu_next, Qf, wmax_acc);
                 }
         } else {
             const float theta = ss_clip_level9(ax, lamq);
@@ -160,11 +178,13 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
                     const int e = c * 3 + dr, o = c * R + dr;
                     const float sv = copysignf(fminf(ax[e], theta), x[e]);
                     const float z = av[e] - sv;            // Z = D - L - S
+                    const float yn = fmaf(mu_f, z, yv[e]);  // Y += mu Z
                     dsp[o] = sv;
-                    ysp[o] = fmaf(mu_f, z, yv[e]);         // Y += mu Z
+                    ysp[o] = yn;
                     zl = fmaf(z, z, zl);
                     nnz_acc += (sv != 0.f);
                     max_acc = fmaxf(max_acc, fabsf(sv));
+                    if (qb != nullptr) ss_emit_q(qb, QS, o0 + o, kstep, dv[e], sv, yn, inv_mu_next, Qf, wmax_acc);
                 }
         }
         zz_acc += (double)zl;
@@ -176,36 +196,18 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
                 const int e = c * 3 + dr, o = c * R + dr;
                 const float sv = copysignf(fmaxf(ax[e] - lamq, 0.f), x[e]);
                 const float z = av[e] - sv;
+                const float yn = fmaf(mu_f, z, yv[e]);
                 dsp[o] = sv;
-                ysp[o] = fmaf(mu_f, z, yv[e]);
+                ysp[o] = yn;
                 zl = fmaf(z, z, zl);
                 nnz_acc += (sv != 0.f);
                 max_acc = fmaxf(max_acc, fabsf(sv));
+                if (qb != nullptr) ss_emit_q(qb, QS, o0 + o, kstep, dv[e], sv, yn, inv_mu_next, Qf, wmax_acc);
             }
         zz_acc += (double)zl;
     } else {                                              // SHRINK_SPILL: hand G_S to a separate prox
 #pragma unroll
         for (int e = 0; e < 9; ++e) dsp[(e / 3) * R + (e % 3)] = x[e];
-    }
-    if (qb != nullptr) {
-        // W of the next iteration, exactly as the next pass will form it from the stored S and Y, as 32-bit fixed point
-        // q = rint(W * Q) split into four balanced base-256 digits (one byte plane each)
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int dr = 0; dr < 3; ++dr) {
-                const int e = c * 3 + dr, o = c * R + dr;
-                const float wn = fmaf(ysp[o], inv_mu_next, dv[e] - dsp[o]);
-                wmax_acc = fmaxf(wmax_acc, fabsf(wn));
-                // cvt saturates; a clipped value is detected afterwards through wmax (the slices are then discarded)
-                const int q = __float2int_rn(wn * Qf);
-                // balanced base-256 digits in one go: byte k of ((q + 0x808080) ^ 0x808080) is d_k as a signed byte
-                const unsigned int u = ((unsigned int)q + 0x00808080u) ^ 0x00808080u;
-                // stage layout per plane: [k16 block of the tile][frame][16 B]  (k-block-major, see gram_i8.cu)
-                const int po = ((o0 + o) >> 4) * kstep + ((o0 + o) & 15);
-                qb[po] = (unsigned char)u; qb[QS + po] = (unsigned char)(u >> 8); qb[2 * QS + po] = (unsigned char)(u >> 16);
-                qb[3 * QS + po] = (unsigned char)(u >> 24);
-            }
     }
 }
 
