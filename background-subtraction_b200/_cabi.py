@@ -35,7 +35,7 @@ class IterLog(ctypes.Structure):
                 ("err", ctypes.c_double), ("mu", ctypes.c_double), ("nnz", ctypes.c_uint64)]
 
 
-PROX_FLAT_LINF, PROX_GRAPH_LINF, PROX_BLOCK_L2, PROX_L1 = 0, 1, 2, 3
+PROX_FLAT_LINF, PROX_GRAPH_LINF, PROX_BLOCK_L2, PROX_L1, PROX_GRAPH_CENTER_BG = 0, 1, 2, 3, 4
 
 # every symbol include/bsub_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -48,6 +48,7 @@ SIGNATURES = {
     "bsub_set_flat_groups": (ctypes.c_int, [vp, c_int32_p]),
     "bsub_set_graph_windows": (ctypes.c_int, [vp, c_double_p, ctypes.c_int64]),
     "bsub_set_blocks": (ctypes.c_int, [vp, c_uint8_p, c_int32_p, c_double_p]),
+    "bsub_set_center_windows": (ctypes.c_int, [vp, c_float_p, c_uint8_p]),
     "bsub_load_D_f64_host": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp]),
     "bsub_load_D_f32_host": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp]),
     "bsub_load_D_f32_dev": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp]),

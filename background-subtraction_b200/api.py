@@ -10,6 +10,9 @@ Same names, argument meaning, return tuples and error convention (`raise Excepti
   block_shrinkage_operator           /root/reference/group_sparse_RPCA.py:13-42
   svd_k_largest                      /root/reference/utils.py:204-212
   getGraphSPAMS_all_groups           /root/reference/inexact_alm_lsd.py:13-46
+  inexact_alm_lsd_with_background    /root/reference/lsd_improvement.py:215-304
+  get_proximal_graph_group_centers   /root/reference/lsd_improvement.py:74-120
+  apply_background_shrinkage_operator /root/reference/lsd_improvement.py:199-212
   get_proximal_flat_groups_nonoverlap /root/reference/lsd_improvement.py:14-34
 Everything numerical happens in libbsub_b200.so (CUDA, sm_100a) behind the C ABI of include/bsub_b200.h;
 this module only marshals arrays.  torch is used for device buffers and streams of the stand-alone operators.
@@ -69,6 +72,86 @@ def getGraphSPAMS_all_groups(img_shape, group_shape):
     groups_var = ssp.csc_matrix((np.full(len(indices), True), indices, indptr), shape=(rows * cols, ng), dtype=bool)
     return {'eta_g': np.ones(ng, dtype=np.float64), 'groups': ssp.csc_matrix((ng, ng), dtype=bool),
             'groups_var': groups_var}
+
+
+def center_window_csc(img_shape, group_centers, group_radius=1):
+    """(indptr, indices, eta) of the windows centred on the pixels with a positive weight, clipped to the image
+    (get_vars_idx_center, utils.py:234-246), enumerated column by column like lsd_improvement.py:97-111."""
+    rows, cols = int(img_shape[0]), int(img_shape[1])
+    gc = np.asarray(group_centers)
+    cj, ci = np.where(gc.T > 0)
+    i0, i1 = np.maximum(ci - group_radius, 0), np.minimum(ci + group_radius, rows - 1)
+    j0, j1 = np.maximum(cj - group_radius, 0), np.minimum(cj + group_radius, cols - 1)
+    hh, ww = i1 - i0 + 1, j1 - j0 + 1
+    indptr = np.concatenate([[0], np.cumsum(hh * ww)]).astype(np.int32)
+    indices = np.empty(int(indptr[-1]), dtype=np.int32)
+    w = 2 * group_radius + 1
+    for dj in range(w):
+        for di in range(w):
+            ok = (di < hh) & (dj < ww)
+            indices[indptr[:-1][ok] + dj * hh[ok] + di] = (j0[ok] + dj) * rows + i0[ok] + di
+    return indptr, indices, np.ascontiguousarray(gc[ci, cj], dtype=np.float64)
+
+
+def get_proximal_graph_group_centers(img_shape, group_size, group_centers):
+    """Same SPAMS graph dict as /root/reference/lsd_improvement.py:74-120 (group_size is the window RADIUS there); the
+    weight map is kept under a private key so that inexact_alm_lsd_with_background need not recover it."""
+    import scipy.sparse as ssp
+    rows, cols = int(img_shape[0]), int(img_shape[1])
+    indptr, indices, eta = center_window_csc((rows, cols), group_centers, int(group_size))
+    ng = len(eta)
+    groups_var = ssp.csc_matrix((np.full(len(indices), True), indices, indptr), shape=(rows * cols, ng), dtype=bool)
+    return {'eta_g': eta, 'groups': ssp.csc_matrix((ng, ng), dtype=bool), 'groups_var': groups_var,
+            '_group_centers': np.array(group_centers, dtype=np.float64), '_group_radius': int(group_size)}
+
+
+def detect_center_windows(graph, m, img_shape=None):
+    """eta map float32[m] (F-order pixel index, 0 = no window) if the SPAMS graph dict is a radius-1 centre-window graph
+    of get_proximal_graph_group_centers, else None.  The candidate map is verified by rebuilding the CSC arrays."""
+    gc = graph.get('_group_centers', None) if isinstance(graph, dict) else None
+    if gc is not None and graph.get('_group_radius', 1) == 1 and gc.size == m:
+        return (int(gc.shape[0]), int(gc.shape[1])), np.where(gc > 0, gc, 0).astype(np.float32).flatten(order='F')
+    gv = graph['groups_var'].tocsc()
+    if gv.shape[0] != m:
+        raise Exception("graph has %d variables, matrix has %d rows" % (gv.shape[0], m))
+    nested = graph.get('groups', None)
+    if nested is not None and getattr(nested, 'nnz', 0) != 0:
+        return None
+    ptr, idx = np.asarray(gv.indptr), np.asarray(gv.indices)
+    eta = np.asarray(graph['eta_g'], dtype=np.float64)
+    ng = len(ptr) - 1
+    shapes = [tuple(int(v) for v in img_shape)] if img_shape is not None else []
+    if not shapes:                                   # rows = jump between the first two columns of any multi-column window
+        for g in range(min(ng, 64)):
+            w = idx[ptr[g]:ptr[g + 1]]
+            jump = np.nonzero(np.diff(w) != 1)[0]
+            if jump.size:
+                rows = int(w[jump[0] + 1] - w[0])
+                if rows > 0 and m % rows == 0:
+                    shapes.append((rows, m // rows))
+                    break
+    for rows, cols in shapes:
+        if rows * cols != m:
+            continue
+        if ng == 0:
+            return (rows, cols), np.zeros(m, dtype=np.float32)
+        first, size = idx[ptr[:-1]], np.diff(ptr)
+        i0, j0 = first % rows, first // rows
+        # height of the window = length of the first run of consecutive indices
+        hh = np.array([(np.nonzero(np.diff(idx[ptr[g]:ptr[g + 1]]) != 1)[0][:1].tolist() or [size[g] - 1])[0] + 1
+                       for g in range(ng)])
+        hh = np.minimum(hh, rows)                     # a window as tall as the image runs on into its next column
+        ww = size // np.maximum(hh, 1)
+        ci = np.where(hh == 3, i0 + 1, np.where(i0 == 0, 0, rows - 1)) if rows > 2 else None
+        cj = np.where(ww == 3, j0 + 1, np.where(j0 == 0, 0, cols - 1)) if cols > 2 else None
+        if ci is None or cj is None:
+            continue
+        emap = np.zeros((rows, cols), dtype=np.float64)
+        emap[ci, cj] = eta
+        p2, i2, e2 = center_window_csc((rows, cols), emap, 1)
+        if np.array_equal(p2, ptr) and np.array_equal(i2, idx) and np.array_equal(e2, eta):
+            return (rows, cols), emap.astype(np.float32).flatten(order='F')
+    return None
 
 
 def detect_flat_tiling(groups, img_shape=None):
@@ -414,6 +497,56 @@ def inexact_alm_lsd(D0, graphs=None, groups=None, delta=10, img_shape=None, verb
     """Drop-in for /root/reference/inexact_alm_lsd.py:82-179 -> (L, S, iter_out, converged)."""
     dec = lsd_decomposition(D0, graphs=graphs, groups=groups, delta=delta, img_shape=img_shape, **tuning)
     return _finish(dec, D0, verbose)
+
+
+def with_background_decomposition(D0, graphs, background_masks, delta=10, img_shape=None, **tuning):
+    if not isinstance(graphs, list) and not isinstance(graphs, np.ndarray):
+        raise Exception('graphs must be list/array')                       # lsd_improvement.py:223-224
+    m, n = _shape_of(D0)
+    if len(graphs) != n or len(background_masks) != n:
+        raise Exception("graphs and background_masks must have one entry per frame")
+    eta = np.empty((n, m), dtype=np.float32)
+    shape = tuple(img_shape) if img_shape is not None else None
+    for f in range(n):
+        det = detect_center_windows(graphs[f], m, shape)
+        if det is None:
+            raise Exception("frame %d: only the radius-1 centre-window graphs of get_proximal_graph_group_centers are "
+                            "implemented in this build" % f)
+        if shape is None or graphs[f].get('_group_centers', None) is not None:
+            shape = det[0] if shape is None else shape
+        if det[0] != tuple(shape):
+            raise Exception("frame %d: graph built for image shape %s, expected %s" % (f, det[0], tuple(shape)))
+        eta[f] = det[1]
+    bg = np.ascontiguousarray(np.stack([np.asarray(b, dtype=bool).ravel() for b in background_masks]).astype(np.uint8))
+    if bg.shape != (n, m):
+        raise Exception("background_masks must hold %d boolean masks of %d pixels" % (n, m))
+    cfg = make_config(m, n, C.PROX_GRAPH_CENTER_BG, shape[0], shape[1], delta=delta, **tuning)
+    dec = Decomposition(cfg)
+    C.check(dec.lib.bsub_set_center_windows(dec.h, eta.ctypes.data_as(C.c_float_p), bg.ctypes.data_as(C.c_uint8_p)))
+    dec.load(D0)
+    dec.run()
+    return dec
+
+
+def inexact_alm_lsd_with_background(D0, graphs, background_masks, delta=10, img_shape=None, verbose=False, **tuning):
+    """Drop-in for /root/reference/lsd_improvement.py:215-304 -> (L, S, iter_out, converged): one centre-window graph
+    per frame (prox_by_frame) plus the l2 shrink of every frame's background pixels at 100 lambda / mu."""
+    dec = with_background_decomposition(D0, graphs, background_masks, delta=delta, img_shape=img_shape, **tuning)
+    return _finish(dec, D0, verbose)
+
+
+def apply_background_shrinkage_operator(G, output, epsilon, background_masks):
+    """Drop-in for /root/reference/lsd_improvement.py:199-212 (in place on `output`, which is also returned): every
+    frame's background pixels become max(1 - epsilon/||G_bg||_2, 0) * G_bg.  Runs block_shrinkage_operator on the
+    device with the background as the only (complement) group, mu = 1, non-block lambda = epsilon."""
+    G = np.asarray(G)
+    n = G.shape[1]
+    fg_blocks = [[~np.asarray(background_masks[f], dtype=bool)] for f in range(n)]
+    shrunk = block_shrinkage_operator(G, fg_blocks, [[0.0]] * n, 1.0, float(epsilon))
+    for f in range(n):
+        mk = np.asarray(background_masks[f], dtype=bool)
+        output[mk, f] = shrunk[mk, f]
+    return output
 
 
 def group_sparse_decomposition(D0, blocks_by_frame, lambdas_by_frame, delta=10, use_sv_prediction=True, img_shape=None,

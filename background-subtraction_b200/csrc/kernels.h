@@ -144,11 +144,11 @@ int launch_block_l2_sums(const float* U, const unsigned char* labels, long long 
                          double* sums, const DevState* st, cudaStream_t s);
 int launch_block_l2_apply(const float* U, float* V, const unsigned char* labels, long long ld, long long m, int n,
                           int nlab, const double* sums, const double* lam_table, const DevState* st,
-                          double mu_override, double non_block_lambda, cudaStream_t s);
+                          double mu_override, double non_block_lambda, cudaStream_t s, int keep_other = 0);
 int launch_prox_l1(const float* U, float* V, long long ld, long long m, int n, float lam, cudaStream_t s);
 struct GraphProxPlan { int rows, cols, n; long long ld; size_t xi_floats; int max_sweeps; float tol; };
 int launch_prox_graph3(const float* U, float* V, float* xi, float* tot, const float* eta, long long ld, int rows,
                        int cols, int n, float lam, int max_sweeps, float tol, int* sweeps_out, const DevState* st,
-                       cudaStream_t s);
+                       cudaStream_t s, int center = 0, long long eta_stride = 0);
 
 }  // namespace bsub

@@ -164,7 +164,7 @@ int launch_block_l2_sums(const float* U, const unsigned char* labels, long long 
 __global__ void block_l2_apply_kernel(const float* __restrict__ U, float* __restrict__ V, const unsigned char* __restrict__ labels,
                                       long long ld, long long m, int nlab, const double* __restrict__ sums,
                                       const double* __restrict__ lam_table, const DevState* st, double mu_override,
-                                      double non_block_lambda) {
+                                      double non_block_lambda, int keep_other) {
     extern __shared__ float fac_s[];
     if (st != nullptr && st->done) return;
     const int f = blockIdx.y;
@@ -182,19 +182,20 @@ __global__ void block_l2_apply_kernel(const float* __restrict__ U, float* __rest
     const unsigned char* lab = labels + (size_t)f * m;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (long long)gridDim.x * blockDim.x) {
         const int l = lab[p];
-        v[p] = (l < nlab) ? fac_s[l] * u[p] : 0.f;
+        if (l < nlab) v[p] = fac_s[l] * u[p];
+        else if (!keep_other) v[p] = 0.f;               // keep_other: pixels outside every group keep what V already holds
     }
 }
 
 int launch_block_l2_apply(const float* U, float* V, const unsigned char* labels, long long ld, long long m, int n, int nlab,
                           const double* sums, const double* lam_table, const DevState* st, double mu_override,
-                          double non_block_lambda, cudaStream_t s) {
+                          double non_block_lambda, cudaStream_t s, int keep_other) {
     long long gx = (m + PX_THREADS * 8 - 1) / (PX_THREADS * 8);
     if (gx < 1) gx = 1;
     if (gx > 256) gx = 256;
     dim3 g((unsigned)gx, n);
     block_l2_apply_kernel<<<g, PX_THREADS, sizeof(float) * nlab, s>>>(U, V, labels, ld, m, nlab, sums, lam_table, st, mu_override,
-                                                                     non_block_lambda);
+                                                                     non_block_lambda, keep_other);
     BSUB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -229,6 +230,9 @@ struct GraphArgs {
     long long ld; int rows, cols, n; float lam; int max_sweeps; float tol;
     int* sweeps_out; unsigned int* change_bits;   // [2] ping-pong max-change (as float bits)
     const DevState* st;
+    // centre mode (get_proximal_graph_group_centers, /root/reference/lsd_improvement.py:74-120): one candidate window per
+    // pixel, centred on it and clipped to the image (utils.py:234-246); eta[f][pixel] > 0 selects and weights it
+    int center; long long eta_stride;
 };
 
 __global__ void __launch_bounds__(PX_THREADS) prox_graph3_kernel(GraphArgs a) {
@@ -239,7 +243,8 @@ __global__ void __launch_bounds__(PX_THREADS) prox_graph3_kernel(GraphArgs a) {
         a.tol = a.tol * a.lam;                                   // relative tolerance in solver mode
     }
     const int rows = a.rows, cols = a.cols;
-    const int nwi = rows - min(3, rows) + 1, nwj = cols - min(3, cols) + 1;     // numX, numY of the reference
+    const bool ctr = a.center != 0;
+    const int nwi = ctr ? rows : rows - min(3, rows) + 1, nwj = ctr ? cols : cols - min(3, cols) + 1;   // numX, numY of the reference
     const long long nw = (long long)nwi * nwj;
     const long long gsz = (long long)gridDim.x * blockDim.x, gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     // init
@@ -258,13 +263,17 @@ __global__ void __launch_bounds__(PX_THREADS) prox_graph3_kernel(GraphArgs a) {
                 const int f = (int)(t / nwc);
                 const long long wq = t - (long long)f * nwc;
                 const int wj = (int)(wq / ni) * 3 + cj, wi = (int)(wq % ni) * 3 + ci;
-                const int hh = min(3, rows - 1 - wi), ww = min(3, cols - 1 - wj);
+                const int i0 = ctr ? max(wi - 1, 0) : wi, j0 = ctr ? max(wj - 1, 0) : wj;
+                const int hh = ctr ? min(wi + 1, rows - 1) - i0 + 1 : min(3, rows - 1 - wi);
+                const int ww = ctr ? min(wj + 1, cols - 1) - j0 + 1 : min(3, cols - 1 - wj);
                 if (hh <= 0 || ww <= 0) continue;
                 const long long widx = (long long)wj * nwi + wi;
+                const float eta_w = ctr ? a.eta[(size_t)f * a.eta_stride + widx] : (a.eta != nullptr ? a.eta[widx] : 1.f);
+                if (ctr && !(eta_w > 0.f)) continue;                      // no group centred on this pixel in this frame
                 const float* u = a.U + (size_t)f * a.ld;
                 float* tot = a.tot + (size_t)f * a.ld;
                 float* xi = a.xi + ((size_t)f * nw + widx) * 9;
-                const float radius = a.lam * (a.eta != nullptr ? a.eta[widx] : 1.f);
+                const float radius = a.lam * eta_w;
                 float r[9], ar[9], xo[9];
                 float sabs = 0.f;
 #pragma unroll
@@ -275,7 +284,7 @@ __global__ void __launch_bounds__(PX_THREADS) prox_graph3_kernel(GraphArgs a) {
                         const bool ok = (dr < hh) && (c < ww);
                         float val = 0.f, x0 = 0.f;
                         if (ok) {
-                            const long long p = (long long)(wj + c) * rows + wi + dr;
+                            const long long p = (long long)(j0 + c) * rows + i0 + dr;
                             x0 = xi[e];
                             val = u[p] - tot[p] + x0;
                         }
@@ -289,7 +298,7 @@ __global__ void __launch_bounds__(PX_THREADS) prox_graph3_kernel(GraphArgs a) {
                     for (int dr = 0; dr < 3; ++dr) {
                         const int e = c * 3 + dr;
                         if ((dr < hh) && (c < ww)) {
-                            const long long p = (long long)(wj + c) * rows + wi + dr;
+                            const long long p = (long long)(j0 + c) * rows + i0 + dr;
                             const float xn = copysignf(fmaxf(ar[e] - theta, 0.f), r[e]);   // projection on the l1 ball
                             const float dlt = xn - xo[e];
                             xi[e] = xn;
@@ -313,7 +322,8 @@ __global__ void __launch_bounds__(PX_THREADS) prox_graph3_kernel(GraphArgs a) {
 }
 
 int launch_prox_graph3(const float* U, float* V, float* xi, float* tot, const float* eta, long long ld, int rows, int cols, int n,
-                       float lam, int max_sweeps, float tol, int* sweeps_out, const DevState* st, cudaStream_t s) {
+                       float lam, int max_sweeps, float tol, int* sweeps_out, const DevState* st, cudaStream_t s, int center,
+                       long long eta_stride) {
     static int blocks_per_sm = 0, num_sms = 0;
     static unsigned int* change_bits = nullptr;
     if (blocks_per_sm == 0) {
@@ -327,6 +337,8 @@ int launch_prox_graph3(const float* U, float* V, float* xi, float* tot, const fl
     GraphArgs a;
     a.U = U; a.V = V; a.xi = xi; a.tot = tot; a.eta = eta; a.ld = ld; a.rows = rows; a.cols = cols; a.n = n; a.lam = lam;
     a.max_sweeps = max_sweeps; a.tol = tol; a.sweeps_out = sweeps_out; a.change_bits = change_bits; a.st = st;
+    a.center = center; a.eta_stride = eta_stride;
+    if (center && eta == nullptr) { set_error("prox_graph3: centre mode needs the per-frame eta map"); return -1; }
     const long long nw9 = ((long long)rows * cols / 9 + 1) * n;
     long long want = (nw9 + PX_THREADS - 1) / PX_THREADS;
     long long maxb = (long long)blocks_per_sm * num_sms;

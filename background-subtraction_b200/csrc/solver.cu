@@ -109,12 +109,12 @@ int bsub_destroy(bsub_solver* s) {
 int bsub_create(const bsub_config* cfg, bsub_solver** out) {
     if (!cfg || !out) { set_error("bsub_create: null argument"); return -1; }
     if (cfg->m <= 0 || cfg->n <= 0) { set_error("bsub_create: empty matrix (m=%lld, n=%d)", (long long)cfg->m, cfg->n); return -1; }
-    if (cfg->prox < 0 || cfg->prox > 3) { set_error("bsub_create: unknown prox %d", cfg->prox); return -1; }
-    if ((cfg->prox == BSUB_PROX_FLAT_LINF || cfg->prox == BSUB_PROX_GRAPH_LINF) &&
+    if (cfg->prox < 0 || cfg->prox > 4) { set_error("bsub_create: unknown prox %d", cfg->prox); return -1; }
+    if ((cfg->prox == BSUB_PROX_FLAT_LINF || cfg->prox == BSUB_PROX_GRAPH_LINF || cfg->prox == BSUB_PROX_GRAPH_CENTER_BG) &&
         ((long long)cfg->rows * cfg->cols != cfg->m)) {
         set_error("bsub_create: rows*cols (%d*%d) != m (%lld)", cfg->rows, cfg->cols, (long long)cfg->m); return -1;
     }
-    if (cfg->prox == BSUB_PROX_GRAPH_LINF && (cfg->group_rows != 3 || cfg->group_cols != 3)) {
+    if ((cfg->prox == BSUB_PROX_GRAPH_LINF || cfg->prox == BSUB_PROX_GRAPH_CENTER_BG) && (cfg->group_rows != 3 || cfg->group_cols != 3)) {
         set_error("bsub_create: overlapping windows are implemented for the reference's 3x3 BLOCK_SIZE only"); return -1;
     }
     bsub_solver* s = new bsub_solver();
@@ -285,6 +285,27 @@ int bsub_set_graph_windows(bsub_solver* s, const double* eta, int64_t n_eta) {
     return 0;
 }
 
+int bsub_set_center_windows(bsub_solver* s, const float* eta, const uint8_t* background) {
+    if (!s || !eta || !background) { set_error("bsub_set_center_windows: null argument"); return -1; }
+    if (s->cfg.prox != BSUB_PROX_GRAPH_CENTER_BG) { set_error("bsub_set_center_windows: solver was not created with BSUB_PROX_GRAPH_CENTER_BG"); return -1; }
+    const size_t nm = (size_t)s->n * s->m;
+    // background pixels form label 0 (the "complement" group of the l2 kernels, shrunk at non_block_lambda = 100 lambda);
+    // everything else gets a label no group uses and keeps the graph prox result
+    std::vector<unsigned char> lab(nm);
+    for (size_t i = 0; i < nm; ++i) lab[i] = background[i] ? 0 : 255;
+    if (!s->eta_dev) CK(cudaMalloc((void**)&s->eta_dev, sizeof(float) * nm));
+    if (!s->labels_dev) CK(cudaMalloc((void**)&s->labels_dev, nm));
+    if (!s->bsums) CK(cudaMalloc((void**)&s->bsums, sizeof(double) * s->n));
+    CK(cudaMemcpy(s->eta_dev, eta, sizeof(float) * nm, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s->labels_dev, lab.data(), nm, cudaMemcpyHostToDevice));
+    s->nlab = 1;
+    if (!s->xi) CK(cudaMalloc((void**)&s->xi, sizeof(float) * nm * 9));          // one candidate window per pixel and frame
+    if (!s->tot) CK(cudaMalloc((void**)&s->tot, sizeof(float) * (size_t)s->n * s->ld));
+    if (!s->sweeps_dev) CK(cudaMalloc((void**)&s->sweeps_dev, sizeof(int)));
+    s->graph_set = true;
+    return 0;
+}
+
 int bsub_set_blocks(bsub_solver* s, const uint8_t* labels, const int32_t* lam_ptr, const double* lam) {
     if (!s || !labels || !lam_ptr) { set_error("bsub_set_blocks: null argument"); return -1; }
     if (s->cfg.prox != BSUB_PROX_BLOCK_L2) { set_error("bsub_set_blocks: solver was not created with BSUB_PROX_BLOCK_L2"); return -1; }
@@ -403,7 +424,7 @@ static int check_ready(bsub_solver* s) {
     if (!s) { set_error("null solver"); return -1; }
     if (!s->loaded) { set_error("no data loaded (call bsub_load_* first)"); return -1; }
     if (s->cfg.prox == BSUB_PROX_FLAT_LINF && !s->groups_set) { set_error("one of graphs or groups must not be None"); return -1; }
-    if (s->cfg.prox == BSUB_PROX_GRAPH_LINF && !s->graph_set) { set_error("one of graphs or groups must not be None"); return -1; }
+    if ((s->cfg.prox == BSUB_PROX_GRAPH_LINF || s->cfg.prox == BSUB_PROX_GRAPH_CENTER_BG) && !s->graph_set) { set_error("one of graphs or groups must not be None"); return -1; }
     if (s->cfg.prox == BSUB_PROX_BLOCK_L2 && !s->blocks_set) { set_error("blocks_by_frame / lambdas_by_frame not set"); return -1; }
     return 0;
 }
@@ -486,6 +507,12 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
         } else if (s->cfg.prox == BSUB_PROX_GRAPH_LINF) {
             RET_IF(launch_prox_graph3(s->U, s->S, s->xi, s->tot, s->eta_dev, s->ld, s->cfg.rows, s->cfg.cols, s->n, 0.f,
                                       s->cfg.graph_max_sweeps, (float)s->cfg.graph_tol, s->sweeps_dev, s->st, st));
+        } else if (s->cfg.prox == BSUB_PROX_GRAPH_CENTER_BG) {
+            // S = prox_by_frame(G_S) then the background pixels of every frame are overwritten by their l2 shrink of G_S
+            RET_IF(launch_prox_graph3(s->U, s->S, s->xi, s->tot, s->eta_dev, s->ld, s->cfg.rows, s->cfg.cols, s->n, 0.f,
+                                      s->cfg.graph_max_sweeps, (float)s->cfg.graph_tol, s->sweeps_dev, s->st, st, 1, s->m));
+            RET_IF(launch_block_l2_sums(s->U, s->labels_dev, s->ld, s->m, s->n, 1, s->bsums, s->st, st));
+            RET_IF(launch_block_l2_apply(s->U, s->S, s->labels_dev, s->ld, s->m, s->n, 1, s->bsums, nullptr, s->st, 0.0, 0.0, st, 1));
         } else {   // BSUB_PROX_BLOCK_L2
             RET_IF(launch_block_l2_sums(s->U, s->labels_dev, s->ld, s->m, s->n, s->nlab, s->bsums, s->st, st));
             RET_IF(launch_block_l2_apply(s->U, s->S, s->labels_dev, s->ld, s->m, s->n, s->nlab, s->bsums, s->lam_table, s->st, 0.0,

@@ -30,7 +30,10 @@ enum {
     BSUB_PROX_FLAT_LINF = 0,   /* spams.proximalFlat 'group-lasso-linf'      inexact_alm_lsd.py:71-79,153-155 */
     BSUB_PROX_GRAPH_LINF = 1,  /* spams.proximalGraph 'graph' (overlapping)   inexact_alm_lsd.py:49-57,159     */
     BSUB_PROX_BLOCK_L2 = 2,    /* block_shrinkage_operator                    group_sparse_RPCA.py:13-42       */
-    BSUB_PROX_L1 = 3           /* elementwise soft threshold                  lsd_improvement.py:176           */
+    BSUB_PROX_L1 = 3,          /* elementwise soft threshold                  lsd_improvement.py:176           */
+    BSUB_PROX_GRAPH_CENTER_BG = 4 /* per-frame windows centred on weighted pixels (prox_by_frame, inexact_alm_lsd.py:60-68,
+                                  graphs of lsd_improvement.py:74-120) + l2 shrink of each frame's background
+                                  (lsd_improvement.py:199-212): inexact_alm_lsd_with_background, lsd_improvement.py:215-304 */
 };
 
 /* Replaces the hard-coded constants of inexact_alm_lsd.py:102-125 / group_sparse_RPCA.py:53-77. */
@@ -93,6 +96,10 @@ int bsub_set_graph_windows(bsub_solver* s, const double* eta_host, int64_t n_eta
 /* blocks: blocks_by_frame / lambdas_by_frame of group_sparse_RPCA.py:45 as a label map uint8[n][m] (0 = complement,
  *       b = block b of that frame) plus the CSR (lam_ptr[n+1], lam) of the per-frame lambda lists. */
 int bsub_set_blocks(bsub_solver* s, const uint8_t* labels_host, const int32_t* lam_ptr, const double* lam);
+/* per-frame centre windows + background (BSUB_PROX_GRAPH_CENTER_BG): eta_host float32[n][m] = weight of the 3x3 window
+ * centred on that pixel in that frame (<= 0: no window; get_proximal_graph_group_centers, lsd_improvement.py:74-120),
+ * background_host uint8[n][m] != 0 where the pixel belongs to the frame's background mask (lsd_improvement.py:434). */
+int bsub_set_center_windows(bsub_solver* s, const float* eta_host, const uint8_t* background_host);
 
 /* ---- data in ---------------------------------------------------------------------------------------------- */
 int bsub_load_D_f64_host(bsub_solver* s, const double* D, int64_t ld, void* stream);      /* host float64 (NumPy)   */

@@ -110,6 +110,31 @@ def graph_all_groups(img_shape, group_shape):
             np.ones(num_x * num_y, dtype=np.float64))
 
 
+def window_pixels_center(i, j, group_radius, img_shape):
+    """Pixel list of the window centred on (i, j), clipped to the image; restates get_vars_idx_center,
+    /root/reference/utils.py:234-246 (unlike the top-left variant the clipping here is exact)."""
+    rows, cols = img_shape
+    left, right = min(group_radius, j), min(group_radius, cols - 1 - j)
+    top, bottom = min(group_radius, i), min(group_radius, rows - 1 - i)
+    tl = (j - left) * rows + (i - top)
+    return [tl + di + rows * dj for dj in range(left + right + 1) for di in range(top + bottom + 1)]
+
+
+def graph_group_centers(img_shape, group_radius, group_centers):
+    """CSC (indptr, indices, eta) of the per-frame graph of windows centred on the pixels with a positive weight;
+    restates get_proximal_graph_group_centers, /root/reference/lsd_improvement.py:74-120 (centres enumerated
+    column by column, eta_g = weight of the centre pixel, no nesting)."""
+    rows, cols = img_shape
+    gc = np.asarray(group_centers)
+    cj, ci = np.where(gc.T > 0)
+    indptr, indices, eta = [0], [], []
+    for i, j in zip(ci, cj):
+        indices.extend(window_pixels_center(int(i), int(j), group_radius, (rows, cols)))
+        indptr.append(len(indices))
+        eta.append(float(gc[i, j]))
+    return (np.asarray(indptr, dtype=np.int32), np.asarray(indices, dtype=np.int32), np.asarray(eta, dtype=np.float64))
+
+
 def graph_from_spams_dict(graph):
     """(indptr, indices, eta) from the SPAMS graph dict the reference passes around
     ({'eta_g','groups','groups_var'}, /root/reference/inexact_alm_lsd.py:45)."""
@@ -341,6 +366,35 @@ def inexact_alm_rpca(D0, delta=1.0, use_sv_prediction=False, log=None, max_iter=
         return np.sign(G_S) * np.maximum(np.abs(G_S) - lam / mu, 0)
     return _alm(D0, prox_fn, 1.25, delta, rho=1.2, use_sv_prediction=use_sv_prediction,
                 sv0=10, log=log, max_iter=max_iter)
+
+
+def apply_background_shrinkage_operator(G, output, epsilon, background_masks):
+    """One l2 group per frame over the frame's background pixels, written over `output`; restates
+    /root/reference/lsd_improvement.py:199-212 (zero norm -> factor max(-inf, 0) = 0)."""
+    for f in range(len(background_masks)):
+        mask = np.asarray(background_masks[f], dtype=bool)
+        g = G[mask, f]
+        nrm = LA.norm(g, ord=2)
+        fac = max(1 - epsilon / nrm, 0) if nrm > 0 else 0.0
+        output[mask, f] = fac * g
+    return output
+
+
+def inexact_alm_lsd_with_background(D0, graphs, background_masks, delta=10, log=None, prox_tol=1e-13,
+                                    prox_max_sweeps=20000, max_iter=500):
+    """Restates /root/reference/lsd_improvement.py:215-304: the LSD loop with one graph per frame
+    (prox_by_frame) followed by an l2 shrink of every frame's background pixels at 100 lambda / mu."""
+    if not isinstance(graphs, list) and not isinstance(graphs, np.ndarray):
+        raise Exception('graphs must be list/array')
+    m, n = np.shape(D0)
+    lambda_param = (np.sqrt(max(m, n)) * delta) ** (-1)
+    background_lambda = 1e2 * lambda_param
+    gl = [graph_from_spams_dict(g) if isinstance(g, dict) else g for g in graphs]
+
+    def prox_fn(G_S, lam, mu):
+        S = prox_by_frame(G_S, lam / mu, gl, tol=prox_tol, max_sweeps=prox_max_sweeps)
+        return apply_background_shrinkage_operator(G_S, S, background_lambda / mu, background_masks)
+    return _alm(D0, prox_fn, 12.5, delta, log=log, max_iter=max_iter)
 
 
 def normalize_and_center(cube):

@@ -82,6 +82,27 @@ def test_detect_rejects_other_inputs():
     assert B.detect_window_graph(graph, 72) is None
 
 
+def test_center_window_graphs():
+    """get_proximal_graph_group_centers mirror: same CSC arrays as the oracle restatement (utils.py:234-246,
+    lsd_improvement.py:74-120), recoverable from a bare SPAMS dict, not confused with the all-windows graph."""
+    import background_subtraction_b200 as B
+    from oracle import alm_oracle as O
+    rng = np.random.default_rng(0)
+    for shape in ((7, 9), (12, 5), (3, 3)):
+        w = np.where(rng.random(shape) < 0.35, rng.choice([1.0, 1.5], shape), -1.0)
+        w[0, 0], w[-1, -1] = 1.5, 1.0
+        p, i, e = B.center_window_csc(shape, w)
+        p2, i2, e2 = O.graph_group_centers(shape, 1, w)
+        assert np.array_equal(p, p2) and np.array_equal(i, i2) and np.array_equal(e, e2)
+        g = B.get_proximal_graph_group_centers(shape, 1, w)
+        bare = {k: v for k, v in g.items() if not k.startswith('_')}
+        emap = np.where(w > 0, w, 0).astype(np.float32).flatten(order='F')
+        for cand in (g, bare):
+            det = B.detect_center_windows(cand, w.size)
+            assert det is not None and det[0] == shape and np.array_equal(det[1], emap)
+    assert B.detect_center_windows(B.getGraphSPAMS_all_groups((7, 9), (3, 3)), 63) is None
+
+
 def test_labels_from_blocks():
     m, n = 10, 3
     b0 = np.zeros(m, bool); b0[:4] = True
