@@ -231,7 +231,7 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
 template <int KCNT, int NTC>
 __device__ __forceinline__ void ss_phase_b(const ShrinkStreamArgs& a, float* ring, size_t stage_floats, const float* Tp, const float* VC_s,
                                            uint64_t* full, uint64_t* done, long long& q, int ct, int lane, int NG, int R, int P, int FC,
-                                           int NS, int ncf, bool wq, float inv_mu, float mu_f, float lamq, float inv_mu_next, float Qf,
+                                           int BS, int QS, int NS, int ncf, bool wq, float inv_mu, float mu_f, float lamq, float inv_mu_next, float Qf,
                                            double& zz_acc, unsigned int& nnz_acc, float& max_acc, float& wmax_acc, int& sat_acc) {
     for (int c = 0; c < ncf; ++c, ++q) {
         const int s = (int)(q % NS);
@@ -244,10 +244,10 @@ __device__ __forceinline__ void ss_phase_b(const ShrinkStreamArgs& a, float* rin
             const int fg = fbase + f;
             if (fg >= a.n) continue;
             float* dsp = b + (size_t)f * P + 3 * g;
-            float* ysp = b + (size_t)2 * a.BS + (size_t)f * P + 3 * g;
-            unsigned char* qb = wq ? (reinterpret_cast<unsigned char*>(b + (size_t)a.BS) + (size_t)f * 16) : nullptr;
+            float* ysp = b + (size_t)2 * BS + (size_t)f * P + 3 * g;
+            unsigned char* qb = wq ? (reinterpret_cast<unsigned char*>(b + (size_t)BS) + (size_t)f * 16) : nullptr;
             ss_group<KCNT>(dsp, ysp, Tp + 12 * g, 12 * NG, VC_s + (size_t)fg * SS_KC, R, P, inv_mu, mu_f, lamq, a.mode, zz_acc, nnz_acc,
-                           max_acc, qb, a.QS, 3 * g, FC * 16, inv_mu_next, Qf, wmax_acc, sat_acc);
+                           max_acc, qb, QS, 3 * g, FC * 16, inv_mu_next, Qf, wmax_acc, sat_acc);
         }
         fence_proxy_async_smem();                   // my writes -> visible to the storer's TMA stores
         __syncwarp();
@@ -255,7 +255,10 @@ __device__ __forceinline__ void ss_phase_b(const ShrinkStreamArgs& a, float* rin
     }
 }
 
-template <int NCW>      // number of consumer warps; block = 32 * (NCW + 2)
+// NCW: consumer warps (block = 32 * (NCW + 2)).  RT / FCT: tile rows and frames per stage as compile-time constants
+// (0 = take them from the arguments): with the default plan (48 rows, 28 frames) every index computation of the inner
+// loops folds into immediates and shifts.
+template <int NCW, int RT, int FCT>
 __global__ void __launch_bounds__(32 * (NCW + 2), 1)
 shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_constant__ CUtensorMap mapS,
                      const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapOut,
@@ -269,7 +272,8 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
         return;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int P = a.P, NQ = a.NQ, NFL = a.NFL, R = a.R, FC = a.FC, NS = a.NS;
+    const int R = RT ? RT : a.R, P = 3 * R, NQ = P / 4, NFL = (32 * NCW) / NQ, FC = FCT ? FCT : a.FC, NS = a.NS;
+    const int BS = (RT && FCT) ? ((FCT * 3 * RT + 127) / 128 * 128) : a.BS, QS = (RT && FCT) ? ((FCT * 3 * RT + 127) / 128 * 128) : a.QS;
     const double mu_d = st->mu;
     const float inv_mu = (float)(1.0 / mu_d), mu_f = (float)mu_d;
     const float lamq = (float)(st->lambda / mu_d);
@@ -281,7 +285,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
     int sat_acc = 0;
 
     extern __shared__ __align__(128) unsigned char ss_smem_raw[];
-    const size_t stage_floats = (size_t)3 * a.BS;
+    const size_t stage_floats = (size_t)3 * BS;
     float* ring = reinterpret_cast<float*>(ss_smem_raw);            // [NS][3][BS]
     float* scr = ring + (size_t)NS * stage_floats;                  // [NFL][SS_KRED][P]   (T reduction)
     float* Tp = scr + (size_t)NFL * SS_KRED * P;                    // [SS_KC][R/3 groups][12]: T of the tile, 9 entries per 3x3 group
@@ -393,7 +397,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                     const long long u = q / NS;
                     mbar_wait(&full[s], (uint32_t)(u & 1));
                     const float* b = ring + (size_t)s * stage_floats;
-                    if (tact) { SS_DISPATCH_K(r, (ss_accumulate<K_>(acc, b, b + a.BS, b + 2 * a.BS, Vr_s, P, qd, fl, NFL, FC, c * FC, a.n, inv_mu))); }
+                    if (tact) { SS_DISPATCH_K(r, (ss_accumulate<K_>(acc, b, b + BS, b + 2 * BS, Vr_s, P, qd, fl, NFL, FC, c * FC, a.n, inv_mu))); }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&done[s]);
                 }
@@ -430,7 +434,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                 }
             }
             // phase B
-            SS_DISPATCH_K(r, (ss_phase_b<K_, NTC>(a, ring, stage_floats, Tp, VC_s, full, done, q, ct, lane, NG, R, P, FC, NS, ncf, wq, inv_mu,
+            SS_DISPATCH_K(r, (ss_phase_b<K_, NTC>(a, ring, stage_floats, Tp, VC_s, full, done, q, ct, lane, NG, R, P, FC, BS, QS, NS, ncf, wq, inv_mu,
                                                   mu_f, lamq, inv_mu_next, Qf, zz_acc, nnz_acc, max_acc, wmax_acc, sat_acc)));
         }
     }
@@ -521,15 +525,15 @@ int make_shrink_stream_qmap(const ShrinkStreamPlan& p, signed char* Wq, ShrinkTm
     return 0;
 }
 
-template <int NCW>
+template <int NCW, int RT, int FCT>
 static int launch_ss(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, const ShrinkStreamArgs& a, int mode, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        BSUB_CUDA_CHECK(cudaFuncSetAttribute(shrink_stream_kernel<NCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM_CAP));
+        BSUB_CUDA_CHECK(cudaFuncSetAttribute(shrink_stream_kernel<NCW, RT, FCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM_CAP));
         attr_set = true;
     }
     const CUtensorMap& outmap = (mode == SHRINK_SPILL) ? maps.U : maps.S;
-    shrink_stream_kernel<NCW><<<p.grid, 32 * (NCW + 2), p.smem_bytes, stream>>>(maps.D, maps.S, maps.Y, outmap, maps.Q, a);
+    shrink_stream_kernel<NCW, RT, FCT><<<p.grid, 32 * (NCW + 2), p.smem_bytes, stream>>>(maps.D, maps.S, maps.Y, outmap, maps.Q, a);
     BSUB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -544,8 +548,9 @@ int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, S
     a.part_max = b.part_max; a.part_wmax = b.part_wmax; a.mode = mode;
     a.wq = (maps.has_Q && b.part_wmax != nullptr) ? 1 : 0; a.Pq = p.P;
     a.QS = (int)(((size_t)p.FC * p.P + 127) / 128 * 128);
-    if (p.NCW == 16) return launch_ss<16>(p, maps, a, mode, stream);
-    return launch_ss<8>(p, maps, a, mode, stream);
+    if (p.NCW == 16) return launch_ss<16, 0, 0>(p, maps, a, mode, stream);
+    if (p.R == 48 && p.FC == 28) return launch_ss<8, 48, 28>(p, maps, a, mode, stream);
+    return launch_ss<8, 0, 0>(p, maps, a, mode, stream);
 }
 
 }  // namespace bsub
