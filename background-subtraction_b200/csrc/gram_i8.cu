@@ -16,11 +16,15 @@
 //   warp 1     MMA issuer (one elected thread): tcgen05.mma, tcgen05.commit -> mbarriers
 //   warp 2     TMEM allocator (512 columns = 4 classes x 128)
 //   warps 4-7  epilogue: tcgen05.ld of the four class accumulators, recombination into int64, atomicAdd to global
+#include <cooperative_groups.h>
+#include <stdio.h>
 #include <algorithm>
 #include <vector>
 #include "common.cuh"
 #include "kernels.h"
 #include "tma.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace bsub {
 
@@ -130,8 +134,8 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                 mbar_expect_tx(&full[s], tx);
                 const int k16 = (kb0 + kb * kstride) * (GI_KB / 16);
                 for (int sl = 0; sl < 4; ++sl) {
-                    tma_load_4d(base + (size_t)sl * GI_TILE_BYTES, &mapQ, &full[s], 0, bi * 128, k16, sl);
-                    if (!diag) tma_load_4d(base + (size_t)(4 + sl) * GI_TILE_BYTES, narrowB ? &mapQlast : &mapQ, &full[s], 0, bj * 128, k16, sl);
+                    tma_load_3d(base + (size_t)sl * GI_TILE_BYTES, &mapQ, &full[s], bi * 256, k16, sl);
+                    if (!diag) tma_load_3d(base + (size_t)(4 + sl) * GI_TILE_BYTES, narrowB ? &mapQlast : &mapQ, &full[s], bj * 256, k16, sl);
                 }
             }
         }
@@ -210,6 +214,196 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         }
     }
     __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Three frame blocks (256 < n <= 384, the 300-frame clips): clusters of 3 CTAs share operand tiles through TMA multicast.
+// gram_i8_kernel above is bound by L2 -> SM bytes: every 128-frame block is fetched by each of the block pairs that use
+// it (912 frame rows per 64-pixel step for n = 300).  Here a cluster owns a block ROW of the output triangle:
+//   type X  rank 0: (0,0)   rank 1: (0,1)   rank 2: (0,2)     block 0 -> slot A of all three (one multicast load)
+//   type Y  rank 0: (1,1)   rank 1: (1,2)   rank 2: (2,2)     block 1 -> slot A of ranks 0,1; block 2 -> slot B of ranks 1,2
+// => 300 + 172 = 472 rows per step.  Stage hand-back: the MMA thread commits (tcgen05.commit ... multicast::cluster) to
+// the `empty` barrier of every CTA that supplied one of its operands, and to its own `mine` barrier, which paces the
+// re-arming of its `full` barrier.  X and Y clusters cost the same per step and take alternating pixel blocks.
+struct GramI8C3Args {
+    int n, nkb;                           // frames; 64-pixel stages in the slice matrix
+    int nX, nY;                           // clusters of each type (cluster id < nX: type X)
+    int n2;                               // MMA N of frame block 2 (multiple of 16)
+    int prefetch_dist;                    // stages the L2 prefetch runs ahead of the loads
+    unsigned long long* Gint;
+    const DevState* st;
+    int require_mode;
+};
+
+__device__ __forceinline__ void gi_tma_load_3d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                                  uint16_t cta_mask) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void gi_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
+__global__ void __launch_bounds__(GI_THREADS, 1)
+gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
+    if (a.st != nullptr && (a.st->done || a.st->gram_mode != a.require_mode)) return;      // uniform over the grid
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(1024) unsigned char gi_smem[];
+    unsigned char* stages = gi_smem;                                             // [GI_STAGES][A: 4 planes | B: 4 planes][128][64]
+    uint64_t* full = reinterpret_cast<uint64_t*>(gi_smem + (size_t)GI_STAGES * GI_STAGE_BYTES);   // [GI_STAGES]
+    uint64_t* empty = full + GI_STAGES;                                          // [GI_STAGES] consumers of the slot I load are done
+    uint64_t* mine = empty + GI_STAGES;                                          // [GI_STAGES] my own MMAs on the stage are done
+    uint64_t* tmem_full = mine + GI_STAGES;
+    uint64_t* tmem_empty = tmem_full + 1;
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster.block_rank();
+    const int cid = blockIdx.x / 3;
+    const bool tX = cid < a.nX;
+    const int kb0 = tX ? cid : cid - a.nX, kstride = tX ? a.nX : a.nY;
+    const int nkb = (a.nkb > kb0) ? (a.nkb - kb0 + kstride - 1) / kstride : 0;
+    // role table (see the header comment)
+    const int bi = tX ? 0 : (rank == 2 ? 2 : 1);
+    const int bj = tX ? rank : (rank == 0 ? 1 : 2);
+    const bool useA = tX || rank < 2, useB = tX ? (rank > 0) : (rank > 0);
+    const bool diag = (bi == bj);
+    const int Nj = (bj == 2) ? a.n2 : 128;
+    // what I load: slot (0 = A, 1 = B), frame block, destination CTAs
+    int ld_slot = -1, ld_blk = 0; uint16_t ld_mask = 0;
+    if (tX) { if (rank == 0) { ld_slot = 0; ld_blk = 0; ld_mask = 0x7; } else { ld_slot = 1; ld_blk = rank; ld_mask = (uint16_t)(1u << rank); } }
+    else { if (rank == 0) { ld_slot = 0; ld_blk = 1; ld_mask = 0x3; } else if (rank == 1) { ld_slot = 1; ld_blk = 2; ld_mask = 0x6; } }
+    // who supplies my operands
+    const uint16_t sup_mask = tX ? (uint16_t)(0x1 | (rank > 0 ? (1u << rank) : 0u)) : (uint16_t)(rank == 0 ? 0x1 : (rank == 1 ? 0x3 : 0x2));
+    const int n_consumers = __popc((unsigned)ld_mask);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GI_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], n_consumers > 0 ? n_consumers : 1); mbar_init(&mine[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 128);
+        mbar_fence_init();
+        tma_prefetch_desc(&mapQ);
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster.sync();                                        // barriers of all three CTAs exist before anything is signalled
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0) {
+        // ===================== TMA producer: arms my full barrier, loads the slot I own =====================
+        if (lane == 0) {
+            const uint32_t tx = (uint32_t)((useA ? 4 : 0) + (useB ? 4 : 0)) * GI_TILE_BYTES;
+            // every operand byte is fetched from DRAM exactly once per cluster type, so the three smem stages alone do not
+            // keep enough bytes in flight to cover the DRAM latency: an L2 prefetch runs `pd` stages ahead of the loads
+            const int pd = a.prefetch_dist;
+            auto prefetch = [&](int kb) {
+                if (ld_slot < 0 || kb >= nkb) return;
+                const int k16 = (kb0 + kb * kstride) * (GI_KB / 16);
+                for (int sl = 0; sl < 4; ++sl)
+                    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
+                                 ::"l"(&mapQ), "r"(ld_blk * 256), "r"(k16), "r"(sl) : "memory");
+            };
+            for (int kb = 0; kb < pd; ++kb) prefetch(kb);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % GI_STAGES;
+                const int u = kb / GI_STAGES;
+                if (pd > 0) prefetch(kb + pd);
+                if (u > 0) gi_mbar_wait(&mine[s], (uint32_t)((u - 1) & 1));           // my MMAs of the previous round are done
+                mbar_expect_tx(&full[s], tx);
+                if (ld_slot >= 0) {
+                    if (u > 0) gi_mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));      // and so are those of everyone I feed
+                    unsigned char* base = stages + (size_t)s * GI_STAGE_BYTES + (size_t)ld_slot * 4 * GI_TILE_BYTES;
+                    const int k16 = (kb0 + kb * kstride) * (GI_KB / 16);
+                    for (int sl = 0; sl < 4; ++sl)
+                        gi_tma_load_3d_mc(base + (size_t)sl * GI_TILE_BYTES, &mapQ, &full[s], ld_blk * 256, k16, sl, ld_mask);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = gi_instr_desc(Nj);
+            const uint32_t offA = useA ? 0u : (uint32_t)(4 * GI_TILE_BYTES);             // (2,2) takes both operands from slot B
+            const uint32_t offB = diag ? offA : (uint32_t)(4 * GI_TILE_BYTES);
+            int since_flush = 0, nflush = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % GI_STAGES;
+                const int u = kb / GI_STAGES;
+                if (since_flush == 0 && nflush > 0) {
+                    gi_mbar_wait(tmem_empty, (uint32_t)((nflush - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                gi_mbar_wait(&full[s], (uint32_t)(u & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sbase = smem_u32(stages + (size_t)s * GI_STAGE_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < GI_KB / 32; ++ks) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int cls = i + j - 3;
+                            if (cls < 0) continue;
+                            const uint64_t da = gi_smem_desc(sbase + offA + (uint32_t)(i * GI_TILE_BYTES) + ks * 4096, 2048u);
+                            const uint64_t db = gi_smem_desc(sbase + offB + (uint32_t)(j * GI_TILE_BYTES) + ks * 4096, 2048u);
+                            const bool first = (since_flush == 0 && ks == 0 && j == 3);
+                            gi_mma(tmem_base + (uint32_t)(cls * 128), da, db, idesc, first ? 0u : 1u);
+                        }
+                }
+                gi_commit_mc(&empty[s], sup_mask);                                 // hand the operand slots back to their loaders
+                gi_commit(&mine[s]);
+                ++since_flush;
+                if (since_flush == GI_FLUSH_KB || kb == nkb - 1) {
+                    gi_commit(tmem_full);
+                    since_flush = 0; ++nflush;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue (as in gram_i8_kernel) =====================
+        const int ew = warp - 4;
+        const int nflush_total = (nkb + GI_FLUSH_KB - 1) / GI_FLUSH_KB;
+        const int row = bi * 128 + ew * 32 + lane;
+        const size_t ldg = (size_t)3 * 128;
+        for (int fl = 0; fl < nflush_total; ++fl) {
+            gi_mbar_wait(tmem_full, (uint32_t)(fl & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int c0 = 0; c0 < Nj; c0 += 16) {
+                uint32_t v3[16], v4[16], v5[16], v6[16];
+                const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0;
+                gi_tmem_ld16(ta + 0 * 128, v3);
+                gi_tmem_ld16(ta + 1 * 128, v4);
+                gi_tmem_ld16(ta + 2 * 128, v5);
+                gi_tmem_ld16(ta + 3 * 128, v6);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < a.n) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int col = bj * 128 + c0 + e;
+                        if (col < a.n) {
+                            const long long val = (long long)(int)v3[e] + ((long long)(int)v4[e] << 8) + ((long long)(int)v5[e] << 16) +
+                                                  ((long long)(int)v6[e] << 24);
+                            if (val != 0) atomicAdd(a.Gint + (size_t)row * ldg + col, (unsigned long long)val);
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            gi_mbar_arrive(tmem_empty);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster.sync();                                        // nobody leaves while a neighbour may still write or signal here
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -347,12 +541,14 @@ int gram_i8_last_block_n(const GramI8Plan& p) {
 }
 
 int make_gram_i8_map(const GramI8Plan& p, const signed char* Wq, CUtensorMap* map, int box_frames) {
-    // u8 tensor {16 B, n frames, ldq/16 k-blocks, 4 slices} (k-block-major slice matrix); boxes {16, 128, 4, 1};
+    // k-block-major slice matrix [slice][k16][frame][16 B]: the frames of one k16 block are contiguous (16 n bytes), so the
+    // map views them as 2 n eight-byte elements and a box row carries 16 * box_frames contiguous bytes (a 16-byte inner
+    // dimension would make the TMA unit issue one request per frame and cap the feed rate); boxes {2 box_frames, 4, 1};
     // frames beyond n read as zero
-    const uint64_t dims[4] = {16, (uint64_t)p.n, (uint64_t)(p.ldq / 16), 4};
-    const uint64_t strides[3] = {16, (uint64_t)16 * p.n, (uint64_t)p.ldq * (uint64_t)p.n};
-    const uint32_t box[4] = {16, (uint32_t)box_frames, 4, 1};
-    return make_tensor_map_u8(map, Wq, 4, dims, strides, box, 0);
+    const uint64_t dims[3] = {(uint64_t)2 * p.n, (uint64_t)(p.ldq / 16), 4};
+    const uint64_t strides[2] = {(uint64_t)16 * p.n, (uint64_t)p.ldq * (uint64_t)p.n};
+    const uint32_t box[3] = {(uint32_t)(2 * box_frames), 4, 1};
+    return make_tensor_map_u64(map, Wq, 3, dims, strides, box);
 }
 
 int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const CUtensorMap& map_last, const int4* cta_info_dev, int ncta, const int* blk_n_dev,
@@ -365,6 +561,37 @@ int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const CUtensorMa
     }
     const size_t gbytes = sizeof(unsigned long long) * (size_t)p.nblk * 128 * p.nblk * 128;
     BSUB_CUDA_CHECK(cudaMemsetAsync(Gint, 0, gbytes, stream));
+    // three frame blocks: the 3-CTA multicast clusters (gram_i8_c3_kernel); anything else: independent CTAs
+    static int c3_clusters = -1;                           // -1: not probed yet, 0: unavailable
+    if (p.nblk == 3 && c3_clusters != 0) {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 3; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(GI_THREADS); cfg.dynamicSmemBytes = p.smem_bytes; cfg.stream = stream; cfg.attrs = at; cfg.numAttrs = 1;
+        if (c3_clusters < 0) {
+            c3_clusters = 0;
+            if (getenv("BSUB_NO_GRAM_CLUSTER") == nullptr &&
+                cudaFuncSetAttribute(gram_i8_c3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes) == cudaSuccess) {
+                cfg.gridDim = dim3(3 * (p.grid / 3));
+                int ncl = 0;
+                if (cudaOccupancyMaxActiveClusters(&ncl, gram_i8_c3_kernel, &cfg) == cudaSuccess && ncl >= 2) c3_clusters = std::min(ncl, p.grid / 3);
+            }
+            (void)cudaGetLastError();
+            if (getenv("BSUB_DEBUG")) fprintf(stderr, "gram_i8: %d multicast clusters of 3 CTAs\n", c3_clusters);
+        }
+        if (c3_clusters >= 2) {
+            GramI8C3Args c;
+            c.n = p.n; c.nkb = p.nkb; c.nX = (c3_clusters + 1) / 2; c.nY = c3_clusters / 2; c.n2 = gram_i8_last_block_n(p);
+            c.Gint = Gint; c.st = st; c.require_mode = require_mode;
+            { static const int pd = getenv("BSUB_GRAM_PREFETCH") ? atoi(getenv("BSUB_GRAM_PREFETCH")) : 0; c.prefetch_dist = pd; }
+            cfg.gridDim = dim3(3 * c3_clusters);
+            BSUB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_c3_kernel, map, c));
+            gram_i8_finish_kernel<<<64, 256, 0, stream>>>(Gint, p.nblk, p.n, npad, G, st, scale_override, require_mode);
+            BSUB_CUDA_CHECK(cudaGetLastError());
+            return 0;
+        }
+    }
     GramI8Args a;
     a.n = p.n; a.nblk = p.nblk; a.nkb = p.nkb; a.cta_info = cta_info_dev; a.blk_n = blk_n_dev; a.Gint = Gint; a.st = st; a.require_mode = require_mode;
     gram_i8_kernel<<<ncta, GI_THREADS, p.smem_bytes, stream>>>(map, map_last, a);

@@ -367,7 +367,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                         if (a.mode != SHRINK_SPILL) tma_store_3d_hint(&mapY, b + (size_t)2 * a.BS, i0, j0, fbase, pol_stream);
                         if (wq) {                      // four byte planes of W_next, pixel order = tile-major (gram_i8.cu does not care)
                             const unsigned char* qbase = reinterpret_cast<const unsigned char*>(b + (size_t)a.BS);
-                            for (int sl = 0; sl < 4; ++sl) tma_store_4d(&mapQ, qbase + (size_t)sl * a.QS, 0, fbase, (int)(tl * (P / 16)), sl);
+                            for (int sl = 0; sl < 4; ++sl) tma_store_3d(&mapQ, qbase + (size_t)sl * a.QS, 2 * fbase, (int)(tl * (P / 16)), sl);
                         }
                         tma_store_commit();
                         tma_store_wait_read<0>();                                                  // stage may be overwritten
@@ -516,11 +516,12 @@ long long shrink_stream_ldq(const ShrinkStreamPlan& p) { return (p.P % 16 == 0) 
 
 int make_shrink_stream_qmap(const ShrinkStreamPlan& p, signed char* Wq, ShrinkTmaMaps* m) {
     const long long ldq = shrink_stream_ldq(p);
-    // [slice][k16][frame][16 B]; a tile's chunk of FC frames is one box {16, FC, P/16, 1} per plane
-    const uint64_t dims[4] = {16, (uint64_t)p.n, (uint64_t)(ldq / 16), 4};
-    const uint64_t strides[3] = {16, (uint64_t)16 * p.n, (uint64_t)ldq * (uint64_t)p.n};
-    const uint32_t box[4] = {16, (uint32_t)p.FC, (uint32_t)(p.P / 16), 1};
-    if (make_tensor_map_u8(&m->Q, Wq, 4, dims, strides, box, 0) != 0) return -1;
+    // [slice][k16][frame][16 B]; the frames of a k16 block are contiguous, so the map views them as 2 n eight-byte elements:
+    // a tile's chunk of FC frames is one box {2 FC, P/16, 1} per plane whose rows are 16 FC contiguous bytes
+    const uint64_t dims[3] = {(uint64_t)2 * p.n, (uint64_t)(ldq / 16), 4};
+    const uint64_t strides[2] = {(uint64_t)16 * p.n, (uint64_t)ldq * (uint64_t)p.n};
+    const uint32_t box[3] = {(uint32_t)(2 * p.FC), (uint32_t)(p.P / 16), 1};
+    if (make_tensor_map_u64(&m->Q, Wq, 3, dims, strides, box) != 0) return -1;
     m->has_Q = true;
     return 0;
 }

@@ -11,6 +11,9 @@ namespace bsub {
 // rank-2 or rank-3 float32 tensor map.  dims/box are innermost-first; strides_bytes[i] is the byte stride of dim i+1.
 int make_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                         const uint32_t* box);
+// 8-byte-element tensor map (no swizzle): lets one box row span up to 2 KB of contiguous bytes (boxDim <= 256 elements)
+int make_tensor_map_u64(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box);
 // uint8 tensor map; swizzle_bytes in {0, 32, 64, 128}
 int make_tensor_map_u8(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                        const uint32_t* box, int swizzle_bytes);
