@@ -143,6 +143,45 @@ __device__ void eig_control(const EigArgs& a, DevState* st, int K, double mu, do
     }
 }
 
+// ---- back-transformation z <- H_0 H_1 ... H_{n-3} z of the tridiagonal eigenvectors, one warp per vector.  The vector
+// lives in registers (lane owns entries lane + 32 t), the next reflector row is prefetched from L2 while the current one is
+// applied: a step costs one register dot product, one warp all-reduce and one register update.
+template <int NT>
+__device__ void eig_backtransform(const EigArgs& a, int K, const double* tau_s, int warp, int lane) {
+    const int n = a.n;
+    auto load_row = [&](int j, auto& v) {          // reflector j: entries i > j (the rest of the row is not part of it)
+        const double* vh = a.Vh + (size_t)(j < 0 ? 0 : j) * n;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { const int i = lane + 32 * t; v[t] = (j >= 0 && i > j && i < n) ? ldcg_d(vh + i) : 0.0; }
+    };
+    for (int k = warp; k < K; k += EIG_WARPS) {
+        constexpr bool DEEP = (NT <= 10);                   // second prefetch level only while the registers last
+        double z[NT], v0[NT], v1[NT], v2[DEEP ? NT : 1];    // current reflector and the next one or two (an L2 round trip is ~2 steps)
+        double* zrow = a.Z + (size_t)k * n;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { const int i = lane + 32 * t; z[t] = (i < n) ? zrow[i] : 0.0; }
+        load_row(n - 3, v0);
+        load_row(n - 4, v1);
+        for (int j = n - 3; j >= 0; --j) {
+            if constexpr (DEEP) load_row(j - 2, v2);
+            const double tau = tau_s[j];
+            if (tau != 0.0) {
+                double sa = 0.0, sb = 0.0;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) { if (t & 1) sb = fma(v0[t], z[t], sb); else sa = fma(v0[t], z[t], sa); }
+                const double s = warp_allsum(sa + sb) * tau;
+#pragma unroll
+                for (int t = 0; t < NT; ++t) z[t] = fma(-s, v0[t], z[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < NT; ++t) { v0[t] = v1[t]; if constexpr (DEEP) v1[t] = v2[t]; }
+            if constexpr (!DEEP) load_row(j - 2, v1);
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) { const int i = lane + 32 * t; if (i < n) zrow[i] = z[t]; }
+    }
+}
+
 // ---- Householder tridiagonalisation with the matrix rows in shared memory, dealt cyclically over the cluster.
 // Both exchanges of a step go through distributed shared memory: (1) after its rank-2 update every CTA pushes its
 // entries of the next column into all CTAs, so every warp forms the reflector redundantly; (2) every CTA pushes its
@@ -593,58 +632,13 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
     double* tau_s = d_s;                                  // d_s / e_s / e2_s are dead now
     for (int i = tid; i < n; i += EIG_THREADS) tau_s[i] = a.tau[i];
     __syncthreads();
-    constexpr int VHR = 20;                               // register prefetch covers n <= 32 * VHR
-    for (int kb = 0; kb < K; kb += EIG_BT) {
-        const int k = kb + warp;
-        if (warp < EIG_BT && k < K) {
-            double* z = zs + (size_t)warp * n;
-            const double* zrow = a.Z + (size_t)k * n;
-            for (int i = lane; i < n; i += 32) z[i] = zrow[i];
-            __syncwarp();
-            if (n <= 32 * VHR) {
-                double vcur[VHR], vnxt[VHR];
-                {
-                    const int j = n - 3;
-                    const double* vh = a.Vh + (size_t)(j < 0 ? 0 : j) * n;
-#pragma unroll
-                    for (int t = 0; t < VHR; ++t) { const int i = j + 1 + lane + 32 * t; vcur[t] = (j >= 0 && i < n) ? vh[i] : 0.0; }
-                }
-                for (int j = n - 3; j >= 0; --j) {
-                    if (j > 0) {
-                        const double* vh = a.Vh + (size_t)(j - 1) * n;
-#pragma unroll
-                        for (int t = 0; t < VHR; ++t) { const int i = j + lane + 32 * t; vnxt[t] = (i < n) ? vh[i] : 0.0; }
-                    }
-                    const double tau = tau_s[j];
-                    if (tau != 0.0) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int t = 0; t < VHR; ++t) { const int i = j + 1 + lane + 32 * t; if (i < n) s = fma(vcur[t], z[i], s); }
-                        s = warp_sum(s) * tau;
-#pragma unroll
-                        for (int t = 0; t < VHR; ++t) { const int i = j + 1 + lane + 32 * t; if (i < n) z[i] -= s * vcur[t]; }
-                        __syncwarp();
-                    }
-#pragma unroll
-                    for (int t = 0; t < VHR; ++t) vcur[t] = vnxt[t];
-                }
-            } else {
-                for (int j = n - 3; j >= 0; --j) {
-                    const double tau = tau_s[j];
-                    if (tau == 0.0) continue;
-                    const double* vh = a.Vh + (size_t)j * n;
-                    double s = 0.0;
-                    for (int i = j + 1 + lane; i < n; i += 32) s += vh[i] * z[i];
-                    s = warp_sum(s) * tau;
-                    for (int i = j + 1 + lane; i < n; i += 32) z[i] -= s * vh[i];
-                    __syncwarp();
-                }
-            }
-            double* zout = a.Z + (size_t)k * n;
-            for (int i = lane; i < n; i += 32) zout[i] = z[i];
-        }
-        __syncthreads();
-    }
+    (void)zs;
+    if (n <= 64) eig_backtransform<2>(a, K, tau_s, warp, lane);
+    else if (n <= 128) eig_backtransform<4>(a, K, tau_s, warp, lane);
+    else if (n <= 224) eig_backtransform<7>(a, K, tau_s, warp, lane);
+    else if (n <= 320) eig_backtransform<10>(a, K, tau_s, warp, lane);
+    else if (n <= 448) eig_backtransform<14>(a, K, tau_s, warp, lane);
+    else eig_backtransform<20>(a, K, tau_s, warp, lane);
     __threadfence_block();
     __syncthreads();
 

@@ -77,6 +77,7 @@ struct ShrinkBuffers {
     unsigned long long* part_nnz;
     float* part_max;
     float* part_wmax;          // [stream grid] max |W_next| written with the int8 slices (nullptr: slices off)
+    int implied_first = 0;     // shrink_stream only: iteration 1 derives S0 = 0, Y0 = D / dual_norm from D (init_Y skipped)
 };
 int launch_shrink(const ShrinkPlan& p, ShrinkBuffers b, const DevState* st, int mode, cudaStream_t stream);
 

@@ -38,6 +38,7 @@ struct ShrinkStreamArgs {
     int wq;                                // write the int8 slices of W_next (gram_i8.cu)
     int QS;                                // bytes per slice sub-buffer of a stage (FC*Pq rounded up to 128)
     int Pq;                                // = P (a multiple of 16 when the slices are on): bytes per frame of a tile
+    int implied_first;                     // iteration 1 takes S = 0, Y = D / dual_norm from D instead of reading them (no init pass)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -75,13 +76,19 @@ __device__ __forceinline__ float ss_clip_level9(const float* a_in, float z) {
 template <int KCNT>
 __device__ __forceinline__ void ss_accumulate(float (&acc)[SS_KC][4], const float* bD, const float* bS, const float* bY,
                                               const float* Vr_s, int P, int qd, int fl, int NFL, int FC, int fbase, int n,
-                                              float inv_mu) {
+                                              float inv_mu, bool first, double inv_dual) {
     for (int f = fl; f < FC; f += NFL) {
         const int fg = fbase + f;
         if (fg >= n) break;
         const float4 d4 = *reinterpret_cast<const float4*>(bD + (size_t)f * P + 4 * qd);
-        const float4 s4 = *reinterpret_cast<const float4*>(bS + (size_t)f * P + 4 * qd);
-        const float4 y4 = *reinterpret_cast<const float4*>(bY + (size_t)f * P + 4 * qd);
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), y4;
+        if (first) {                                      // S0 = 0, Y0 = D / dual_norm (inexact_alm_lsd.py:108-120), as init_Y_kernel forms it
+            y4.x = (float)((double)d4.x * inv_dual); y4.y = (float)((double)d4.y * inv_dual);
+            y4.z = (float)((double)d4.z * inv_dual); y4.w = (float)((double)d4.w * inv_dual);
+        } else {
+            s4 = *reinterpret_cast<const float4*>(bS + (size_t)f * P + 4 * qd);
+            y4 = *reinterpret_cast<const float4*>(bY + (size_t)f * P + 4 * qd);
+        }
         float4 w;
         w.x = (d4.x - s4.x) + y4.x * inv_mu; w.y = (d4.y - s4.y) + y4.y * inv_mu;
         w.z = (d4.z - s4.z) + y4.z * inv_mu; w.w = (d4.w - s4.w) + y4.w * inv_mu;
@@ -122,7 +129,7 @@ template <int KCNT>
 __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg, int tk_stride, const float* vc, int R, int P, float inv_mu,
                                          float mu_f, float lamq, int mode, double& zz_acc, unsigned int& nnz_acc, float& max_acc,
                                          unsigned char* qb, int QS, int o0, int kstep, float inv_mu_next, float Qf, float& wmax_acc,
-                                         int& sat_acc) {
+                                         int& sat_acc, bool first, double inv_dual) {
     float vv[SS_KC];
 #pragma unroll
     for (int k4 = 0; k4 < (KCNT + 3) / 4; ++k4) {
@@ -150,7 +157,7 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
             const float l = lw[e];
             dv[e] = dsp[o];
             av[e] = dv[e] - l;                            // a = D - L
-            yv[e] = ysp[o];
+            yv[e] = first ? (float)((double)dv[e] * inv_dual) : ysp[o];
             x[e] = fmaf(yv[e], inv_mu, av[e]);            // G_S
             ax[e] = fabsf(x[e]);
             sabs += ax[e];
@@ -232,7 +239,8 @@ template <int KCNT, int NTC>
 __device__ __forceinline__ void ss_phase_b(const ShrinkStreamArgs& a, float* ring, size_t stage_floats, const float* Tp, const float* VC_s,
                                            uint64_t* full, uint64_t* done, long long& q, int ct, int lane, int NG, int R, int P, int FC,
                                            int BS, int QS, int NS, int ncf, bool wq, float inv_mu, float mu_f, float lamq, float inv_mu_next, float Qf,
-                                           double& zz_acc, unsigned int& nnz_acc, float& max_acc, float& wmax_acc, int& sat_acc) {
+                                           double& zz_acc, unsigned int& nnz_acc, float& max_acc, float& wmax_acc, int& sat_acc, bool first,
+                                           double inv_dual) {
     for (int c = 0; c < ncf; ++c, ++q) {
         const int s = (int)(q % NS);
         const long long u = q / NS;
@@ -247,7 +255,7 @@ __device__ __forceinline__ void ss_phase_b(const ShrinkStreamArgs& a, float* rin
             float* ysp = b + (size_t)2 * BS + (size_t)f * P + 3 * g;
             unsigned char* qb = wq ? (reinterpret_cast<unsigned char*>(b + (size_t)BS) + (size_t)f * 16) : nullptr;
             ss_group<KCNT>(dsp, ysp, Tp + 12 * g, 12 * NG, VC_s + (size_t)fg * SS_KC, R, P, inv_mu, mu_f, lamq, a.mode, zz_acc, nnz_acc,
-                           max_acc, qb, QS, 3 * g, FC * 16, inv_mu_next, Qf, wmax_acc, sat_acc);
+                           max_acc, qb, QS, 3 * g, FC * 16, inv_mu_next, Qf, wmax_acc, sat_acc, first, inv_dual);
         }
         fence_proxy_async_smem();                   // my writes -> visible to the storer's TMA stores
         __syncwarp();
@@ -276,6 +284,8 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
     const int BS = (RT && FCT) ? ((FCT * 3 * RT + 127) / 128 * 128) : a.BS, QS = (RT && FCT) ? ((FCT * 3 * RT + 127) / 128 * 128) : a.QS;
     const double mu_d = st->mu;
     const float inv_mu = (float)(1.0 / mu_d), mu_f = (float)mu_d;
+    const bool first = (a.implied_first != 0) && (st->iter == 1);
+    const double inv_dual = 1.0 / st->dual_norm;
     const float lamq = (float)(st->lambda / mu_d);
     const bool wq = (a.wq != 0) && (a.mode != SHRINK_SPILL);
     // the next pass uses mu_next = min(mu rho, mu 1e7) (control_post_kernel): same double arithmetic here
@@ -338,11 +348,13 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                     float* b = ring + (size_t)s * stage_floats;
                     const bool isA = phaseA && c < ncf;
                     const int fbase = (isA ? c : c - (phaseA ? ncf : 0)) * FC;
-                    mbar_expect_tx(&full[s], (uint32_t)((isA ? 3 : 2) * (size_t)FC * P * sizeof(float)));
+                    mbar_expect_tx(&full[s], (uint32_t)((first ? 1 : (isA ? 3 : 2)) * (size_t)FC * P * sizeof(float)));
                     const uint64_t pol = (isA && phaseA) ? pol_keep : pol_stream;
                     tma_load_3d_hint(b, &mapD, &full[s], i0, j0, fbase, pol);
-                    tma_load_3d_hint(b + (size_t)2 * a.BS, &mapY, &full[s], i0, j0, fbase, pol);
-                    if (isA) tma_load_3d_hint(b + (size_t)a.BS, &mapS, &full[s], i0, j0, fbase, pol_stream);
+                    if (!first) {
+                        tma_load_3d_hint(b + (size_t)2 * a.BS, &mapY, &full[s], i0, j0, fbase, pol);
+                        if (isA) tma_load_3d_hint(b + (size_t)a.BS, &mapS, &full[s], i0, j0, fbase, pol_stream);
+                    }
                 }
             }
         }
@@ -397,7 +409,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                     const long long u = q / NS;
                     mbar_wait(&full[s], (uint32_t)(u & 1));
                     const float* b = ring + (size_t)s * stage_floats;
-                    if (tact) { SS_DISPATCH_K(r, (ss_accumulate<K_>(acc, b, b + BS, b + 2 * BS, Vr_s, P, qd, fl, NFL, FC, c * FC, a.n, inv_mu))); }
+                    if (tact) { SS_DISPATCH_K(r, (ss_accumulate<K_>(acc, b, b + BS, b + 2 * BS, Vr_s, P, qd, fl, NFL, FC, c * FC, a.n, inv_mu, first, inv_dual))); }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&done[s]);
                 }
@@ -435,7 +447,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
             }
             // phase B
             SS_DISPATCH_K(r, (ss_phase_b<K_, NTC>(a, ring, stage_floats, Tp, VC_s, full, done, q, ct, lane, NG, R, P, FC, BS, QS, NS, ncf, wq, inv_mu,
-                                                  mu_f, lamq, inv_mu_next, Qf, zz_acc, nnz_acc, max_acc, wmax_acc, sat_acc)));
+                                                  mu_f, lamq, inv_mu_next, Qf, zz_acc, nnz_acc, max_acc, wmax_acc, sat_acc, first, inv_dual)));
         }
     }
     __syncthreads();
@@ -547,7 +559,7 @@ int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, S
     a.R = p.R; a.P = p.P; a.NQ = p.P / 4; a.NFL = (32 * p.NCW) / a.NQ; a.FC = p.FC; a.NS = p.NS; a.BS = p.bufstride;
     a.nchunkf = p.nchunkf; a.ntile_r = p.ntile_r; a.ntiles = p.ntiles; a.st = st; a.part_zz = b.part_zz; a.part_nnz = b.part_nnz;
     a.part_max = b.part_max; a.part_wmax = b.part_wmax; a.mode = mode;
-    a.wq = (maps.has_Q && b.part_wmax != nullptr) ? 1 : 0; a.Pq = p.P;
+    a.wq = (maps.has_Q && b.part_wmax != nullptr) ? 1 : 0; a.Pq = p.P; a.implied_first = b.implied_first;
     a.QS = (int)(((size_t)p.FC * p.P + 127) / 128 * 128);
     if (p.NCW == 16) return launch_ss<16, 0, 0>(p, maps, a, mode, stream);
     if (p.R == 48 && p.FC == 28) return launch_ss<8, 48, 28>(p, maps, a, mode, stream);

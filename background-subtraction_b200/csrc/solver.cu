@@ -63,6 +63,7 @@ struct bsub_solver {
     // l2 blocks
     unsigned char* labels_dev = nullptr; double* lam_table = nullptr; double* bsums = nullptr; int nlab = 0; bool blocks_set = false;
     unsigned char* mask_stage = nullptr;      // bsub_mask_host staging
+    bool implied_first = false;               // see bsub_step_init_finish
     bool loaded = false, finalized = false, initialised = false;
     cudaEvent_t ev[kRunAhead + 1];
     int iters_enqueued = 0;
@@ -137,6 +138,7 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
         const size_t mat = sizeof(float) * (size_t)s->ld * s->n;
 #define ALLOC(ptr, bytes) if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) { set_error("bsub_create: cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(cudaGetLastError())); rc = -1; break; }
         ALLOC(s->D, mat); ALLOC(s->S, mat); ALLOC(s->Y, mat);
+        cudaMemset(s->S, 0, mat); cudaMemset(s->Y, 0, mat);     // pad columns stay zero even when init_Y is skipped
         ALLOC(s->T, mat);                                    // T has up to n rows (rank <= n)
         cudaMemset(s->T, 0, mat);                            // pad columns must read as zero
         ALLOC(s->st, sizeof(DevState)); ALLOC(s->log, sizeof(IterLog) * kMaxIterLog);
@@ -214,6 +216,8 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
             case BSUB_PROX_L1: s->shrink_mode = SHRINK_L1; break;
             default: s->shrink_mode = SHRINK_SPILL; break;
         }
+        s->implied_first = s->use_i8 && s->use_stream && s->shrink_mode != SHRINK_SPILL && s->cfg.use_sv_prediction &&
+                           s->cfg.sv0 >= 1 && s->cfg.sv0 <= kStreamMaxRank && getenv("BSUB_NO_IMPLIED_FIRST") == nullptr;
         if (s->shrink_mode == SHRINK_SPILL) { ALLOC(s->U, mat); ALLOC(s->L, mat); cudaMemset(s->U, 0, mat); cudaMemset(s->L, 0, mat); }
 #undef ALLOC
         if (cudaGetLastError() != cudaSuccess) { /* clear sticky-less errors from memset probing */ }
@@ -453,7 +457,9 @@ int bsub_step_init_finish(bsub_solver* s, void* stream) {
     RET_IF(check_ready(s));
     cudaStream_t st = as_stream(stream);
     RET_IF(launch_eig(s->ep, s->comm_sum, s->comm_max, s->eb, s->st, 0, 1, st));
-    RET_IF(launch_init_Y(s->D, s->Y, s->S, s->ld, s->n, s->st, st));
+    // S0 = 0 and Y0 = D / dual_norm are only materialised when some kernel of iteration 1 reads them: with the int8 path
+    // iteration 1 has no Gram pass and the streamed shrink kernel forms both from D on the fly
+    if (!s->implied_first) RET_IF(launch_init_Y(s->D, s->Y, s->S, s->ld, s->n, s->st, st));
     s->initialised = true;
     return 0;
 }
@@ -480,6 +486,7 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
     b.D = s->D; b.S = s->S; b.Y = s->Y; b.T = s->T; b.U = s->U; b.tpart = s->tpart; b.Vr = s->eb.Vr; b.VC = s->eb.VC;
     b.vstride = s->eb.vstride; b.part_zz = s->part_zz; b.part_nnz = s->part_nnz; b.part_max = s->part_max;
     b.part_wmax = s->use_i8 ? s->part_wmax : nullptr;
+    b.implied_first = s->implied_first ? 1 : 0;
     int nparts = s->sp.nparts;
     if (s->use_tma) {
         if (!s->stmaps_ready) {
