@@ -302,7 +302,7 @@ def main():
         sys.stderr.write("host ms at marks: %s\n" % [(t, round((h - mark_host[0][1]) * 1e3, 2)) for t, h in mark_host])
     use_i8 = bool(info["use_i8"])
     gram_first_ms = float(np.mean([s[0][0].elapsed_time(s[0][1]) for s in ev["gram"] if s])) if ev["gram"] else 0.0
-    gram_ms, n_gram = phase_ms("gram", 1 if use_i8 else 0)      # with the int8 path the first iteration is the fp64 DMMA Gram
+    gram_ms, n_gram = phase_ms("gram", 1 if use_i8 else 0)      # int8 path: iteration 1 has no Gram (W_1 = c D, eigenpairs of the initialisation)
     solve_ms, n_solve = phase_ms("solve")
     shrink_ms, n_shrink = phase_ms("shrink")
     # kernels launched per enqueued iteration: gram_dmma, gram_reduce, (gram_i8, gram_i8_finish), eig, shrink_stream /
@@ -413,7 +413,9 @@ def main():
     peak, peak_src = measured_peaks()
     elems_local = float(frames) * m_local
     shrink_name = "shrink_stream_kernel" if info["use_stream"] else ("shrink_tma_kernel" if info["use_tma"] else "shrink_kernel")
-    gram_name = "gram_i8_kernel" if use_i8 else "gram_dmma_kernel"
+    # three 128-frame blocks run the multicast-cluster variant (gram_i8.cu)
+    c3 = use_i8 and 256 < frames <= 384 and os.environ.get("BSUB_NO_GRAM_CLUSTER") is None
+    gram_name = ("gram_i8_c3_kernel" if c3 else "gram_i8_kernel") if use_i8 else "gram_dmma_kernel"
     # algorithmic bytes per matrix element: shrink reads D,S,Y and writes S,Y (20 B) plus the four
     # int8 slices of the next W (4 B) when the tcgen05 Gram is on; the Gram then reads those 4 B instead of D,S,Y (12 B)
     kern = {
@@ -422,9 +424,6 @@ def main():
                     "bound": "hbm" if use_i8 else "fp64 tensor pipe"},
         "eig_kernel": {"ms": solve_ms, "launches": n_solve, "alg_bytes": 8.0 * frames * frames, "bound": "latency"},
     }
-    if use_i8:
-        kern["gram_dmma_kernel (iteration 1 only)"] = {"ms": gram_first_ms, "launches": args.steps, "alg_bytes": 12.0 * elems_local,
-                                                      "bound": "fp64 tensor pipe"}
     for k in kern.values():
         k["gbs"] = (k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9) if k["ms"] > 0 else 0.0
         k["share"] = (k["ms"] * k["launches"]) / (ms_step * args.steps) if ms_step > 0 else 0.0
