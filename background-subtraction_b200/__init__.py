@@ -10,6 +10,6 @@ from .api import (BLOCK_SIZE, Decomposition, LSD, apply_background_shrinkage_ope
                   inexact_alm_lsd_with_background, inexact_alm_rpca,
                   labels_from_blocks, lsd_decomposition, make_config, normalizeImage, prox, prox_by_frame, prox_flat,
                   resize_with_cv2, svd_k_largest, window_csc, with_background_decomposition)
-from . import _cabi, build  # noqa: F401
+from . import _cabi, api, build  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -632,7 +632,6 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
     double* tau_s = d_s;                                  // d_s / e_s / e2_s are dead now
     for (int i = tid; i < n; i += EIG_THREADS) tau_s[i] = a.tau[i];
     __syncthreads();
-    (void)zs;
     if (n <= 64) eig_backtransform<2>(a, K, tau_s, warp, lane);
     else if (n <= 128) eig_backtransform<4>(a, K, tau_s, warp, lane);
     else if (n <= 224) eig_backtransform<7>(a, K, tau_s, warp, lane);

@@ -232,7 +232,6 @@ struct GramI8C3Args {
     int n, nkb;                           // frames; 64-pixel stages in the slice matrix
     int nX, nY;                           // clusters of each type (cluster id < nX: type X)
     int n2;                               // MMA N of frame block 2 (multiple of 16)
-    int prefetch_dist;                    // stages the L2 prefetch runs ahead of the loads
     unsigned long long* Gint;
     const DevState* st;
     int require_mode;
@@ -301,21 +300,9 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
         // ===================== TMA producer: arms my full barrier, loads the slot I own =====================
         if (lane == 0) {
             const uint32_t tx = (uint32_t)((useA ? 4 : 0) + (useB ? 4 : 0)) * GI_TILE_BYTES;
-            // every operand byte is fetched from DRAM exactly once per cluster type, so the three smem stages alone do not
-            // keep enough bytes in flight to cover the DRAM latency: an L2 prefetch runs `pd` stages ahead of the loads
-            const int pd = a.prefetch_dist;
-            auto prefetch = [&](int kb) {
-                if (ld_slot < 0 || kb >= nkb) return;
-                const int k16 = (kb0 + kb * kstride) * (GI_KB / 16);
-                for (int sl = 0; sl < 4; ++sl)
-                    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
-                                 ::"l"(&mapQ), "r"(ld_blk * 256), "r"(k16), "r"(sl) : "memory");
-            };
-            for (int kb = 0; kb < pd; ++kb) prefetch(kb);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % GI_STAGES;
                 const int u = kb / GI_STAGES;
-                if (pd > 0) prefetch(kb + pd);
                 if (u > 0) gi_mbar_wait(&mine[s], (uint32_t)((u - 1) & 1));           // my MMAs of the previous round are done
                 mbar_expect_tx(&full[s], tx);
                 if (ld_slot >= 0) {
@@ -584,7 +571,6 @@ int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const CUtensorMa
             GramI8C3Args c;
             c.n = p.n; c.nkb = p.nkb; c.nX = (c3_clusters + 1) / 2; c.nY = c3_clusters / 2; c.n2 = gram_i8_last_block_n(p);
             c.Gint = Gint; c.st = st; c.require_mode = require_mode;
-            { static const int pd = getenv("BSUB_GRAM_PREFETCH") ? atoi(getenv("BSUB_GRAM_PREFETCH")) : 0; c.prefetch_dist = pd; }
             cfg.gridDim = dim3(3 * c3_clusters);
             BSUB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_c3_kernel, map, c));
             gram_i8_finish_kernel<<<64, 256, 0, stream>>>(Gint, p.nblk, p.n, npad, G, st, scale_override, require_mode);

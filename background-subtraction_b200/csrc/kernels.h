@@ -96,6 +96,7 @@ int launch_shrink_tma(const ShrinkTmaPlan& p, const ShrinkTmaMaps& maps, ShrinkB
 // ---------------------------------------------------------------- shrink_stream.cu (fastest path: rank <= 16, rows % 4 == 0)
 struct ShrinkStreamPlan {
     int n, rows, cols, R, P, FC, NS, NCW, nchunkf, grid, nparts, ntile_r, ntile_c, bufstride;
+    int kcap;                  // largest rank the streamed kernel takes with this plan (16, or 8 for long clips)
     long long ld, ntiles;
     size_t smem_bytes;
 };

@@ -22,7 +22,7 @@
 
 namespace bsub {
 
-constexpr int SS_KC = 16;                 // largest rank handled by this kernel
+constexpr int SS_KC = 16;                 // largest rank handled by this kernel (a plan may cap it at 8 to fit Vr, VC of long clips)
 constexpr int SS_KRED = 8;                // singular vectors per round of the per-tile T reduction
 constexpr size_t SS_SMEM_CAP = 227 * 1024 - 256;
 
@@ -38,6 +38,7 @@ struct ShrinkStreamArgs {
     int wq;                                // write the int8 slices of W_next (gram_i8.cu)
     int QS;                                // bytes per slice sub-buffer of a stage (FC*Pq rounded up to 128)
     int Pq;                                // = P (a multiple of 16 when the slices are on): bytes per frame of a tile
+    int kcap;                              // ranks <= kcap are handled here (row stride of the Vr / VC copies in shared memory)
     int implied_first;                     // iteration 1 takes S = 0, Y = D / dual_norm from D instead of reading them (no init pass)
 };
 
@@ -75,7 +76,7 @@ __device__ __forceinline__ float ss_clip_level9(const float* a_in, float z) {
 // phase A, one stage: T partial of this thread's pixel quad over its frames of the stage
 template <int KCNT>
 __device__ __forceinline__ void ss_accumulate(float (&acc)[SS_KC][4], const float* bD, const float* bS, const float* bY,
-                                              const float* Vr_s, int P, int qd, int fl, int NFL, int FC, int fbase, int n,
+                                              const float* Vr_s, int kst, int P, int qd, int fl, int NFL, int FC, int fbase, int n,
                                               float inv_mu, bool first, double inv_dual) {
     for (int f = fl; f < FC; f += NFL) {
         const int fg = fbase + f;
@@ -92,7 +93,7 @@ __device__ __forceinline__ void ss_accumulate(float (&acc)[SS_KC][4], const floa
         float4 w;
         w.x = (d4.x - s4.x) + y4.x * inv_mu; w.y = (d4.y - s4.y) + y4.y * inv_mu;
         w.z = (d4.z - s4.z) + y4.z * inv_mu; w.w = (d4.w - s4.w) + y4.w * inv_mu;
-        const float* vrow = Vr_s + (size_t)fg * SS_KC;
+        const float* vrow = Vr_s + (size_t)fg * kst;
         float vv[SS_KC];
 #pragma unroll
         for (int k4 = 0; k4 < (KCNT + 3) / 4; ++k4) {
@@ -254,7 +255,7 @@ __device__ __forceinline__ void ss_phase_b(const ShrinkStreamArgs& a, float* rin
             float* dsp = b + (size_t)f * P + 3 * g;
             float* ysp = b + (size_t)2 * BS + (size_t)f * P + 3 * g;
             unsigned char* qb = wq ? (reinterpret_cast<unsigned char*>(b + (size_t)BS) + (size_t)f * 16) : nullptr;
-            ss_group<KCNT>(dsp, ysp, Tp + 12 * g, 12 * NG, VC_s + (size_t)fg * SS_KC, R, P, inv_mu, mu_f, lamq, a.mode, zz_acc, nnz_acc,
+            ss_group<KCNT>(dsp, ysp, Tp + 12 * g, 12 * NG, VC_s + (size_t)fg * a.kcap, R, P, inv_mu, mu_f, lamq, a.mode, zz_acc, nnz_acc,
                            max_acc, qb, QS, 3 * g, FC * 16, inv_mu_next, Qf, wmax_acc, sat_acc, first, inv_dual);
         }
         fence_proxy_async_smem();                   // my writes -> visible to the storer's TMA stores
@@ -275,7 +276,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
     const DevState* st = a.st;
     if (st->done) return;
     const int r = st->svp;
-    if (r > SS_KC) {                                       // large ranks take the fallback kernel launched next
+    if (r > a.kcap) {                                      // large ranks take the fallback kernel launched next
         if (threadIdx.x == 0) { a.part_zz[blockIdx.x] = 0.0; a.part_nnz[blockIdx.x] = 0ull; a.part_max[blockIdx.x] = 0.f; if (a.part_wmax != nullptr) a.part_wmax[blockIdx.x] = -1.f; }
         return;
     }
@@ -299,9 +300,10 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
     float* ring = reinterpret_cast<float*>(ss_smem_raw);            // [NS][3][BS]
     float* scr = ring + (size_t)NS * stage_floats;                  // [NFL][SS_KRED][P]   (T reduction)
     float* Tp = scr + (size_t)NFL * SS_KRED * P;                    // [SS_KC][R/3 groups][12]: T of the tile, 9 entries per 3x3 group
-    float* Vr_s = Tp + (size_t)SS_KC * (4 * R);                     // [n][SS_KC]
-    float* VC_s = Vr_s + (size_t)a.n * SS_KC;                       // [n][SS_KC]
-    uint64_t* full = reinterpret_cast<uint64_t*>(VC_s + (size_t)a.n * SS_KC);   // [NS]
+    const int kst = a.kcap;
+    float* Vr_s = Tp + (size_t)SS_KC * (4 * R);                     // [n][kcap]
+    float* VC_s = Vr_s + (size_t)a.n * kst;                         // [n][kcap]
+    uint64_t* full = reinterpret_cast<uint64_t*>(VC_s + (size_t)a.n * kst);     // [NS]
     uint64_t* done = full + NS;                                     // [NS]
     uint64_t* freeb = done + NS;                                    // [NS]
     __shared__ double redd[32];
@@ -311,8 +313,8 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
         mbar_fence_init();
         tma_prefetch_desc(&mapD); tma_prefetch_desc(&mapS); tma_prefetch_desc(&mapY); tma_prefetch_desc(&mapOut);
     }
-    for (int idx = threadIdx.x; idx < a.n * SS_KC; idx += blockDim.x) {
-        const int f = idx / SS_KC, k = idx - f * SS_KC;
+    for (int idx = threadIdx.x; idx < a.n * kst; idx += blockDim.x) {
+        const int f = idx / kst, k = idx - f * kst;
         const bool ok = k < r;
         Vr_s[idx] = ok ? a.Vr[(size_t)f * a.vstride + k] : 0.f;
         VC_s[idx] = ok ? a.VC[(size_t)f * a.vstride + k] : 0.f;
@@ -409,7 +411,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                     const long long u = q / NS;
                     mbar_wait(&full[s], (uint32_t)(u & 1));
                     const float* b = ring + (size_t)s * stage_floats;
-                    if (tact) { SS_DISPATCH_K(r, (ss_accumulate<K_>(acc, b, b + BS, b + 2 * BS, Vr_s, P, qd, fl, NFL, FC, c * FC, a.n, inv_mu, first, inv_dual))); }
+                    if (tact) { SS_DISPATCH_K(r, (ss_accumulate<K_>(acc, b, b + BS, b + 2 * BS, Vr_s, kst, P, qd, fl, NFL, FC, c * FC, a.n, inv_mu, first, inv_dual))); }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&done[s]);
                 }
@@ -464,10 +466,10 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
 }
 
 // -------------------------------------------------------------------------------------------------------------
-static size_t ss_smem_bytes(int n, int R, int FC, int NS, int NTC) {
+static size_t ss_smem_bytes(int n, int R, int FC, int NS, int NTC, int kcap) {
     const int P = 3 * R, NQ = P / 4, NFL = NTC / NQ;
     const size_t bs = ((size_t)FC * P + 127) / 128 * 128;
-    size_t fl = (size_t)NS * 3 * bs + (size_t)NFL * SS_KRED * P + (size_t)SS_KC * 4 * R + (size_t)2 * n * SS_KC;
+    size_t fl = (size_t)NS * 3 * bs + (size_t)NFL * SS_KRED * P + (size_t)SS_KC * 4 * R + (size_t)2 * n * kcap;
     return fl * sizeof(float) + (size_t)3 * NS * sizeof(uint64_t) + 64;
 }
 
@@ -490,12 +492,17 @@ bool make_shrink_stream_plan(int n, int rows, int cols, long long ld, int num_sm
         const int NFL = NTC / NQ;
         int FC = env_fc ? atoi(env_fc) : 4 * NFL;
         FC = std::max(1, std::min(FC, std::min(n, 256)));
-        int NS = env_ns ? atoi(env_ns) : 6;
-        while (NS >= 3 && ss_smem_bytes(n, R, FC, NS, NTC) > SS_SMEM_CAP) --NS;
-        if (NS < 3) continue;
-        p.R = R; p.P = 3 * R; p.FC = FC; p.NS = NS; p.NCW = NCW;
+        // ranks up to 16 if the Vr / VC copies fit next to a 3-stage ring, else up to 8 (long clips, e.g. 600 frames)
+        int NS = 0, kcap = 0;
+        for (int kc : {SS_KC, 8}) {
+            NS = env_ns ? atoi(env_ns) : 6;
+            while (NS >= 3 && ss_smem_bytes(n, R, FC, NS, NTC, kc) > SS_SMEM_CAP) --NS;
+            if (NS >= 3) { kcap = kc; break; }
+        }
+        if (kcap == 0) continue;
+        p.R = R; p.P = 3 * R; p.FC = FC; p.NS = NS; p.NCW = NCW; p.kcap = kcap;
         p.bufstride = (int)(((size_t)FC * p.P + 127) / 128 * 128);
-        p.smem_bytes = ss_smem_bytes(n, R, FC, NS, NTC);
+        p.smem_bytes = ss_smem_bytes(n, R, FC, NS, NTC, kcap);
         p.nchunkf = (n + FC - 1) / FC;
         p.ntile_r = (rows + R - 1) / R;
         p.ntile_c = (cols + 2) / 3;
@@ -559,7 +566,7 @@ int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, S
     a.R = p.R; a.P = p.P; a.NQ = p.P / 4; a.NFL = (32 * p.NCW) / a.NQ; a.FC = p.FC; a.NS = p.NS; a.BS = p.bufstride;
     a.nchunkf = p.nchunkf; a.ntile_r = p.ntile_r; a.ntiles = p.ntiles; a.st = st; a.part_zz = b.part_zz; a.part_nnz = b.part_nnz;
     a.part_max = b.part_max; a.part_wmax = b.part_wmax; a.mode = mode;
-    a.wq = (maps.has_Q && b.part_wmax != nullptr) ? 1 : 0; a.Pq = p.P; a.implied_first = b.implied_first;
+    a.wq = (maps.has_Q && b.part_wmax != nullptr) ? 1 : 0; a.Pq = p.P; a.implied_first = b.implied_first; a.kcap = p.kcap;
     a.QS = (int)(((size_t)p.FC * p.P + 127) / 128 * 128);
     if (p.NCW == 16) return launch_ss<16, 0, 0>(p, maps, a, mode, stream);
     if (p.R == 48 && p.FC == 28) return launch_ss<8, 48, 28>(p, maps, a, mode, stream);

@@ -217,7 +217,7 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
             default: s->shrink_mode = SHRINK_SPILL; break;
         }
         s->implied_first = s->use_i8 && s->use_stream && s->shrink_mode != SHRINK_SPILL && s->cfg.use_sv_prediction &&
-                           s->cfg.sv0 >= 1 && s->cfg.sv0 <= kStreamMaxRank && getenv("BSUB_NO_IMPLIED_FIRST") == nullptr;
+                           s->cfg.sv0 >= 1 && s->cfg.sv0 <= s->ssp.kcap && getenv("BSUB_NO_IMPLIED_FIRST") == nullptr;
         if (s->shrink_mode == SHRINK_SPILL) { ALLOC(s->U, mat); ALLOC(s->L, mat); cudaMemset(s->U, 0, mat); cudaMemset(s->L, 0, mat); }
 #undef ALLOC
         if (cudaGetLastError() != cudaSuccess) { /* clear sticky-less errors from memset probing */ }
@@ -498,7 +498,7 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
         int off = 0, min_rank = 0;
         if (s->use_stream) {          // rank <= 16: streamed kernel; larger ranks fall through to the cluster kernel
             RET_IF(launch_shrink_stream(s->ssp, s->ssmaps, b, s->st, s->shrink_mode, st));
-            off = s->ssp.nparts; min_rank = kStreamMaxRank + 1;
+            off = s->ssp.nparts; min_rank = s->ssp.kcap + 1;
         }
         ShrinkBuffers b2 = b;
         b2.part_zz += off; b2.part_nnz += off; b2.part_max += off;

@@ -30,6 +30,8 @@ WORKLOADS = {
     "synthetic_4k_600": (2160, 3840, 600, 1, 12),
     "synthetic_qvga_200": (240, 320, 200, 100, 3),
     "synthetic_small": (240, 320, 48, 5, 3),
+    # the reference's own clip (BASELINE.json config 1): data/WaterSurface.mat, kept as tests/golden/watersurface_u8.npz
+    "watersurface": (128, 160, 48, None, None),
 }
 
 
@@ -138,16 +140,25 @@ def cpu_sample(video_u8, rows, cols, frames, div):
     return D, r, c
 
 
+def load_video(workload):
+    """uint8 clip [frames][m], frame-major with the reference's pixel order p = j*rows + i."""
+    rows, cols, frames, seed, nrect = WORKLOADS[workload]
+    if workload == "watersurface":
+        cube = np.load(os.path.join(ROOT, "tests", "golden", "watersurface_u8.npz"))["ImData"]       # [rows, cols, frames]
+        return np.ascontiguousarray(cube.transpose(2, 1, 0)).reshape(frames, rows * cols)
+    from background_subtraction_b200 import synth
+    return synth.make_clip(rows, cols, frames, seed=seed, n_rect=nrect)[0]
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is pure Python and is not
     present on the GPU box) on all host cores, bounded sample, same metric/config."""
     if rank != 0:
         return None
-    from background_subtraction_b200 import synth
     rows, cols, frames, seed, nrect = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
-    video, _ = synth.make_clip(rows, cols, frames, seed=seed, n_rect=nrect)
-    D, r, c = cpu_sample(video, rows, cols, frames, args.cpu_sample_div)
+    video = load_video(args.workload)
+    D, r, c = cpu_sample(video, rows, cols, frames, args.cpu_sample_div if rows * cols > 200000 else 1)
     scale = (rows * cols) / float(r * c)
     times = []
     for i in range(args.warmup + args.steps):
@@ -159,7 +170,7 @@ def run_reference(args, rank, world):
     sample = f"{r}x{c} pixel window of every frame ({r * c}/{rows * cols} of the pixels), full solve, time scaled x{scale:.1f}"
     return {"impl": "reference", "metric": "frames/s decomposed", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64", "data": "reference fixture (WaterSurface)" if args.workload == "watersurface" else "synthetic",
             "config": {"workload": args.workload, "rows": rows, "cols": cols, "frames": frames, "prox": "flat 3x3 l_inf (LSD)",
                        "delta": 10},
             "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample,
@@ -196,7 +207,7 @@ def main():
 
     # ---- data: every rank generates the same seeded clip and keeps its column shard ----
     t_gen = time.perf_counter()
-    video, _ = synth.make_clip(rows, cols, frames, seed=seed, n_rect=nrect)
+    video = load_video(args.workload)
     c0, c1 = bdist.shard_columns(cols, world, rank)
     cols_local = c1 - c0
     m_local = rows * cols_local
@@ -444,7 +455,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        D64, r, c = cpu_sample(video, rows, cols, frames, args.cpu_sample_div)
+        D64, r, c = cpu_sample(video, rows, cols, frames, args.cpu_sample_div if rows * cols > 200000 else 1)
         threads = os.cpu_count() or 1
         dt, it_c, conv_c = cpu_port_solve(D64, r, c, threads)
         sc = (rows * cols) / float(r * c)
@@ -456,7 +467,7 @@ def main():
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None,
            "dtype": "f32 (state) / exact int8-slice Gram on tcgen05 + f64 eigensolve" if use_i8 else "f32 (state) / f64 Gram + eigensolve",
-           "data": "synthetic",
+           "data": "reference fixture (WaterSurface)" if args.workload == "watersurface" else "synthetic",
            "config": {"workload": args.workload, "rows": rows, "cols": cols, "frames": frames, "prox": "flat 3x3 l_inf (LSD)",
                       "delta": 10, "sharding": f"pixel columns over {world} GPU(s)", "l2": "inputs (2.5 GB/matrix) larger than L2",
                       "tile_rows": info["stream_R"] if info["use_stream"] else solver.dec.cfg.tile_rows, "paths": info},

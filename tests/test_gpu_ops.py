@@ -154,7 +154,8 @@ def test_svd_k_largest(B):
     assert rel_fro((u * s) @ vh, (lambda U, S, V: (U[:, :6] * S[:6]) @ V[:6])(*np.linalg.svd(A, full_matrices=False))) <= 1e-8
 
 
-@pytest.mark.parametrize("n,ldq", [(44, 256), (128, 64 * 7), (130, 64 * 40), (300, 64 * 33), (300, 64 * 1000)])
+@pytest.mark.parametrize("n,ldq", [(44, 256), (128, 64 * 7), (130, 64 * 40), (300, 64 * 33), (300, 64 * 1000), (257, 64 * 50),
+                                   (384, 64 * 9), (600, 64 * 20)])
 def test_gram_i8_exact(B, n, ldq):
     """tcgen05 int8 slice Gram: exact integer equality with NumPy (classes i + j >= 3 of the 4x4 slice pairs)."""
     import ctypes

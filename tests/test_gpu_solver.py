@@ -139,6 +139,57 @@ def test_with_background_golden(B, watersurface_u8):
     assert rel_fro(got, ref) <= 1e-6
 
 
+def test_fmeasure_parity_synthetic(B):
+    """north_star acceptance: the CUDA mask and the reference-algorithm mask score the same F-measure (compute_score.py
+    metric, restated in oracle/score_oracle.py) against the known foreground of a synthetic clip; masks agree >= 99.9 %."""
+    from background_subtraction_b200 import synth
+    from oracle import alm_oracle as O
+    from oracle import score_oracle as SC
+    rows, cols, n = 48, 60, 24
+    video, gt = synth.make_clip(rows, cols, n, seed=21, n_rect=2, return_gt=True)
+    D = np.asfortranarray(synth.preprocess_u8(video).T.astype(np.float64))
+    groups = B.get_proximal_flat_groups_nonoverlap((rows, cols), (3, 3))
+    L, S, it, conv = B.inexact_alm_lsd(D, groups=groups)
+    Lr, Sr, itr, convr = O.inexact_alm_lsd(D, groups=groups)
+    assert abs(it - itr) <= 1 and conv == convr
+    mask, mref = B.foreground_mask(D, L, S), O.foreground_mask(D, Lr, Sr)
+    assert (mask == mref).mean() >= 0.999
+    cube = lambda a: np.asarray(a).reshape((rows, cols, n), order='F')          # noqa: E731
+    f_gpu, f_ref = SC.mean_fscore(cube(mask), cube(gt.T)), SC.mean_fscore(cube(mref), cube(gt.T))
+    print("F-measure gpu %.4f  reference algorithm %.4f" % (f_gpu, f_ref))
+    assert abs(f_gpu - f_ref) <= 1e-3
+
+
+@pytest.mark.parametrize("rows,cols,n", [(48, 60, 600), (96, 63, 130)])
+def test_fast_paths_match_fallback(B, rows, cols, n):
+    """The tensor-core / streamed kernels (int8 Gram incl. the 5-block and 2-block layouts, rank cap 8 of long clips,
+    implied first iterate) against the fp64-Gram + cluster-kernel fallback on the same clip."""
+    from background_subtraction_b200 import synth
+    video, _ = synth.make_clip(rows, cols, n, seed=33, n_rect=2)
+    D = np.asfortranarray(synth.preprocess_u8(video).T.astype(np.float64))
+    groups = B.get_proximal_flat_groups_nonoverlap((rows, cols), (3, 3))
+    keys = ("BSUB_NO_I8", "BSUB_NO_STREAM")
+    old = {k: os.environ.get(k) for k in keys}
+    try:
+        for k in keys:
+            os.environ.pop(k, None)
+        dec = B.lsd_decomposition(D, groups=groups, img_shape=(rows, cols))
+        info = dec.debug_info()
+        L1, S1, it1, c1 = B.api._finish(dec, D, False)
+        for k in keys:
+            os.environ[k] = "1"
+        L0, S0, it0, c0 = B.inexact_alm_lsd(D, groups=groups, img_shape=(rows, cols))
+    finally:
+        for k in keys:
+            if old[k] is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = old[k]
+    assert info["use_stream"] == 1 and info["use_i8"] == 1
+    assert it1 == it0 and c1 == c0
+    assert rel_fro(L1, L0) <= 2e-5 and rel_fro(S1, S0) <= 2e-4
+
+
 def test_rpca_l1(B, watersurface_u8):
     from oracle import alm_oracle as O
     D, _x, _mean = O.normalize_and_center(watersurface_u8[:48, :60, :20])
