@@ -7,7 +7,7 @@ from .api import (BLOCK_SIZE, Decomposition, LSD, apply_background_shrinkage_ope
                   eig_topk, foreground_mask, getGraphSPAMS_all_groups, get_proximal_flat_groups_nonoverlap,
                   get_proximal_graph_group_centers, gram,
                   group_sparse_decomposition, inexact_alm_group_sparse_RPCA, inexact_alm_lsd,
-                  inexact_alm_lsd_with_background, inexact_alm_rpca,
+                  inexact_alm_lsd_batch, inexact_alm_lsd_with_background, inexact_alm_rpca,
                   labels_from_blocks, lsd_decomposition, make_config, normalizeImage, prox, prox_by_frame, prox_flat,
                   resize_with_cv2, svd_k_largest, window_csc, with_background_decomposition)
 from . import _cabi, api, build  # noqa: F401

@@ -499,6 +499,45 @@ def inexact_alm_lsd(D0, graphs=None, groups=None, delta=10, img_shape=None, verb
     return _finish(dec, D0, verbose)
 
 
+def inexact_alm_lsd_batch(clips, groups=None, graphs=None, delta=10, img_shape=None, in_flight=4, **tuning):
+    """Independent decompositions of several clips (BASELINE.json config 5: "one decomposition per clip"), `in_flight` of
+    them at a time on this GPU: one solver handle, host thread and CUDA stream per clip in flight, so the uploads and
+    downloads of one clip and the 8-SM eigensolve of another overlap the streaming kernels of the rest.  Same arguments
+    as inexact_alm_lsd for every clip; returns a list of (L, S, iter_out, converged) in input order."""
+    import threading
+    torch = _require_cuda()
+    clips = list(clips)
+    out = [None] * len(clips)
+    errs = []
+    nxt = [0]
+    lock = threading.Lock()
+    dev = torch.cuda.current_device()
+
+    def worker():
+        try:
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(torch.cuda.Stream()):
+                while True:
+                    with lock:
+                        i = nxt[0]
+                        nxt[0] += 1
+                    if i >= len(clips) or errs:
+                        return
+                    out[i] = inexact_alm_lsd(clips[i], graphs=graphs, groups=groups, delta=delta, img_shape=img_shape, **tuning)
+                    torch.cuda.current_stream().synchronize()
+        except Exception as ex:                                  # re-raised in the caller
+            errs.append(ex)
+
+    th = [threading.Thread(target=worker) for _ in range(max(1, min(int(in_flight), len(clips))))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errs:
+        raise errs[0]
+    return out
+
+
 def with_background_decomposition(D0, graphs, background_masks, delta=10, img_shape=None, **tuning):
     if not isinstance(graphs, list) and not isinstance(graphs, np.ndarray):
         raise Exception('graphs must be list/array')                       # lsd_improvement.py:223-224

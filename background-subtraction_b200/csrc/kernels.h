@@ -87,7 +87,7 @@ struct ShrinkTmaPlan {
     long long ld, ntiles;
     size_t smem_bytes, tpart_floats;
 };
-struct ShrinkTmaMaps { CUtensorMap D, S, Y, U, Q; bool has_U, has_Q; };
+struct ShrinkTmaMaps { CUtensorMap D, S, Y, U, Q, Vr, VC; bool has_U, has_Q; };
 bool make_shrink_tma_plan(int n, int rows, int cols, long long ld, int num_sms, int R_hint, int Cf_hint, ShrinkTmaPlan* out);
 int make_shrink_tma_maps(const ShrinkTmaPlan& p, const float* D, float* S, float* Y, float* U, ShrinkTmaMaps* m);
 int launch_shrink_tma(const ShrinkTmaPlan& p, const ShrinkTmaMaps& maps, ShrinkBuffers b, const DevState* st, int mode,
@@ -96,7 +96,7 @@ int launch_shrink_tma(const ShrinkTmaPlan& p, const ShrinkTmaMaps& maps, ShrinkB
 // ---------------------------------------------------------------- shrink_stream.cu (fastest path: rank <= 16, rows % 4 == 0)
 struct ShrinkStreamPlan {
     int n, rows, cols, R, P, FC, NS, NCW, nchunkf, grid, nparts, ntile_r, ntile_c, bufstride;
-    int kcap;                  // largest rank the streamed kernel takes with this plan (16, or 8 for long clips)
+    int kcap;                  // largest rank the streamed kernel takes (16)
     long long ld, ntiles;
     size_t smem_bytes;
 };
@@ -104,6 +104,7 @@ constexpr int kStreamMaxRank = 16;
 bool make_shrink_stream_plan(int n, int rows, int cols, long long ld, int num_sms, int R_hint, ShrinkStreamPlan* out);
 int make_shrink_stream_maps(const ShrinkStreamPlan& p, const float* D, float* S, float* Y, float* U, ShrinkTmaMaps* m);
 long long shrink_stream_ldq(const ShrinkStreamPlan& p);
+int make_shrink_stream_vmaps(const ShrinkStreamPlan& p, const float* Vr, const float* VC, int vstride, ShrinkTmaMaps* m);
 int make_shrink_stream_qmap(const ShrinkStreamPlan& p, signed char* Wq, ShrinkTmaMaps* m);
 int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, ShrinkBuffers b, const DevState* st, int mode,
                          cudaStream_t stream);

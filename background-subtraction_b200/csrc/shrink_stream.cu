@@ -76,7 +76,7 @@ __device__ __forceinline__ float ss_clip_level9(const float* a_in, float z) {
 // phase A, one stage: T partial of this thread's pixel quad over its frames of the stage
 template <int KCNT>
 __device__ __forceinline__ void ss_accumulate(float (&acc)[SS_KC][4], const float* bD, const float* bS, const float* bY,
-                                              const float* Vr_s, int kst, int P, int qd, int fl, int NFL, int FC, int fbase, int n,
+                                              const float* Vst, int P, int qd, int fl, int NFL, int FC, int fbase, int n,
                                               float inv_mu, bool first, double inv_dual) {
     for (int f = fl; f < FC; f += NFL) {
         const int fg = fbase + f;
@@ -93,7 +93,7 @@ __device__ __forceinline__ void ss_accumulate(float (&acc)[SS_KC][4], const floa
         float4 w;
         w.x = (d4.x - s4.x) + y4.x * inv_mu; w.y = (d4.y - s4.y) + y4.y * inv_mu;
         w.z = (d4.z - s4.z) + y4.z * inv_mu; w.w = (d4.w - s4.w) + y4.w * inv_mu;
-        const float* vrow = Vr_s + (size_t)fg * kst;
+        const float* vrow = Vst + f * SS_KC;               // Vr rows of this stage's frames (TMA-loaded with the stage)
         float vv[SS_KC];
 #pragma unroll
         for (int k4 = 0; k4 < (KCNT + 3) / 4; ++k4) {
@@ -237,9 +237,9 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
 
 // phase B of one tile: every stage = FC frames; thread item = one 3x3 group of one frame
 template <int KCNT, int NTC>
-__device__ __forceinline__ void ss_phase_b(const ShrinkStreamArgs& a, float* ring, size_t stage_floats, const float* Tp, const float* VC_s,
+__device__ __forceinline__ void ss_phase_b(const ShrinkStreamArgs& a, float* ring, size_t stage_floats, const float* Tp, const float* Vst_all,
                                            uint64_t* full, uint64_t* done, long long& q, int ct, int lane, int NG, int R, int P, int FC,
-                                           int BS, int QS, int NS, int ncf, bool wq, float inv_mu, float mu_f, float lamq, float inv_mu_next, float Qf,
+                                           int BS, int QS, int VSS, int NS, int ncf, bool wq, float inv_mu, float mu_f, float lamq, float inv_mu_next, float Qf,
                                            double& zz_acc, unsigned int& nnz_acc, float& max_acc, float& wmax_acc, int& sat_acc, bool first,
                                            double inv_dual) {
     for (int c = 0; c < ncf; ++c, ++q) {
@@ -255,7 +255,7 @@ __device__ __forceinline__ void ss_phase_b(const ShrinkStreamArgs& a, float* rin
             float* dsp = b + (size_t)f * P + 3 * g;
             float* ysp = b + (size_t)2 * BS + (size_t)f * P + 3 * g;
             unsigned char* qb = wq ? (reinterpret_cast<unsigned char*>(b + (size_t)BS) + (size_t)f * 16) : nullptr;
-            ss_group<KCNT>(dsp, ysp, Tp + 12 * g, 12 * NG, VC_s + (size_t)fg * a.kcap, R, P, inv_mu, mu_f, lamq, a.mode, zz_acc, nnz_acc,
+            ss_group<KCNT>(dsp, ysp, Tp + 12 * g, 12 * NG, Vst_all + (size_t)s * VSS + f * SS_KC, R, P, inv_mu, mu_f, lamq, a.mode, zz_acc, nnz_acc,
                            max_acc, qb, QS, 3 * g, FC * 16, inv_mu_next, Qf, wmax_acc, sat_acc, first, inv_dual);
         }
         fence_proxy_async_smem();                   // my writes -> visible to the storer's TMA stores
@@ -271,7 +271,8 @@ template <int NCW, int RT, int FCT>
 __global__ void __launch_bounds__(32 * (NCW + 2), 1)
 shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_constant__ CUtensorMap mapS,
                      const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapOut,
-                     const __grid_constant__ CUtensorMap mapQ, ShrinkStreamArgs a) {
+                     const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapVr,
+                     const __grid_constant__ CUtensorMap mapVC, ShrinkStreamArgs a) {
     constexpr int NTC = 32 * NCW;
     const DevState* st = a.st;
     if (st->done) return;
@@ -300,10 +301,11 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
     float* ring = reinterpret_cast<float*>(ss_smem_raw);            // [NS][3][BS]
     float* scr = ring + (size_t)NS * stage_floats;                  // [NFL][SS_KRED][P]   (T reduction)
     float* Tp = scr + (size_t)NFL * SS_KRED * P;                    // [SS_KC][R/3 groups][12]: T of the tile, 9 entries per 3x3 group
-    const int kst = a.kcap;
-    float* Vr_s = Tp + (size_t)SS_KC * (4 * R);                     // [n][kcap]
-    float* VC_s = Vr_s + (size_t)a.n * kst;                         // [n][kcap]
-    uint64_t* full = reinterpret_cast<uint64_t*>(VC_s + (size_t)a.n * kst);     // [NS]
+    // Vr (phase A) / VC (phase B) rows of the frames of a stage, loaded by TMA together with the stage: the footprint does
+    // not grow with the number of frames
+    const int VSS = (FC * SS_KC + 31) / 32 * 32;                   // floats per stage slice (128-byte multiple: TMA destination)
+    float* Vst = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(Tp + (size_t)SS_KC * (4 * R)) + 127) & ~(uintptr_t)127);   // [NS][VSS]
+    uint64_t* full = reinterpret_cast<uint64_t*>(Vst + (size_t)NS * VSS);   // [NS]
     uint64_t* done = full + NS;                                     // [NS]
     uint64_t* freeb = done + NS;                                    // [NS]
     __shared__ double redd[32];
@@ -312,12 +314,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], NCW); mbar_init(&freeb[s], 1); }
         mbar_fence_init();
         tma_prefetch_desc(&mapD); tma_prefetch_desc(&mapS); tma_prefetch_desc(&mapY); tma_prefetch_desc(&mapOut);
-    }
-    for (int idx = threadIdx.x; idx < a.n * kst; idx += blockDim.x) {
-        const int f = idx / kst, k = idx - f * kst;
-        const bool ok = k < r;
-        Vr_s[idx] = ok ? a.Vr[(size_t)f * a.vstride + k] : 0.f;
-        VC_s[idx] = ok ? a.VC[(size_t)f * a.vstride + k] : 0.f;
+        tma_prefetch_desc(&mapVr); tma_prefetch_desc(&mapVC);
     }
     for (int idx = threadIdx.x; idx < SS_KC * 4 * R; idx += blockDim.x) Tp[idx] = 0.f;   // rows >= svp stay zero
     __syncthreads();
@@ -350,7 +347,9 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                     float* b = ring + (size_t)s * stage_floats;
                     const bool isA = phaseA && c < ncf;
                     const int fbase = (isA ? c : c - (phaseA ? ncf : 0)) * FC;
-                    mbar_expect_tx(&full[s], (uint32_t)((first ? 1 : (isA ? 3 : 2)) * (size_t)FC * P * sizeof(float)));
+                    mbar_expect_tx(&full[s], (uint32_t)((first ? 1 : (isA ? 3 : 2)) * (size_t)FC * P * sizeof(float)) +
+                                             (uint32_t)(FC * SS_KC * sizeof(float)));
+                    tma_load_2d(Vst + (size_t)s * VSS, isA ? &mapVr : &mapVC, &full[s], 0, fbase);
                     const uint64_t pol = (isA && phaseA) ? pol_keep : pol_stream;
                     tma_load_3d_hint(b, &mapD, &full[s], i0, j0, fbase, pol);
                     if (!first) {
@@ -411,7 +410,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                     const long long u = q / NS;
                     mbar_wait(&full[s], (uint32_t)(u & 1));
                     const float* b = ring + (size_t)s * stage_floats;
-                    if (tact) { SS_DISPATCH_K(r, (ss_accumulate<K_>(acc, b, b + BS, b + 2 * BS, Vr_s, kst, P, qd, fl, NFL, FC, c * FC, a.n, inv_mu, first, inv_dual))); }
+                    if (tact) { SS_DISPATCH_K(r, (ss_accumulate<K_>(acc, b, b + BS, b + 2 * BS, Vst + (size_t)s * VSS, P, qd, fl, NFL, FC, c * FC, a.n, inv_mu, first, inv_dual))); }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&done[s]);
                 }
@@ -448,7 +447,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                 }
             }
             // phase B
-            SS_DISPATCH_K(r, (ss_phase_b<K_, NTC>(a, ring, stage_floats, Tp, VC_s, full, done, q, ct, lane, NG, R, P, FC, BS, QS, NS, ncf, wq, inv_mu,
+            SS_DISPATCH_K(r, (ss_phase_b<K_, NTC>(a, ring, stage_floats, Tp, Vst, full, done, q, ct, lane, NG, R, P, FC, BS, QS, VSS, NS, ncf, wq, inv_mu,
                                                   mu_f, lamq, inv_mu_next, Qf, zz_acc, nnz_acc, max_acc, wmax_acc, sat_acc, first, inv_dual)));
         }
     }
@@ -466,10 +465,11 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
 }
 
 // -------------------------------------------------------------------------------------------------------------
-static size_t ss_smem_bytes(int n, int R, int FC, int NS, int NTC, int kcap) {
+static size_t ss_smem_bytes(int n, int R, int FC, int NS, int NTC) {
+    (void)n;
     const int P = 3 * R, NQ = P / 4, NFL = NTC / NQ;
     const size_t bs = ((size_t)FC * P + 127) / 128 * 128;
-    size_t fl = (size_t)NS * 3 * bs + (size_t)NFL * SS_KRED * P + (size_t)SS_KC * 4 * R + (size_t)2 * n * kcap;
+    size_t fl = (size_t)NS * 3 * bs + (size_t)NFL * SS_KRED * P + (size_t)SS_KC * 4 * R + (size_t)NS * ((FC * SS_KC + 31) / 32 * 32) + 32;
     return fl * sizeof(float) + (size_t)3 * NS * sizeof(uint64_t) + 64;
 }
 
@@ -492,17 +492,12 @@ bool make_shrink_stream_plan(int n, int rows, int cols, long long ld, int num_sm
         const int NFL = NTC / NQ;
         int FC = env_fc ? atoi(env_fc) : 4 * NFL;
         FC = std::max(1, std::min(FC, std::min(n, 256)));
-        // ranks up to 16 if the Vr / VC copies fit next to a 3-stage ring, else up to 8 (long clips, e.g. 600 frames)
-        int NS = 0, kcap = 0;
-        for (int kc : {SS_KC, 8}) {
-            NS = env_ns ? atoi(env_ns) : 6;
-            while (NS >= 3 && ss_smem_bytes(n, R, FC, NS, NTC, kc) > SS_SMEM_CAP) --NS;
-            if (NS >= 3) { kcap = kc; break; }
-        }
-        if (kcap == 0) continue;
-        p.R = R; p.P = 3 * R; p.FC = FC; p.NS = NS; p.NCW = NCW; p.kcap = kcap;
+        int NS = env_ns ? atoi(env_ns) : 6;
+        while (NS >= 3 && ss_smem_bytes(n, R, FC, NS, NTC) > SS_SMEM_CAP) --NS;
+        if (NS < 3) continue;
+        p.R = R; p.P = 3 * R; p.FC = FC; p.NS = NS; p.NCW = NCW; p.kcap = SS_KC;
         p.bufstride = (int)(((size_t)FC * p.P + 127) / 128 * 128);
-        p.smem_bytes = ss_smem_bytes(n, R, FC, NS, NTC, kcap);
+        p.smem_bytes = ss_smem_bytes(n, R, FC, NS, NTC);
         p.nchunkf = (n + FC - 1) / FC;
         p.ntile_r = (rows + R - 1) / R;
         p.ntile_c = (cols + 2) / 3;
@@ -526,6 +521,17 @@ int make_shrink_stream_maps(const ShrinkStreamPlan& p, const float* D, float* S,
     if (U != nullptr) { if (make_tensor_map_f32(&m->U, U, 3, dims, strides, box) != 0) return -1; m->has_U = true; }
     else m->U = m->S;
     m->has_Q = false; m->Q = m->S;
+    return 0;
+}
+
+int make_shrink_stream_vmaps(const ShrinkStreamPlan& p, const float* Vr, const float* VC, int vstride, ShrinkTmaMaps* m) {
+    // Vr / VC: float32 [n frames][vstride]; a stage takes the first SS_KC columns of its FC frames (frames beyond n: zero)
+    if (vstride < SS_KC) { set_error("shrink_stream: Vr row stride %d < %d", vstride, SS_KC); return -1; }
+    const uint64_t dims[2] = {(uint64_t)vstride, (uint64_t)p.n};
+    const uint64_t strides[1] = {(uint64_t)vstride * sizeof(float)};
+    const uint32_t box[2] = {(uint32_t)SS_KC, (uint32_t)p.FC};
+    if (make_tensor_map_f32(&m->Vr, Vr, 2, dims, strides, box) != 0) return -1;
+    if (make_tensor_map_f32(&m->VC, VC, 2, dims, strides, box) != 0) return -1;
     return 0;
 }
 
@@ -553,7 +559,8 @@ static int launch_ss(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, const
         attr_set = true;
     }
     const CUtensorMap& outmap = (mode == SHRINK_SPILL) ? maps.U : maps.S;
-    shrink_stream_kernel<NCW, RT, FCT><<<p.grid, 32 * (NCW + 2), p.smem_bytes, stream>>>(maps.D, maps.S, maps.Y, outmap, maps.Q, a);
+    shrink_stream_kernel<NCW, RT, FCT><<<p.grid, 32 * (NCW + 2), p.smem_bytes, stream>>>(maps.D, maps.S, maps.Y, outmap, maps.Q, maps.Vr,
+                                                                                        maps.VC, a);
     BSUB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -570,6 +577,7 @@ int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, S
     a.QS = (int)(((size_t)p.FC * p.P + 127) / 128 * 128);
     if (p.NCW == 16) return launch_ss<16, 0, 0>(p, maps, a, mode, stream);
     if (p.R == 48 && p.FC == 28) return launch_ss<8, 48, 28>(p, maps, a, mode, stream);
+    if (p.R == 48 && p.FC == 32) return launch_ss<8, 48, 32>(p, maps, a, mode, stream);
     return launch_ss<8, 0, 0>(p, maps, a, mode, stream);
 }
 

@@ -163,7 +163,7 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
         ALLOC(s->eb.work, sizeof(double) * s->ep.work_doubles);
         ALLOC(s->eb.lam, sizeof(double) * s->n);
         ALLOC(s->eb.Z, sizeof(double) * (size_t)s->n * s->n);
-        s->eb.vstride = ((s->n + 3) / 4) * 4;
+        s->eb.vstride = std::max(16, ((s->n + 3) / 4) * 4);        // >= 16: the streamed shrink loads 16-column boxes
         ALLOC(s->eb.Vr, sizeof(float) * (size_t)s->n * s->eb.vstride);
         ALLOC(s->eb.VC, sizeof(float) * (size_t)s->n * s->eb.vstride);
         cudaMemset(s->eb.Vr, 0, sizeof(float) * (size_t)s->n * s->eb.vstride);
@@ -492,6 +492,7 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
         if (!s->stmaps_ready) {
             RET_IF(make_shrink_tma_maps(s->stp, s->D, s->S, s->Y, s->U, &s->stmaps));
             if (s->use_stream) RET_IF(make_shrink_stream_maps(s->ssp, s->D, s->S, s->Y, s->U, &s->ssmaps));
+            if (s->use_stream) RET_IF(make_shrink_stream_vmaps(s->ssp, s->eb.Vr, s->eb.VC, s->eb.vstride, &s->ssmaps));
             if (s->use_stream && s->use_i8) RET_IF(make_shrink_stream_qmap(s->ssp, s->Wq, &s->ssmaps));
             s->stmaps_ready = true;
         }

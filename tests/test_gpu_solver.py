@@ -190,6 +190,21 @@ def test_fast_paths_match_fallback(B, rows, cols, n):
     assert rel_fro(L1, L0) <= 2e-5 and rel_fro(S1, S0) <= 2e-4
 
 
+def test_batch_of_clips_in_flight(B):
+    """BASELINE.json config 5 in miniature: independent clips decomposed with several solver handles in flight (threads +
+    streams) give what one clip at a time gives."""
+    from background_subtraction_b200 import synth
+    rows, cols, n = 48, 63, 40
+    clips = [np.asfortranarray(synth.preprocess_u8(synth.make_clip(rows, cols, n, seed=100 + i, n_rect=2)[0]).T.astype(np.float64))
+             for i in range(6)]
+    groups = B.get_proximal_flat_groups_nonoverlap((rows, cols), (3, 3))
+    seq = [B.inexact_alm_lsd(D, groups=groups) for D in clips]
+    par = B.inexact_alm_lsd_batch(clips, groups=groups, in_flight=3)
+    for (L0, S0, it0, c0), (L1, S1, it1, c1) in zip(seq, par):
+        assert it0 == it1 and c0 == c1 and c1
+        assert rel_fro(L1, L0) <= 1e-6 and rel_fro(S1, S0) <= 1e-6      # (the kernels are deterministic: in practice identical)
+
+
 def test_rpca_l1(B, watersurface_u8):
     from oracle import alm_oracle as O
     D, _x, _mean = O.normalize_and_center(watersurface_u8[:48, :60, :20])
