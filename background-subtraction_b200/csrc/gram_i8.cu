@@ -144,6 +144,8 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = gi_instr_desc(Nj);
+            const uint32_t lboB = (diag || Nj == 128) ? 2048u : (uint32_t)(Nj * 16);
+            const uint64_t descA0 = gi_smem_desc(0u, 2048u), descB0 = gi_smem_desc(0u, lboB);
             int since_flush = 0, nflush = 0;
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % GI_STAGES;
@@ -155,6 +157,10 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                 gi_mbar_wait(&full[s], (uint32_t)(u & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sbase = smem_u32(stages + (size_t)s * GI_STAGE_BYTES);
+                // descriptors = per-kernel constant part + (address >> 4): one 64-bit add per operand keeps the single issuing
+                // thread ahead of the tensor pipe (a 128x128x32 MMA lasts ~68 cycles)
+                const uint64_t sa = descA0 + (uint64_t)((sbase >> 4) & 0x3FFF);
+                const uint64_t sb = descB0 + (uint64_t)(((sbase + (diag ? 0u : (uint32_t)(4 * GI_TILE_BYTES))) >> 4) & 0x3FFF);
 #pragma unroll
                 for (int ks = 0; ks < GI_KB / 32; ++ks) {
 #pragma unroll
@@ -163,9 +169,8 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                         for (int j = 0; j < 4; ++j) {
                             const int cls = i + j - 3;
                             if (cls < 0) continue;
-                            const uint32_t lboB = (diag || Nj == 128) ? 2048u : (uint32_t)(Nj * 16);
-                            const uint64_t da = gi_smem_desc(sbase + (uint32_t)(i * GI_TILE_BYTES) + ks * 4096, 2048u);
-                            const uint64_t db = gi_smem_desc(sbase + (uint32_t)(((diag ? 0 : 4) + j) * GI_TILE_BYTES) + ks * 2 * lboB, lboB);
+                            const uint64_t da = sa + (uint64_t)((i * GI_TILE_BYTES + ks * 4096) >> 4);
+                            const uint64_t db = sb + (uint64_t)((j * GI_TILE_BYTES) >> 4) + (uint64_t)ks * (uint64_t)((2 * lboB) >> 4);
                             // first pair of a class right after a flush overwrites the accumulator
                             const bool first = (since_flush == 0 && ks == 0 && j == 3);   // (i, 3) is the first pair of class i
                             gi_mma(tmem_base + (uint32_t)(cls * 128), da, db, idesc, first ? 0u : 1u);
@@ -321,6 +326,7 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
             const uint32_t idesc = gi_instr_desc(Nj);
             const uint32_t offA = useA ? 0u : (uint32_t)(4 * GI_TILE_BYTES);             // (2,2) takes both operands from slot B
             const uint32_t offB = diag ? offA : (uint32_t)(4 * GI_TILE_BYTES);
+            const uint64_t desc0 = gi_smem_desc(0u, 2048u);      // constant part of the operand descriptors (see gram_i8_kernel)
             int since_flush = 0, nflush = 0;
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % GI_STAGES;
@@ -332,6 +338,8 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
                 gi_mbar_wait(&full[s], (uint32_t)(u & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sbase = smem_u32(stages + (size_t)s * GI_STAGE_BYTES);
+                // (in a cluster launch the shared-window address carries CTA-rank bits above the 14-bit descriptor field: mask)
+                const uint64_t sa = desc0 + (uint64_t)(((sbase + offA) >> 4) & 0x3FFF), sb = desc0 + (uint64_t)(((sbase + offB) >> 4) & 0x3FFF);
 #pragma unroll
                 for (int ks = 0; ks < GI_KB / 32; ++ks) {
 #pragma unroll
@@ -340,8 +348,8 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
                         for (int j = 0; j < 4; ++j) {
                             const int cls = i + j - 3;
                             if (cls < 0) continue;
-                            const uint64_t da = gi_smem_desc(sbase + offA + (uint32_t)(i * GI_TILE_BYTES) + ks * 4096, 2048u);
-                            const uint64_t db = gi_smem_desc(sbase + offB + (uint32_t)(j * GI_TILE_BYTES) + ks * 4096, 2048u);
+                            const uint64_t da = sa + (uint64_t)((i * GI_TILE_BYTES + ks * 4096) >> 4);
+                            const uint64_t db = sb + (uint64_t)((j * GI_TILE_BYTES + ks * 4096) >> 4);
                             const bool first = (since_flush == 0 && ks == 0 && j == 3);
                             gi_mma(tmem_base + (uint32_t)(cls * 128), da, db, idesc, first ? 0u : 1u);
                         }
