@@ -318,9 +318,10 @@ def main():
     shrink_ms, n_shrink = phase_ms("shrink")
     # kernels launched per enqueued iteration: gram_dmma, gram_reduce, (gram_i8, gram_i8_finish), eig, shrink_stream /
     # shrink_tma / shrink (whichever exist), control_post x2; per step: rowsum, Gram(D) (quantize_D + gram_i8 + finish, or
-    # gram_dmma + reduce), eig, init_Y, lowrank, absmax, mask_stats, mask_write
+    # gram_dmma + reduce), eig, init_Y (not with the int8 path: iteration 1 derives S0, Y0 from D), lowrank, absmax, mask_stats,
+    # mask_write
     per_iter = 2 + (2 if use_i8 else 0) + 1 + (2 if info["use_stream"] else 1) + 2
-    gpu_launches = int(args.steps * (driver.iters_enqueued * per_iter + (11 if use_i8 else 9)))
+    gpu_launches = int(args.steps * (driver.iters_enqueued * per_iter + (10 if use_i8 else 9)))
 
     # ---- end to end through the public host-buffer API (single GPU only) ----
     # Every clip: H2D of D from pinned memory, bsub_run, D2H of L, S and the mask -- all inside the timed region.  PCIe moves
