@@ -18,6 +18,7 @@
 //      Vr and VC = Vr * diag(1 - 1/(mu sigma)) written in fp32 for the shrink pass.
 #include <cooperative_groups.h>
 #include <float.h>
+#include <stdlib.h>
 #include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
@@ -654,7 +655,9 @@ EigPlan make_eig_plan(int n, int npad) {
     EigPlan p;
     p.n = n; p.npad = npad;
     int C = 1;
-    while (C < 16 && (n + C - 1) / C > 40) C *= 2;
+    int rows_target = 40;
+    if (const char* e = getenv("BSUB_EIG_ROWS")) rows_target = std::max(1, atoi(e));
+    while (C < 16 && (n + C - 1) / C > rows_target) C *= 2;
     const size_t cap = 225 * 1024;
     auto bytes_for = [&](int Cc, bool in_smem) {
         size_t rows = (size_t)(n + Cc - 1) / Cc;

@@ -325,7 +325,7 @@ def main():
 
     # ---- end to end through the public host-buffer API (single GPU only) ----
     # Every clip: H2D of D from pinned memory, bsub_run, D2H of L, S and the mask -- all inside the timed region.  PCIe moves
-    # 8.1 GB per clip (~150 ms), about as long as the solve itself, so a serving loop keeps several clips in flight (default 3,
+    # 8.1 GB per clip (~150 ms), about as long as the solve itself, so a serving loop keeps several clips in flight (default 4,
     # BSUB_E2E_CLIPS): one solver handle per clip, each driven by its own host thread and stream, so the copies of one clip
     # overlap the kernels of the others -- and the 8-SM eigensolve of one clip runs beside the streaming kernels of another,
     # which is why this throughput can exceed the one-clip-at-a-time `value`.  `serial_ms_per_step` is the latency of one
@@ -334,7 +334,7 @@ def main():
     if not args.no_e2e and world == 1:
         import ctypes
         from background_subtraction_b200 import _cabi as C
-        nwork = int(os.environ.get("BSUB_E2E_CLIPS", "3"))
+        nwork = int(os.environ.get("BSUB_E2E_CLIPS", "4"))
         decs = [solver.dec] + [bdist.CudaStepSolver(rows, cols_local, frames, m, tile_rows=args.tile_rows,
                                                     cluster_frames=args.cluster_frames).dec for _ in range(nwork - 1)]
         outs = [tuple(torch.empty((frames, m), dtype=dt).pin_memory() for dt in (torch.float32, torch.float32, torch.uint8))
