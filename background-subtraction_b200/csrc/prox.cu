@@ -336,7 +336,10 @@ int launch_prox_graph3(const float* U, float* V, float* xi, float* tot, const fl
     }
     GraphArgs a;
     a.U = U; a.V = V; a.xi = xi; a.tot = tot; a.eta = eta; a.ld = ld; a.rows = rows; a.cols = cols; a.n = n; a.lam = lam;
-    a.max_sweeps = max_sweeps; a.tol = tol; a.sweeps_out = sweeps_out; a.change_bits = change_bits; a.st = st;
+    // sweeps_out, when given, is an int[4] owned by the caller: [0] sweeps used, [1..2] the ping-pong change flags (per solver
+    // handle, so that handles running concurrently on different streams do not share them)
+    a.max_sweeps = max_sweeps; a.tol = tol; a.sweeps_out = sweeps_out; a.st = st;
+    a.change_bits = (sweeps_out != nullptr) ? reinterpret_cast<unsigned int*>(sweeps_out + 1) : change_bits;
     a.center = center; a.eta_stride = eta_stride;
     if (center && eta == nullptr) { set_error("prox_graph3: centre mode needs the per-frame eta map"); return -1; }
     const long long nw9 = ((long long)rows * cols / 9 + 1) * n;

@@ -284,7 +284,7 @@ int bsub_set_graph_windows(bsub_solver* s, const double* eta, int64_t n_eta) {
     }
     if (!s->xi) CK(cudaMalloc((void**)&s->xi, sizeof(float) * (size_t)s->n * nw * 9));
     if (!s->tot) CK(cudaMalloc((void**)&s->tot, sizeof(float) * (size_t)s->n * s->ld));
-    if (!s->sweeps_dev) CK(cudaMalloc((void**)&s->sweeps_dev, sizeof(int)));
+    if (!s->sweeps_dev) CK(cudaMalloc((void**)&s->sweeps_dev, sizeof(int) * 4));
     s->graph_set = true;
     return 0;
 }
@@ -305,7 +305,7 @@ int bsub_set_center_windows(bsub_solver* s, const float* eta, const uint8_t* bac
     s->nlab = 1;
     if (!s->xi) CK(cudaMalloc((void**)&s->xi, sizeof(float) * nm * 9));          // one candidate window per pixel and frame
     if (!s->tot) CK(cudaMalloc((void**)&s->tot, sizeof(float) * (size_t)s->n * s->ld));
-    if (!s->sweeps_dev) CK(cudaMalloc((void**)&s->sweeps_dev, sizeof(int)));
+    if (!s->sweeps_dev) CK(cudaMalloc((void**)&s->sweeps_dev, sizeof(int) * 4));
     s->graph_set = true;
     return 0;
 }
@@ -761,7 +761,7 @@ int bsub_prox_graph3_dev(const float* U, float* V, int64_t ld, int32_t rows, int
     float *xi = nullptr, *tot = nullptr, *eta = nullptr; int* sw = nullptr;
     CK(cudaMalloc((void**)&xi, sizeof(float) * (size_t)n * nw * 9));
     CK(cudaMalloc((void**)&tot, sizeof(float) * (size_t)n * ld));
-    CK(cudaMalloc((void**)&sw, sizeof(int)));
+    CK(cudaMalloc((void**)&sw, sizeof(int) * 4));
     if (eta_host) {
         std::vector<float> ef((size_t)nw);
         for (long long i = 0; i < nw; ++i) ef[i] = (float)eta_host[i];
