@@ -8,12 +8,17 @@
 // through a ring of shared-memory stages (FC frames per stage) filled by 3-D TMA box loads:
 //   phase A  D,S,Y  -> W on the fly -> T accumulated in registers over all frames (one reduction per tile)
 //   phase B  D,Y    -> per 3x3 group and frame: L from T, G_S, prox, dual update, results written in place and sent
-//                      out with TMA box stores (S and Y).  The second read of D,Y hits L2 (a tile's D,Y are
-//                      n*P*8 bytes; 148 tiles in flight ~ 51 MB << 126 MB of L2).
+//                      out with TMA box stores (S and Y).  The second read of D,Y partly hits L2 (a tile's D,Y are
+//                      n*P*8 bytes; 148 tiles in flight ~ 51 MB of the 126 MB L2; measured hit rate ~60 %).
+//                      With the int8 Gram on, W of the NEXT iteration is quantised here too and leaves as four digit
+//                      planes (gram_i8.cu): the Gram pass then reads 4 B per element instead of D,S,Y.
+// Every stage also carries the Vr (phase A) / VC (phase B) rows of its frames, so shared memory does not grow with n.
+// Iteration 1 can run from D alone (S0 = 0, Y0 = D / dual_norm formed on the fly: `implied_first`).
 // Roles: warp 0 lane 0 = loader (TMA loads), warp 1 lane 0 = storer (TMA stores, stage recycling), the remaining
 // warps compute.  All hand-offs are mbarriers (full / done / free per stage); the only CTA-wide barriers are the two
 // named barriers of the per-tile T reduction.  No thread-block clusters, no cross-CTA exchange.
-// HBM traffic: read D,S,Y + write S,Y = 20 B per matrix element (+8 B of L2 re-reads).
+// HBM traffic: read D,S,Y + write S,Y = 20 B per matrix element, + 4 B for the digit planes (+ the part of the 8 B
+// phase-B re-read that misses L2).
 #include <stdlib.h>
 #include <algorithm>
 #include "common.cuh"
@@ -38,7 +43,7 @@ struct ShrinkStreamArgs {
     int wq;                                // write the int8 slices of W_next (gram_i8.cu)
     int QS;                                // bytes per slice sub-buffer of a stage (FC*Pq rounded up to 128)
     int Pq;                                // = P (a multiple of 16 when the slices are on): bytes per frame of a tile
-    int kcap;                              // ranks <= kcap are handled here (row stride of the Vr / VC copies in shared memory)
+    int kcap;                              // ranks <= kcap (= SS_KC) are handled here; larger ones by the fallback kernel
     int implied_first;                     // iteration 1 takes S = 0, Y = D / dual_norm from D instead of reading them (no init pass)
 };
 
