@@ -285,28 +285,72 @@ __device__ void eig_tridiag_dsmem(const EigArgs& a, double* Asm, double* xb, dou
         EIG_TICK(3)
         double* xn = xb_rem + (par ^ 1) * n;
         const int fl = (j + 1) & 31;                        // lane / block (t0) that hold column j + 1
-        for (int li = l0 + warp; li < a.rows_per; li += EIG_WARPS) {          // same rows per warp as in the product above
-            const int i = c + li * C;
-            if (i < n) {
-                double* r = Asm + (size_t)li * n;
-                const double vi = (i == j + 1) ? 1.0 : x[i] * scale;
-                const double wi = fma(kc, vi, pb[i]);
-                double first = 0.0;
-#pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    const int col = lane + 32 * t;
-                    if (t >= t0 && col > j && col < n) {
-                        const double nv = r[col] - (vi * w[t] + wi * v[t]);
-                        r[col] = nv;
-                        if (t == t0) first = nv;
+        if constexpr (NT <= 10) {
+            // (a) the entries of the NEXT column first: they are all the other CTAs wait for.  A[i][j+1] -= v_i w_{j+1} + w_i v_{j+1}
+            //     with v_{j+1} = 1.  Then arrive at the cluster barrier, (b) update the rest of my rows while the barrier
+            //     completes, and only then wait.  Everything read from pb is taken before the arrive: a CTA that is through
+            //     the barrier may already be writing the next p into it.
+            double wsel = 0.0;
+    #pragma unroll
+            for (int t = 0; t < NT; ++t) if (t == t0) wsel = w[t];
+            const double wnext = __shfl_sync(0xffffffffu, wsel, fl);
+            double vi_[3], wi_[3];
+            bool ok_[3];
+    #pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int li = l0 + warp + k * EIG_WARPS, i = c + li * C;
+                ok_[k] = (li < a.rows_per) && (i < n);
+                vi_[k] = 0.0; wi_[k] = 0.0;
+                if (ok_[k]) {
+                    double* r = Asm + (size_t)li * n;
+                    vi_[k] = (i == j + 1) ? 1.0 : x[i] * scale;
+                    wi_[k] = fma(kc, vi_[k], pb[i]);
+                    const double nv = r[j + 1] - (vi_[k] * wnext + wi_[k]);
+                    __syncwarp();
+                    if (lane == 0) r[j + 1] = nv;
+                    if (lane < C && i > j + 1) xn[i] = nv;     // this CTA's entry of the next column, into every CTA
+                }
+            }
+            EIG_TICK(4)
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    #pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (ok_[k]) {
+                    double* r = Asm + (size_t)(l0 + warp + k * EIG_WARPS) * n;
+                    const double vi = vi_[k], wi = wi_[k];
+    #pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        const int col = lane + 32 * t;
+                        if (t >= t0 && col > j + 1 && col < n) r[col] -= vi * w[t] + wi * v[t];
                     }
                 }
-                first = __shfl_sync(0xffffffffu, first, fl);   // new A[i][j+1] = this CTA's entry of the next column
-                if (lane < C && i > j + 1) xn[i] = first;
             }
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        } else {
+            // long rows: the split version costs registers that the NT > 10 instances do not have; one pass, full barrier
+            for (int li = l0 + warp; li < a.rows_per; li += EIG_WARPS) {
+                const int i = c + li * C;
+                if (i < n) {
+                    double* r = Asm + (size_t)li * n;
+                    const double vi = (i == j + 1) ? 1.0 : x[i] * scale;
+                    const double wi = fma(kc, vi, pb[i]);
+                    double first = 0.0;
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        const int col = lane + 32 * t;
+                        if (t >= t0 && col > j && col < n) {
+                            const double nv = r[col] - (vi * w[t] + wi * v[t]);
+                            r[col] = nv;
+                            if (t == t0) first = nv;
+                        }
+                    }
+                    first = __shfl_sync(0xffffffffu, first, fl);
+                    if (lane < C && i > j + 1) xn[i] = first;
+                }
+            }
+            EIG_TICK(4)
+            cluster.sync();
         }
-        EIG_TICK(4)
-        cluster.sync();
         EIG_TICK(5)
     }
     if (c == 0 && tid == 0) for (int k = 0; k < 6; ++k) st->eig_clk[8 + k] = tph[k];
@@ -656,7 +700,7 @@ EigPlan make_eig_plan(int n, int npad) {
     p.n = n; p.npad = npad;
     int C = 1;
     int rows_target = 40;
-    if (const char* e = getenv("BSUB_EIG_ROWS")) rows_target = std::max(1, atoi(e));
+    if (const char* e = getenv("BSUB_EIG_ROWS")) rows_target = std::max(1, std::min(atoi(e), 3 * EIG_WARPS));   // <= 3 rows per warp
     while (C < 16 && (n + C - 1) / C > rows_target) C *= 2;
     const size_t cap = 225 * 1024;
     auto bytes_for = [&](int Cc, bool in_smem) {
