@@ -483,10 +483,12 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
         } else if (c == 0) { const double* r = Arow(0); a.dd[0] = r[0]; a.ee[0] = 0.0; a.tau[0] = 0.0; }
     }
     cluster.sync();
-    if (c != 0) return;
-    if (tid == 0) st->eig_clk[1] = clock64();
+    if (c == 0 && tid == 0) st->eig_clk[1] = clock64();
 
-    // ---- 2. top-K eigenvalues of the tridiagonal matrix: multisection on Sturm counts ------------------------
+    // ---- 2. top-K eigenvalues of the tridiagonal matrix: multisection on Sturm counts, by the whole cluster -----
+    // Every round cuts each bracket into C * S + 1 pieces: CTA c evaluates the shifts c*S .. c*S+S-1, tells every CTA how
+    // many of its shifts lie at or below the eigenvalue (they form a prefix: the count is monotone in the shift), and all
+    // CTAs update their identical copies of the brackets from the C counts.  One cluster barrier per round.
     // shared-memory carve-up for the remaining phases (the matrix rows are dead now)
     double* d_s = Asm;                 // [n]
     double* e2_s = Asm + n;            // [n]
@@ -522,36 +524,53 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
         double widen = 2.1 * tnorm * DBL_EPSILON * n + 2.1 * pivmin;
         gl -= widen; gu += widen;
     }
+    int* mycnt_s = reinterpret_cast<int*>(nlo_s);                 // [EIG_THREADS] my CTA's count per eigenvalue
+    int* cnt_s = reinterpret_cast<int*>(zs);                      // [2][C][EIG_THREADS] counts of every CTA, by round parity
+    int* cnt_rem = (lane < C) ? cluster.map_shared_rank(cnt_s, lane) : nullptr;
+    int rr = 0;
     for (int kb = 0; kb < K; kb += EIG_THREADS) {
         const int Kb = min(K - kb, EIG_THREADS);
-        const int S = max(1, EIG_THREADS / Kb);
-        int rounds = (int)ceil(62.0 / log2((double)S + 1.0)) + 1;
+        const int S = max(1, EIG_THREADS / Kb), Stot = C * S;
+        const int rounds = (int)ceil(62.0 / log2((double)Stot + 1.0)) + 1;
+        const double inv_pieces = 1.0 / (double)(Stot + 1);
         for (int t = tid; t < Kb; t += EIG_THREADS) { lo_s[t] = gl; hi_s[t] = gu; }
         __syncthreads();
         const int kk = tid / S, s = tid - kk * S;
         const bool active = kk < Kb;
-        for (int r = 0; r < rounds; ++r) {
-            double x = 0.0;
+        for (int r = 0; r < rounds; ++r, ++rr) {
+            const int par = rr & 1;
             int f = 0;
             if (active) {
                 const double lo = lo_s[kk], hi = hi_s[kk];
-                x = lo + (hi - lo) * ((double)(s + 1) / (double)(S + 1));
+                const double x = lo + (hi - lo) * ((double)(c * S + s + 1) * inv_pieces);
                 const int cnt_ge = n - sturm_negcount(d_s, e2_s, n, x, pivmin);   // # eigenvalues >= x
                 f = (cnt_ge >= kb + kk + 1);                                          // x <= lambda_k
             }
             flag_s[tid] = f;
-            nlo_s[tid] = x;
             __syncthreads();
             if (active) {
                 const int fn = (s + 1 < S) ? flag_s[tid + 1] : 0;
-                if (f && !fn) { lo_s[kk] = x; if (s + 1 < S) hi_s[kk] = nlo_s[tid + 1]; }
-                if (s == 0 && !f) hi_s[kk] = x;
+                if (f && !fn) mycnt_s[kk] = s + 1;
+                if (s == 0 && !f) mycnt_s[kk] = 0;
+            }
+            __syncthreads();
+            // one warp per eigenvalue group: lanes < C deliver this CTA's count to every CTA
+            for (int k2 = warp; k2 < Kb; k2 += EIG_WARPS)
+                if (lane < C) cnt_rem[(par * C + c) * EIG_THREADS + k2] = mycnt_s[k2];
+            cluster.sync();
+            if (tid < Kb) {
+                int tot = 0;
+                for (int q = 0; q < C; ++q) tot += cnt_s[(par * C + q) * EIG_THREADS + tid];
+                const double lo = lo_s[tid], hi = hi_s[tid];
+                if (tot > 0) lo_s[tid] = lo + (hi - lo) * ((double)tot * inv_pieces);
+                if (tot < Stot) hi_s[tid] = lo + (hi - lo) * ((double)(tot + 1) * inv_pieces);
             }
             __syncthreads();
         }
-        for (int t = tid; t < Kb; t += EIG_THREADS) a.lam[kb + t] = 0.5 * (lo_s[t] + hi_s[t]);
+        if (c == 0) for (int t = tid; t < Kb; t += EIG_THREADS) a.lam[kb + t] = 0.5 * (lo_s[t] + hi_s[t]);
         __syncthreads();
     }
+    if (c != 0) return;                                           // the rest runs in CTA 0 (nobody writes into a CTA after its last barrier)
     __threadfence_block();
     __syncthreads();
     if (tid == 0) st->eig_clk[2] = clock64();
