@@ -40,8 +40,16 @@ def test_no_silent_cpu_fallback():
         B.inexact_alm_lsd(D, groups=B.get_proximal_flat_groups_nonoverlap((6, 6), (3, 3)))
     with pytest.raises(Exception, match="no CUDA device"):
         B.foreground_mask(D, D, D)
-    src = open(os.path.join(ROOT, "background-subtraction_b200", "api.py")).read() + \
-        open(os.path.join(ROOT, "background-subtraction_b200", "dist.py")).read()
+    with pytest.raises(Exception, match="no CUDA device"):
+        B.inexact_alm_lsd_batch([D, D], groups=B.get_proximal_flat_groups_nonoverlap((6, 6), (3, 3)))
+    w = -np.ones((6, 6)); w[2, 3] = 1.0
+    with pytest.raises(Exception, match="no CUDA device"):
+        B.inexact_alm_lsd_with_background(D, [B.get_proximal_graph_group_centers((6, 6), 1, w)] * 4,
+                                          [(w < 0).flatten(order='F')] * 4)
+    with pytest.raises(Exception, match="graphs must be list/array"):
+        B.inexact_alm_lsd_with_background(D, B.get_proximal_graph_group_centers((6, 6), 1, w), [(w < 0).flatten(order='F')] * 4)
+    src = "".join(open(os.path.join(ROOT, "background-subtraction_b200", f)).read()
+                  for f in ("api.py", "dist.py", "_cabi.py", "synth.py", "build.py", "__init__.py"))
     assert "oracle" not in src.replace("oracle's", "")          # the product never imports the checker
 
 
