@@ -133,6 +133,7 @@ int launch_dual_update(const float* D, const float* Snew, float* S, float* Y, co
 
 // ---------------------------------------------------------------- mask.cu
 int launch_absmax(const float* S, long long ld, long long m, int n, double* out_max, cudaStream_t s);
+int launch_maxS_from_state(const DevState* st, double* out_max, cudaStream_t s);
 int launch_mask_stats(const float* D, const float* L, const float* S, long long ld, long long m, int n,
                       const double* absmax, double* stats /*[3]: count, sum, sumsq*/, cudaStream_t s);
 int launch_mask_write(const float* S, long long ld, long long m, int n, const double* stats, double sigmas,

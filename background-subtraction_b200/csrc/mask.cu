@@ -82,9 +82,32 @@ __global__ void mask_write_kernel(const float* __restrict__ S, long long ld, lon
     } else {
         th = nan("");                       // np.mean of an empty selection is nan -> mask all False
     }
+    if (((m | mask_ld) & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 3) == 0) {
+        // four pixels per thread: 16-byte loads, 4-byte stores (same comparison in double as the scalar path)
+        const long long m4 = m / 4;
+        for (int f = blockIdx.y; f < n; f += gridDim.y)
+            for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < m4; q += (long long)gridDim.x * blockDim.x) {
+                const float4 v = ldg4_stream(S + (size_t)f * ld + 4 * q);
+                uchar4 o;
+                o.x = ((double)fabsf(v.x) > th) ? 1 : 0; o.y = ((double)fabsf(v.y) > th) ? 1 : 0;
+                o.z = ((double)fabsf(v.z) > th) ? 1 : 0; o.w = ((double)fabsf(v.w) > th) ? 1 : 0;
+                *reinterpret_cast<uchar4*>(mask + (size_t)f * mask_ld + 4 * q) = o;
+            }
+        return;
+    }
     for (int f = blockIdx.y; f < n; f += gridDim.y)
         for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < m; p += (long long)gridDim.x * blockDim.x)
             mask[(size_t)f * mask_ld + p] = ((double)fabsf(S[(size_t)f * ld + p]) > th) ? 1 : 0;
+}
+
+// max |S| of a finished solve is already known on the device (control_post keeps the last iteration's value)
+__global__ void maxS_from_state_kernel(const DevState* st, double* out_max) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out_max = (double)st->maxS;
+}
+int launch_maxS_from_state(const DevState* st, double* out_max, cudaStream_t s) {
+    maxS_from_state_kernel<<<1, 32, 0, s>>>(st, out_max);
+    BSUB_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 int launch_mask_write(const float* S, long long ld, long long m, int n, const double* stats, double sigmas, unsigned char* mask,

@@ -684,6 +684,10 @@ int bsub_mask_stats_local(bsub_solver* s, int phase, void* stream) {
     double* tail = s->comm_sum + (size_t)s->npad * s->npad;
     if (phase == 0) {
         CK(cudaMemsetAsync(s->comm_max, 0, sizeof(double) * 8, st));
+        // one shard holding the whole matrix: max |S| is what the last shrink pass reported; shards need the pass (the
+        // per-iteration maximum is not all-reduced)
+        if (s->cfg.m_global == s->m && s->iters_enqueued > 0 && getenv("BSUB_MASK_ABSMAX") == nullptr)
+            return launch_maxS_from_state(s->st, s->comm_max + 1, st);
         return launch_absmax(s->S, s->ld, s->m, s->n, s->comm_max + 1, st);
     }
     CK(cudaMemsetAsync(tail + 4, 0, sizeof(double) * 3, st));
