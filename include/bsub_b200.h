@@ -83,7 +83,11 @@ void bsub_default_config(bsub_config* cfg);
 /* sizeof(bsub_config), sizeof(bsub_status), sizeof(bsub_iter_log): lets a binding verify its struct layouts */
 void bsub_abi_sizes(int32_t out3[3]);
 
-/* ---- solver life cycle ------------------------------------------------------------------------------------ */
+/* ---- solver life cycle ------------------------------------------------------------------------------------
+ * Threading / devices: a handle lives on the CUDA device that is current when bsub_create runs; call its entry points
+ * from threads whose current device is that one (one process per GPU is the intended model: kernel attributes are set
+ * once per process).  Different handles may be driven concurrently from different host threads on different streams
+ * (error text is thread-local); one handle must not be used from two threads at once. */
 int bsub_create(const bsub_config* cfg, bsub_solver** out);
 int bsub_destroy(bsub_solver* s);
 
