@@ -331,10 +331,10 @@ def main():
     # which is why this throughput can exceed the one-clip-at-a-time `value`.  `serial_ms_per_step` is the latency of one
     # clip alone (nothing overlapped).
     e2e = None
-    if not args.no_e2e and world == 1:
+
+    def measure_e2e(nwork):
         import ctypes
         from background_subtraction_b200 import _cabi as C
-        nwork = int(os.environ.get("BSUB_E2E_CLIPS", "4"))
         decs = [solver.dec] + [bdist.CudaStepSolver(rows, cols_local, frames, m, tile_rows=args.tile_rows,
                                                     cluster_frames=args.cluster_frames).dec for _ in range(nwork - 1)]
         outs = [tuple(torch.empty((frames, m), dtype=dt).pin_memory() for dt in (torch.float32, torch.float32, torch.uint8))
@@ -401,12 +401,30 @@ def main():
             for tag, t in sorted(tlog, key=lambda x: x[1][0]):
                 sys.stderr.write("e2e worker %d: start %.1f  load %.1f run %.1f L %.1f S %.1f mask %.1f ms\n" % (
                     tag, (t[0] - t0) * 1e3, *[(b_ - a_) * 1e3 for a_, b_ in zip(t[:-1], t[1:])]))
-        e2e = {"value": frames / dt, "unit": "frames/s", "h2d_bytes_per_step": int(4 * frames * m),
+        return {"value": frames / dt, "unit": "frames/s", "h2d_bytes_per_step": int(4 * frames * m),
                "d2h_bytes_per_step": int(9 * frames * m), "ms_per_step": dt * 1e3, "clips_in_flight": nwork,
                "clips_timed": nwork * nclips_each, "serial_ms_per_step": dt_serial * 1e3, "serial_value": frames / dt_serial,
                "handles_agree": same,
                "what": "pinned float32 D in; float32 L, S and uint8 mask out (bsub_load_D_f32_host, bsub_run, bsub_download_f32 x2, "
                        "bsub_mask_host), %d clips in flight, one solver handle + host thread + stream each" % nwork}
+
+    if not args.no_e2e and world == 1:
+        # pinned host buffers (5.6 GB per clip in flight) and one solver handle (~18.5 GB of HBM) per clip: fall back to fewer
+        # clips in flight if the box cannot give that much
+        tried = []
+        for nw in dict.fromkeys([max(1, int(os.environ.get("BSUB_E2E_CLIPS", "4"))), 2, 1]):
+            try:
+                e2e = measure_e2e(nw)
+                break
+            except Exception as ex:
+                tried.append("%d clips in flight: %s" % (nw, str(ex)[:160]))
+                gc.collect()
+                torch.cuda.empty_cache()
+        if e2e is None:
+            e2e = {"value": None, "unit": "frames/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                   "what": "e2e failed: " + "; ".join(tried)}
+        elif tried:
+            e2e["fell_back_after"] = tried
     elif world > 1:
         e2e = {"value": None, "unit": "frames/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                "what": "not measured for N > 1"}
