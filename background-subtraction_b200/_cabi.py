@@ -81,6 +81,8 @@ SIGNATURES = {
     "bsub_prox_flat_groups_dev": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, c_int32_p, ctypes.c_double, vp]),
     "bsub_prox_graph3_dev": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_double,
                                             c_double_p, ctypes.c_int32, ctypes.c_double, c_int32_p, vp]),
+    "bsub_prox_center3_dev": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_double,
+                              c_float_p, ctypes.c_int32, ctypes.c_double, c_int32_p, vp]),
     "bsub_block_shrink_dev": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, c_uint8_p, c_int32_p, c_double_p,
                                              ctypes.c_double, ctypes.c_double, vp]),
     "bsub_gram_dev": (ctypes.c_int, [vp, vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, c_double_p, vp]),

@@ -731,7 +731,11 @@ def prox(G_S, lambda1, graph, num_threads=None, img_shape=None, max_sweeps=20000
     m, n = _shape_of(G_S)
     geo = detect_window_graph(graph, m, img_shape)
     if geo is None:
-        raise Exception("only the overlapping 3x3 all-windows graph of getGraphSPAMS_all_groups is implemented")
+        ctr = detect_center_windows(graph, m, img_shape)           # a per-frame graph of get_proximal_graph_group_centers
+        if ctr is None:
+            raise Exception("only the overlapping 3x3 all-windows graph of getGraphSPAMS_all_groups and the radius-1 "
+                            "centre-window graphs of get_proximal_graph_group_centers are implemented")
+        return _prox_center(G_S, lambda1, ctr[0], np.tile(ctr[1], (n, 1)), max_sweeps, tol, return_sweeps)
     rows, cols, eta = geo
     lib = C.load()
     u, ld = _to_device_f32(G_S, m, n)
@@ -745,9 +749,30 @@ def prox(G_S, lambda1, graph, num_threads=None, img_shape=None, max_sweeps=20000
     return (out, sw.value) if return_sweeps else out
 
 
+def _prox_center(G_S, lambda1, shape, eta_nm, max_sweeps=20000, tol=1e-7, return_sweeps=False):
+    """Centre-window graphs, one weight map per frame (eta_nm float32 [n][m]); all frames in one launch."""
+    torch = _require_cuda()
+    m, n = _shape_of(G_S)
+    lib = C.load()
+    u, ld = _to_device_f32(G_S, m, n)
+    v = torch.zeros_like(u)
+    sw = ctypes.c_int32(0)
+    eta_nm = np.ascontiguousarray(eta_nm, dtype=np.float32)
+    C.check(lib.bsub_prox_center3_dev(ctypes.c_void_p(u.data_ptr()), ctypes.c_void_p(v.data_ptr()), ld, int(shape[0]), int(shape[1]), n,
+                                      float(lambda1), eta_nm.ctypes.data_as(C.c_float_p), int(max_sweeps),
+                                      float(tol) * float(lambda1), ctypes.byref(sw), _stream_ptr()))
+    out = _op_out(v, m, G_S)
+    return (out, sw.value) if return_sweeps else out
+
+
 def prox_by_frame(G_S, lambda1, graphs, img_shape=None):
-    """/root/reference/inexact_alm_lsd.py:60-68: one graph per column."""
-    cols = [prox(G_S[:, [f]], lambda1, graphs[f], img_shape=img_shape) for f in range(_shape_of(G_S)[1])]
+    """/root/reference/inexact_alm_lsd.py:60-68: one graph per column.  Centre-window graphs (the per-frame graphs the
+    reference builds) go through one launch for all frames; anything else frame by frame through prox()."""
+    m, n = _shape_of(G_S)
+    dets = [detect_center_windows(g, m, img_shape) if detect_window_graph(g, m, img_shape) is None else None for g in graphs]
+    if len(dets) == n and all(d is not None for d in dets) and len({d[0] for d in dets}) == 1:
+        return _prox_center(G_S, lambda1, dets[0][0], np.stack([d[1] for d in dets]))
+    cols = [prox(G_S[:, [f]], lambda1, graphs[f], img_shape=img_shape) for f in range(n)]
     return np.column_stack(cols)
 
 

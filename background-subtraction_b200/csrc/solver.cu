@@ -782,6 +782,27 @@ int bsub_prox_graph3_dev(const float* U, float* V, int64_t ld, int32_t rows, int
     return rc;
 }
 
+int bsub_prox_center3_dev(const float* U, float* V, int64_t ld, int32_t rows, int32_t cols, int32_t n, double lambda1,
+                          const float* eta_host, int32_t max_sweeps, double tol, int32_t* sweeps_used, void* stream) {
+    if (!U || !V || !eta_host || (long long)rows * cols > ld) { set_error("bsub_prox_center3_dev: bad argument"); return -1; }
+    cudaStream_t st = as_stream(stream);
+    const long long m = (long long)rows * cols;
+    float *xi = nullptr, *tot = nullptr, *eta = nullptr; int* sw = nullptr;
+    CK(cudaMalloc((void**)&xi, sizeof(float) * (size_t)n * m * 9));          // one candidate window per pixel and frame
+    CK(cudaMalloc((void**)&tot, sizeof(float) * (size_t)n * ld));
+    CK(cudaMalloc((void**)&eta, sizeof(float) * (size_t)n * m));
+    CK(cudaMalloc((void**)&sw, sizeof(int) * 4));
+    CK(cudaMemcpy(eta, eta_host, sizeof(float) * (size_t)n * m, cudaMemcpyHostToDevice));
+    int rc = launch_prox_graph3(U, V, xi, tot, eta, ld, rows, cols, n, (float)lambda1, max_sweeps > 0 ? max_sweeps : 4000, (float)tol, sw,
+                                nullptr, st, 1, m);
+    int sw_h = 0;
+    if (rc == 0 && cudaMemcpyAsync(&sw_h, sw, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
+    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_prox_center3_dev: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    if (sweeps_used) *sweeps_used = sw_h;
+    cudaFree(xi); cudaFree(tot); cudaFree(eta); cudaFree(sw);
+    return rc;
+}
+
 int bsub_block_shrink_dev(const float* G, float* R, int64_t ld, int64_t m, int32_t n, const uint8_t* labels, const int32_t* lam_ptr,
                           const double* lam, double mu, double non_block_lambda, void* stream) {
     if (!G || !R || !labels || !lam_ptr || ld < m) { set_error("bsub_block_shrink_dev: bad argument"); return -1; }

@@ -158,6 +158,11 @@ int bsub_prox_flat_groups_dev(const float* U, float* V, int64_t ld, int64_t m, i
 /* prox(G_S, lambda1, graph) on the overlapping 3x3 windows   inexact_alm_lsd.py:49-57 */
 int bsub_prox_graph3_dev(const float* U, float* V, int64_t ld, int32_t rows, int32_t cols, int32_t n, double lambda1,
                          const double* eta_host, int32_t max_sweeps, double tol, int32_t* sweeps_used, void* stream);
+/* prox_by_frame(G_S, lambda1, graphs) with the per-frame centre-window graphs of get_proximal_graph_group_centers
+ * (inexact_alm_lsd.py:60-68, lsd_improvement.py:74-120): eta_host float32[n][rows*cols] = weight of the 3x3 window centred on
+ * that pixel of that frame (<= 0: no window) */
+int bsub_prox_center3_dev(const float* U, float* V, int64_t ld, int32_t rows, int32_t cols, int32_t n, double lambda1,
+                          const float* eta_host, int32_t max_sweeps, double tol, int32_t* sweeps_used, void* stream);
 /* block_shrinkage_operator(G, blocks_by_frame, lambdas_by_frame, mu, non_block_lambda)   group_sparse_RPCA.py:13-42 */
 int bsub_block_shrink_dev(const float* G, float* R, int64_t ld, int64_t m, int32_t n, const uint8_t* labels_host,
                           const int32_t* lam_ptr, const double* lam, double mu, double non_block_lambda, void* stream);

@@ -137,6 +137,32 @@ def test_prox_graph(B, shape):
         assert np.array_equal(out3[:, -1, :].astype(np.float32), U3[:, -1, :].astype(np.float32))
 
 
+def test_prox_by_frame_center_windows(B):
+    """prox_by_frame (inexact_alm_lsd.py:60-68) with the per-frame centre-window graphs of get_proximal_graph_group_centers
+    (lsd_improvement.py:74-120): weights 1 / 1.5, exact border clipping, pixels outside every window untouched."""
+    from oracle import alm_oracle as O
+    h, w, t = 18, 23, 4
+    rng = np.random.default_rng(9)
+    U = np.asfortranarray((rng.standard_normal((h * w, t)) * 0.05).astype(np.float32).astype(np.float64))
+    weights = [np.where(rng.random((h, w)) < 0.3, rng.choice([1.0, 1.5], (h, w)), -1.0) for _ in range(t)]
+    for wm in weights:
+        wm[0, 0], wm[-1, -1], wm[0, w // 2] = 1.5, 1.0, 1.0           # windows clipped at corners and an edge
+    graphs = [B.get_proximal_graph_group_centers((h, w), 1, wm) for wm in weights]
+    bare = [{k: v for k, v in g.items() if not k.startswith('_')} for g in graphs]      # as the reference would hand them over
+    gcs = [O.graph_group_centers((h, w), 1, wm) for wm in weights]
+    for lam in (0.004, 0.05):
+        ref = O.prox_by_frame(U, lam, gcs, tol=1e-12)
+        for gl in (graphs, bare):
+            out = B.prox_by_frame(U, lam, gl)
+            assert np.abs(out - ref).max() <= 2e-5 * max(np.abs(U).max(), lam)
+        one = B.prox(U[:, [1]], lam, bare[1])                           # single-graph entry point with a centre graph
+        assert np.abs(one - ref[:, [1]]).max() <= 2e-5 * max(np.abs(U).max(), lam)
+        for f in range(t):                                              # uncovered pixels: identity
+            cov = np.zeros(h * w, dtype=bool)
+            cov[gcs[f][1]] = True
+            assert np.array_equal(out[~cov, f].astype(np.float32), U[~cov, f].astype(np.float32))
+
+
 def test_prox_graph_golden(B, golden_cases):
     G = golden_cases["bs_G"][:, :4]
     graph = B.getGraphSPAMS_all_groups((32, 40), (3, 3))

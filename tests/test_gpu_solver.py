@@ -205,6 +205,45 @@ def test_batch_of_clips_in_flight(B):
         assert rel_fro(L1, L0) <= 1e-6 and rel_fro(S1, S0) <= 1e-6      # (the kernels are deterministic: in practice identical)
 
 
+def test_LSD_pipeline(B, watersurface_u8):
+    """LSD() (inexact_alm_lsd.py:203-235, row a15): in-place normalisation, mean subtraction, solve, mask, reshapes."""
+    from oracle import alm_oracle as O
+    cube0 = np.asfortranarray(watersurface_u8[40:72, 60:100, 0:16].astype(np.float64))
+    D, x_norm, mean = O.normalize_and_center(cube0)
+    groups = O.flat_groups_nonoverlap((32, 40), (3, 3))
+    Lr, Sr, itr, convr = O.inexact_alm_lsd(D, groups=groups)
+    mref = O.foreground_mask(D, Lr, Sr)
+    cube = cube0.copy(order='F')
+    S, S_mask, L, ImData1, ImMean, shape, it, conv = B.LSD(cube, 0, 15, 1, use_flat=True)
+    assert shape == (32, 40, 16) and S.shape == shape and S_mask.shape == shape and L.shape == shape
+    assert ImData1 is cube and np.array_equal(cube, x_norm)            # normalised in place like the reference (SURVEY Q17)
+    assert abs(ImMean - mean) <= 1e-15 and abs(it - itr) <= 1 and conv == convr
+    assert rel_fro(L.reshape(D.shape, order='F'), Lr) <= TOL_F and rel_fro(S.reshape(D.shape, order='F'), Sr) <= TOL_F
+    assert (S_mask.reshape(D.shape, order='F') == mref).mean() >= 0.999
+    # default (overlapping graph) branch on a smaller crop
+    cube2 = np.asfortranarray(watersurface_u8[50:74, 70:100, 0:10].astype(np.float64))
+    D2, _x2, _m2 = O.normalize_and_center(cube2)
+    Lg, Sg, itg, convg = O.inexact_alm_lsd(D2, graphs=O.graph_all_groups((24, 30), (3, 3)))
+    out = B.LSD(cube2.copy(order='F'), 0, 9, 1)
+    assert abs(out[6] - itg) <= 1 and out[7] == convg
+    assert rel_fro(out[2].reshape(D2.shape, order='F'), Lg) <= 1e-3 and rel_fro(out[0].reshape(D2.shape, order='F'), Sg) <= 1e-3
+
+
+def test_device_side_u8_preprocessing(B):
+    """bsub_load_u8_host: LSD()'s min-max normalisation and mean subtraction on the device (inexact_alm_lsd.py:211-225)."""
+    from background_subtraction_b200 import synth
+    from background_subtraction_b200 import _cabi as C
+    rows, cols, n = 24, 30, 12
+    video, _ = synth.make_clip(rows, cols, n, seed=3, n_rect=2)
+    ref = synth.preprocess_u8(video)                                     # float32 [n][m], computed in fp64 on the host
+    dec = B.Decomposition(B.make_config(rows * cols, n, C.PROX_FLAT_LINF, rows, cols))
+    lo, hi, mean_raw = dec.load_u8(video)
+    assert lo == float(video.min()) and hi == float(video.max())
+    assert abs(mean_raw - float(video.mean(dtype=np.float64))) <= 1e-9 * max(1.0, abs(mean_raw))
+    got = dec.device_tensor('D').cpu().numpy()
+    assert np.abs(got - ref).max() <= 2e-7
+
+
 def test_rpca_l1(B, watersurface_u8):
     from oracle import alm_oracle as O
     D, _x, _mean = O.normalize_and_center(watersurface_u8[:48, :60, :20])
