@@ -358,11 +358,21 @@ class Decomposition:
 
     def debug_info(self):
         """Which kernel paths this solver uses (TMA / streamed shrink / int8 tcgen05 Gram) and their tile shapes."""
-        out = (ctypes.c_int32 * 12)()
+        out = (ctypes.c_int32 * 16)()
         C.check(self.lib.bsub_debug_info(self.h, out))
         keys = ["use_tma", "use_stream", "use_i8", "stream_R", "stream_FC", "stream_NS", "gram_types", "gram_kc", "eig_cluster",
-                "tma_R", "tma_Cf", "ld"]
+                "tma_R", "tma_Cf", "ld", "use_proj", "proj_warps", "proj_depth"]
         return dict(zip(keys, [int(v) for v in out]))
+
+    def counters(self):
+        out = (ctypes.c_int64 * 8)()
+        C.check(self.lib.bsub_debug_counters(self.h, out))
+        keys = ["eig_fast_iters", "eig_p", "eig_fast_steps", "eig_gb_ppm", "gram_mode", "wq_saturated"]
+        return dict(zip(keys, [int(v) for v in out]))
+
+    def eig_fast_count(self):
+        """Iterations of the last solve whose eigenpairs came from the warm-started subspace path."""
+        return self.counters()["eig_fast_iters"]
 
     def log(self):
         buf = (C.IterLog * 512)()

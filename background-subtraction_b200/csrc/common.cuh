@@ -47,6 +47,10 @@ struct DevState {
     int gram_mode;          // 0: fp64 DMMA Gram from D,S,Y   1: int8 tcgen05 Gram from the slices
     int wq_saturated;       // the last shrink pass clipped a slice -> fall back to the DMMA Gram once
     int use_i8;             // configuration: int8 path enabled
+    // warm-started eigensolver (eig.cu): rows 0..eig_p-1 of Z hold orthonormal vectors of the previous iteration
+    int eig_p;
+    int eig_fast_iters;     // iterations of this solve that took the warm-started path
+    double eig_gb;          // last certificate: ||G - X theta X^T||_F * mu^2  (must be < 1)
 };
 
 struct IterLog {
@@ -74,6 +78,17 @@ struct HostMirror {
     } while (0)
 
 void set_error(const char* fmt, ...);
+
+// cudaFuncSetAttribute is per (function, device): remember per device whether a launcher has set its attributes
+// (a benign race between host threads only repeats an idempotent call)
+inline bool first_call_on_device(unsigned long long* seen) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (*seen & bit) return false;
+    *seen |= bit;
+    return true;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -48,6 +48,8 @@ struct EigArgs {
     double* Z;                 // [n][n]
     float* Vr; float* VC; int vstride;
     DevState* st;
+    int fast_ok;               // warm-started subspace path allowed (mode 1; BSUB_NO_EIG_FAST unset)
+    size_t smem_total;         // bytes of dynamic shared memory of this launch
 };
 
 __device__ __forceinline__ double ldcg_d(const double* p) { return __ldcg(p); }
@@ -142,6 +144,364 @@ __device__ void eig_control(const EigArgs& a, DevState* st, int K, double mu, do
         a.Vr[(size_t)f * a.vstride + k] = (float)z;
         a.VC[(size_t)f * a.vstride + k] = (float)(z * (1.0 - thresh / sig));
     }
+}
+
+// =====================================================================================================================
+// Warm-started fast path (mode 1).  The leading eigenpairs of G = W^T W change little between ALM iterations, and what
+// lies below them is a tight cluster ~ (1/mu)^2 that only has to be PROVEN smaller than the threshold.
+//   X <- eigenvectors of the previous iteration (p <= 16 columns).  Repeat: Y = G X (rows dealt to the CTAs of the
+//   cluster, result pushed into every CTA through distributed shared memory); Rayleigh-Ritz on span(X) (H = X^T Y,
+//   parallel Jacobi by one warp); residuals ||G x - theta x||; not converged -> X <- orth(Y) by a Cholesky QR of the
+//   rotated (hence nearly orthogonal) Y.
+// Certificate (Weyl): for any orthonormal X and theta >= 0, lambda_{p+1}(G) <= ||G - X diag(theta) X^T||_F =: gb.  With
+// gb < (1/mu)^2 no eigenvalue outside the p Ritz values can exceed the threshold, so svp is decided by the Ritz values
+// alone -- what the reference's rank logic (/root/reference/inexact_alm_lsd.py:133-145, utils.py:204-217) sees from a
+// full SVD.  Anything ambiguous (not converged in 8 steps, gb too large, a Ritz value within its error bound of the
+// threshold, Cholesky breakdown) returns 0 and the full tridiagonalisation runs instead.  Every CTA derives the same
+// decisions from bit-identical data, so the cluster barriers stay uniform.
+// =====================================================================================================================
+constexpr int EIG_PMAX = 16;
+
+struct EigFastLayout { int PM, RB, RG, NJ, JW, RBP; size_t doubles; };
+__host__ __device__ inline EigFastLayout eig_fast_layout(int n, int C) {
+    EigFastLayout L;
+    L.PM = (n <= 448) ? 16 : 8;
+    L.RB = (n + C - 1) / C;
+    L.RG = (L.RB + 31) / 32;
+    L.NJ = EIG_WARPS / L.RG; if (L.NJ < 1) L.NJ = 1;
+    L.JW = (n + L.NJ - 1) / L.NJ;
+    L.RBP = L.RG * 32;
+    size_t scratch = (size_t)L.NJ * L.PM * L.RBP;
+    const size_t s2 = (size_t)EIG_THREADS;                 // [nparts][PM][PM] = one double per thread
+    if (scratch < s2) scratch = s2;
+    L.doubles = (size_t)2 * n * L.PM + scratch + (size_t)5 * L.PM * L.PM + (size_t)6 * L.PM + 16 + 8 + 64;
+    return L;
+}
+
+// Y rows of this CTA = G[rows, :] X, pushed into Ys of every CTA.  Thread = (row, column chunk): G is symmetric, so the
+// lanes of a warp read G[j][i .. i+31] (coalesced) and X[j][0..p) is a shared-memory broadcast.
+__device__ void eig_fast_matvec(const EigArgs& a, const EigFastLayout& L, int p, const double* Xs, double* Ys, double* Pp,
+                                cg::cluster_group& cluster) {
+    const int n = a.n, C = a.C, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, PM = L.PM;
+    const int row0 = c * L.RB, nrows = max(0, min(n, row0 + L.RB) - row0);
+    const int rg = warp % L.RG, jc = warp / L.RG, rl = rg * 32 + lane, i = row0 + rl;
+    if (jc < L.NJ) {
+        double acc[EIG_PMAX];
+#pragma unroll
+        for (int k = 0; k < EIG_PMAX; ++k) acc[k] = 0.0;
+        if (rl < nrows) {
+            const int j1 = min(n, (jc + 1) * L.JW);
+            for (int j = jc * L.JW; j < j1; ++j) {
+                const double g = __ldg(a.G + (size_t)j * a.npad + i);
+                const double* xr = Xs + (size_t)j * PM;
+#pragma unroll
+                for (int k = 0; k < EIG_PMAX; k += 2)
+                    if (k < p) {
+                        const double2 x2 = *reinterpret_cast<const double2*>(xr + k);
+                        acc[k] = fma(g, x2.x, acc[k]); acc[k + 1] = fma(g, x2.y, acc[k + 1]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < EIG_PMAX; ++k) if (k < p) Pp[((size_t)jc * PM + k) * L.RBP + rl] = acc[k];
+    }
+    __syncthreads();
+    cluster.sync();                                   // every CTA has finished reading the previous Ys
+    for (int item = tid; item < p * L.RBP; item += EIG_THREADS) {
+        const int k = item / L.RBP, r2 = item - k * L.RBP;
+        if (r2 < nrows) {
+            double y = 0.0;
+            for (int q = 0; q < L.NJ; ++q) y += Pp[((size_t)q * PM + k) * L.RBP + r2];
+            for (int q = 0; q < C; ++q) cluster.map_shared_rank(Ys, q)[(size_t)(row0 + r2) * PM + k] = y;
+        }
+    }
+    cluster.sync();                                   // Ys complete in every CTA
+}
+
+// out[a][b] = sum_i A[i][a] B[i][b]  (p x p, computed redundantly by every CTA); scratch: one double per thread
+__device__ void eig_fast_gram(int n, int PM, int p, const double* A, const double* B, double* out, double* scratch, bool symmetrise) {
+    const int tid = threadIdx.x, pairs = PM * PM, nparts = EIG_THREADS / pairs, part = tid / pairs, pr = tid - part * pairs;
+    const int ia = pr / PM, ib = pr - ia * PM;
+    double acc = 0.0;
+    if (ia < p && ib < p) for (int i = part; i < n; i += nparts) acc = fma(A[(size_t)i * PM + ia], B[(size_t)i * PM + ib], acc);
+    scratch[tid] = acc;
+    __syncthreads();
+    double t = 0.0;
+    if (tid < pairs) for (int q = 0; q < nparts; ++q) t += scratch[(size_t)q * pairs + tid];
+    __syncthreads();
+    if (tid < pairs) out[tid] = t;
+    __syncthreads();
+    if (symmetrise) {
+        double v = 0.0;
+        if (tid < pairs) { const int r = tid / PM, cc = tid - r * PM; v = 0.5 * (out[r * PM + cc] + out[cc * PM + r]); }
+        __syncthreads();
+        if (tid < pairs) out[tid] = v;
+        __syncthreads();
+    }
+}
+
+// Symmetric p x p eigenproblem by ONE warp: parallel (round-robin) Jacobi.  H is destroyed (its diagonal holds the
+// eigenvalues), W = eigenvectors (columns); both then sorted in descending order through `tmp`.
+__device__ void eig_fast_jacobi(int PM, int p, double* H, double* W, double* th, double* tmp, double* cs) {
+    const int lane = threadIdx.x & 31;
+    for (int idx = lane; idx < PM * PM; idx += 32) W[idx] = ((idx / PM) == (idx % PM)) ? 1.0 : 0.0;
+    __syncwarp();
+    const int pp = p + (p & 1), half = pp / 2;
+    for (int sweep = 0; sweep < 24 && pp >= 2; ++sweep) {
+        int rotated = 0;
+        for (int round = 0; round < pp - 1; ++round) {
+            if (lane < half) {
+                const int ia = (lane == 0) ? pp - 1 : (round + lane) % (pp - 1);
+                const int ib = (round + pp - 1 - lane) % (pp - 1);
+                double cth = 1.0, sth = 0.0;
+                if (ia < p && ib < p) {
+                    const double apq = H[ia * PM + ib], app = H[ia * PM + ia], aqq = H[ib * PM + ib];
+                    if (fabs(apq) > 0.25 * DBL_EPSILON * sqrt(fabs(app * aqq)) && fabs(apq) > DBL_MIN) {
+                        const double theta = (aqq - app) / (2.0 * apq);
+                        const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                        cth = 1.0 / sqrt(fma(t, t, 1.0)); sth = t * cth;
+                        rotated = 1;
+                    }
+                }
+                cs[4 * lane] = cth; cs[4 * lane + 1] = sth; cs[4 * lane + 2] = (double)ia; cs[4 * lane + 3] = (double)ib;
+            }
+            __syncwarp();
+            // columns a, b of H and of W:  (M[k][a], M[k][b]) <- (c M[k][a] - s M[k][b], s M[k][a] + c M[k][b])
+            for (int item = lane; item < half * p; item += 32) {
+                const int q = item / p, k = item - q * p;
+                const double cth = cs[4 * q], sth = cs[4 * q + 1];
+                const int ia = (int)cs[4 * q + 2], ib = (int)cs[4 * q + 3];
+                if (sth != 0.0) {
+                    const double ha = H[k * PM + ia], hb = H[k * PM + ib];
+                    H[k * PM + ia] = cth * ha - sth * hb; H[k * PM + ib] = sth * ha + cth * hb;
+                    const double wa = W[k * PM + ia], wb = W[k * PM + ib];
+                    W[k * PM + ia] = cth * wa - sth * wb; W[k * PM + ib] = sth * wa + cth * wb;
+                }
+            }
+            __syncwarp();
+            // rows a, b of H
+            for (int item = lane; item < half * p; item += 32) {
+                const int q = item / p, k = item - q * p;
+                const double cth = cs[4 * q], sth = cs[4 * q + 1];
+                const int ia = (int)cs[4 * q + 2], ib = (int)cs[4 * q + 3];
+                if (sth != 0.0) {
+                    const double ha = H[ia * PM + k], hb = H[ib * PM + k];
+                    H[ia * PM + k] = cth * ha - sth * hb; H[ib * PM + k] = sth * ha + cth * hb;
+                }
+            }
+            __syncwarp();
+        }
+        if (!__any_sync(0xffffffffu, rotated)) break;
+    }
+    if (lane < p) {                                    // sort descending (rank by counting)
+        const double v = H[lane * PM + lane];
+        int rank = 0;
+        for (int j = 0; j < p; ++j) { const double u = H[j * PM + j]; rank += (u > v) || (u == v && j < lane); }
+        th[rank] = v;
+        for (int k = 0; k < p; ++k) tmp[k * PM + rank] = W[k * PM + lane];
+    }
+    __syncwarp();
+    for (int idx = lane; idx < PM * PM; idx += 32) { const int r = idx / PM, cc = idx - r * PM; if (r < p && cc < p) W[idx] = tmp[idx]; }
+    __syncwarp();
+}
+
+// rows of M (n x p, row stride PM) <- row * W   (one thread per row)
+__device__ void eig_fast_rotate(int n, int PM, int p, double* M, const double* W) {
+    for (int i = threadIdx.x; i < n; i += EIG_THREADS) {
+        double x[EIG_PMAX], y[EIG_PMAX];
+#pragma unroll
+        for (int k = 0; k < EIG_PMAX; ++k) { x[k] = (k < p) ? M[(size_t)i * PM + k] : 0.0; y[k] = 0.0; }
+#pragma unroll
+        for (int aa = 0; aa < EIG_PMAX; ++aa)
+            if (aa < p) {
+#pragma unroll
+                for (int k = 0; k < EIG_PMAX; ++k) if (k < p) y[k] = fma(x[aa], W[aa * PM + k], y[k]);
+            }
+#pragma unroll
+        for (int k = 0; k < EIG_PMAX; ++k) if (k < p) M[(size_t)i * PM + k] = y[k];
+    }
+}
+
+// returns 1: CTA 0 has written lam[0..K) and Z[0..p), *p_out = p (all CTAs return 1); 0: nothing written -> full path
+__device__ int eig_fast_path(const EigArgs& a, DevState* st, int K, double mu, double* esm, int* p_out, cg::cluster_group& cluster) {
+    const int n = a.n, C = a.C, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const EigFastLayout L = eig_fast_layout(n, C);
+    const int PM = L.PM;
+    const int p = st->eig_p;
+    if (!a.fast_ok || p < 1 || n < 32 || 4 * p > n || p > PM || K < 1) return 0;
+    if (L.doubles * sizeof(double) > a.smem_total) return 0;
+    const double tau = 1.0 / (mu * mu);
+
+    size_t scratch_d = (size_t)L.NJ * PM * L.RBP;
+    if (scratch_d < (size_t)EIG_THREADS) scratch_d = EIG_THREADS;
+    double* Xs = esm;                                   // [n][PM]
+    double* Ys = Xs + (size_t)n * PM;                   // [n][PM]
+    double* Pp = Ys + (size_t)n * PM;                   // [NJ][PM][RBP] partial products / scratch of the small reductions
+    double* Hs = Pp + scratch_d;                        // [PM][PM]
+    double* Bs = Hs + PM * PM;
+    double* Ws = Bs + PM * PM;
+    double* Ts = Ws + PM * PM;
+    double* Rs = Ts + PM * PM;                          // Cholesky factor
+    double* th = Rs + PM * PM;                          // [PM]
+    double* res = th + PM;                              // [PM]
+    double* cs = res + PM;                              // [4 * PM]
+    double* gbp = cs + 4 * PM;                          // [16] per-CTA partials of gb^2
+    double* flag = gbp + 16;                            // [8]
+    double* red = flag + 8;                             // [64]
+
+    for (int idx = tid; idx < n * PM; idx += EIG_THREADS) {
+        const int i = idx / PM, k = idx - i * PM;
+        Xs[idx] = (k < p) ? a.Z[(size_t)k * n + i] : 0.0;
+    }
+    __syncthreads();
+
+    const int max_steps = 8;
+    int converged = 0, steps = 0;
+    for (int step = 0; step < max_steps; ++step) {
+        steps = step + 1;
+        eig_fast_matvec(a, L, p, Xs, Ys, Pp, cluster);
+        eig_fast_gram(n, PM, p, Xs, Ys, Hs, Pp, true);          // H = X^T G X
+        eig_fast_gram(n, PM, p, Ys, Ys, Bs, Pp, true);          // B = Y^T Y
+        if (warp == 0) eig_fast_jacobi(PM, p, Hs, Ws, th, Ts, cs);
+        __syncthreads();
+        eig_fast_rotate(n, PM, p, Xs, Ws);                      // Ritz vectors X W, and G (X W) = Y W
+        eig_fast_rotate(n, PM, p, Ys, Ws);
+        // B' = W^T B W (Gram of the rotated Y):  Ts = B W, then Bs = W^T Ts
+        if (tid < PM * PM) {
+            const int r = tid / PM, cc = tid - r * PM;
+            double t = 0.0;
+            if (r < p && cc < p) for (int d = 0; d < p; ++d) t = fma(Bs[r * PM + d], Ws[d * PM + cc], t);
+            Ts[tid] = t;
+        }
+        __syncthreads();
+        if (tid < PM * PM) {
+            const int r = tid / PM, cc = tid - r * PM;
+            double t = 0.0;
+            if (r < p && cc < p) for (int d = 0; d < p; ++d) t = fma(Ws[d * PM + r], Ts[d * PM + cc], t);
+            Bs[tid] = t;
+        }
+        {   // residuals r_k = || Y_k - theta_k X_k ||
+            const int k = tid % PM, part = tid / PM, nparts = EIG_THREADS / PM;
+            double acc = 0.0;
+            if (k < p) {
+                const double t = th[k];
+                for (int i = part; i < n; i += nparts) { const double d = fma(-t, Xs[(size_t)i * PM + k], Ys[(size_t)i * PM + k]); acc = fma(d, d, acc); }
+            }
+            Pp[tid] = acc;                                      // [part][PM]
+        }
+        __syncthreads();
+        if (tid < PM) {
+            double t = 0.0;
+            const int nparts = EIG_THREADS / PM;
+            for (int q = 0; q < nparts; ++q) t += Pp[(size_t)q * PM + tid];
+            res[tid] = sqrt(t);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int ok = (th[0] > 0.0) ? 1 : 0;
+            for (int k = 0; k < p; ++k) {
+                if (!(th[k] == th[k])) ok = 0;                                      // NaN
+                if (th[k] > 0.5 * tau && !(res[k] <= 1e-13 * th[0])) ok = 0;       // every pair that may be kept must have converged
+            }
+            flag[0] = (double)ok;
+        }
+        __syncthreads();
+        if (flag[0] != 0.0) { converged = 1; break; }
+        if (step == max_steps - 1) break;
+        // X <- orth(Y) by Cholesky QR: B' = R^T R, X = Y R^{-1}
+        if (warp == 0) {
+            int bad = 0;
+            for (int idx = lane; idx < PM * PM; idx += 32) Rs[idx] = Bs[idx];
+            __syncwarp();
+            for (int j = 0; j < p; ++j) {
+                const double d2 = Rs[j * PM + j];
+                if (!(d2 > 0.0)) { bad = 1; break; }                                // uniform over the warp
+                const double d = sqrt(d2), inv = 1.0 / d;
+                __syncwarp();
+                if (lane > j && lane < p) Rs[j * PM + lane] *= inv;
+                if (lane == j) Rs[j * PM + j] = d;
+                __syncwarp();
+                const int m2 = p - 1 - j;                                           // trailing block, upper triangle incl. diagonal
+                for (int item = lane; item < m2 * m2; item += 32) {
+                    const int r = j + 1 + item / m2, cc = j + 1 + item % m2;
+                    if (cc >= r) Rs[r * PM + cc] = fma(-Rs[j * PM + r], Rs[j * PM + cc], Rs[r * PM + cc]);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) flag[1] = (double)bad;
+        }
+        __syncthreads();
+        if (flag[1] != 0.0) return 0;
+        for (int i = tid; i < n; i += EIG_THREADS) {
+            double x[EIG_PMAX];
+#pragma unroll
+            for (int k = 0; k < EIG_PMAX; ++k) {
+                x[k] = 0.0;
+                if (k < p) {
+                    double v = Ys[(size_t)i * PM + k];
+#pragma unroll
+                    for (int aa = 0; aa < EIG_PMAX; ++aa) if (aa < k) v = fma(-x[aa], Rs[aa * PM + k], v);
+                    x[k] = v / Rs[k * PM + k];
+                    Xs[(size_t)i * PM + k] = x[k];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (!converged) return 0;
+
+    // ---- certificate: gb = || G - X diag(theta) X^T ||_F (rows dealt as in the matvec) and the orthonormality defect of X
+    {
+        const int row0 = c * L.RB, nrows = max(0, min(n, row0 + L.RB) - row0);
+        const int rg = warp % L.RG, jc = warp / L.RG, rl = rg * 32 + lane, i = row0 + rl;
+        double acc = 0.0;
+        if (jc < L.NJ && rl < nrows) {
+            double xt[EIG_PMAX];
+#pragma unroll
+            for (int k = 0; k < EIG_PMAX; ++k) xt[k] = (k < p && th[k] > 0.0) ? th[k] * Xs[(size_t)i * PM + k] : 0.0;
+            const int j1 = min(n, (jc + 1) * L.JW);
+            for (int j = jc * L.JW; j < j1; ++j) {
+                double g = __ldg(a.G + (size_t)j * a.npad + i);
+                const double* xr = Xs + (size_t)j * PM;
+#pragma unroll
+                for (int k = 0; k < EIG_PMAX; ++k) if (k < p) g = fma(-xt[k], xr[k], g);
+                acc = fma(g, g, acc);
+            }
+        }
+        acc = block_sum(acc, red);                               // valid in thread 0
+        if (tid == 0) for (int q = 0; q < C; ++q) cluster.map_shared_rank(gbp, q)[c] = acc;
+        cluster.sync();
+    }
+    eig_fast_gram(n, PM, p, Xs, Xs, Ts, Pp, false);              // X^T X
+    if (tid == 0) {
+        double gb2 = 0.0;
+        for (int q = 0; q < C; ++q) gb2 += gbp[q];
+        const double gb = sqrt(gb2);
+        double orth = 0.0;
+        for (int r = 0; r < p; ++r)
+            for (int cc = 0; cc < p; ++cc) orth = fmax(orth, fabs(Ts[r * PM + cc] - (r == cc ? 1.0 : 0.0)));
+        const double slack = (8.0 * n * DBL_EPSILON + 2.0 * orth) * th[0];
+        int ok = (gb * (1.0 + 1e-6) + slack < tau) && (gb == gb);
+        for (int k = 0; k < p; ++k) {
+            if (th[k] > 0.5 * tau) { if (fabs(th[k] - tau) <= fmax(4.0 * res[k], 1e-13 * th[0])) ok = 0; }   // knife edge: let the full path decide
+            else if (!(th[k] + gb + slack < tau)) ok = 0;                                                    // unconverged pair must be certainly below
+        }
+        flag[2] = (double)ok;
+        if (c == 0) { st->eig_info = steps | (ok ? 0x100 : 0); st->eig_gb = gb / tau; }
+    }
+    __syncthreads();
+    if (flag[2] == 0.0) return 0;
+    if (c == 0) {
+        for (int k = tid; k < K; k += EIG_THREADS) a.lam[k] = (k < p) ? th[k] : 0.0;     // everything else is certified below the threshold
+        for (int idx = tid; idx < n * p; idx += EIG_THREADS) {
+            const int k = idx / n, i = idx - k * n;
+            a.Z[(size_t)k * n + i] = Xs[(size_t)i * PM + k];
+        }
+        __threadfence_block();
+    }
+    __syncthreads();
+    *p_out = p;
+    return 1;
 }
 
 // ---- back-transformation z <- H_0 H_1 ... H_{n-3} z of the tridiagonal eigenvectors, one warp per vector.  The vector
@@ -386,7 +746,17 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
         // W_1 = fma(Y0, 1/mu, D) with Y0 = D / dual_norm  ->  G_1 = c^2 Gram(D)
         const double cc = 1.0 + (1.0 / st->dual_norm) * (double)(float)(1.0 / mu);
         eig_control(a, st, K, mu, cc * cc, red, bc);
+        if (tid == 0) st->eig_p = max(1, min(st->eig_p, st->svp + 2));
         return;
+    }
+    if (a.mode == 1) {
+        int pf = 0;
+        if (eig_fast_path(a, st, K, mu, esm, &pf, cluster)) {
+            if (c != 0) return;
+            eig_control(a, st, K, mu, 1.0, red, bc);
+            if (tid == 0) { st->eig_p = max(1, min(pf, st->svp + 2)); st->eig_fast_iters += 1; }
+            return;
+        }
     }
     if (c == 0 && tid == 0) st->eig_clk[0] = clock64();
     // ---- load my rows -------------------------------------------------------------------------------------
@@ -707,6 +1077,12 @@ __global__ void __launch_bounds__(EIG_THREADS, 1) eig_kernel(EigArgs a) {
 
     if (tid == 0) st->eig_clk[5] = clock64();
     eig_control(a, st, K, mu, 1.0, red, bc);
+    // warm start of the next call: the kept vectors plus two guards (rows 0..eig_p-1 of Z)
+    if (tid == 0 && a.mode != 2) {
+        const int pcap = min(K, eig_fast_layout(n, C).PM);
+        st->eig_p = (a.mode == 0) ? pcap : max(1, min(pcap, st->svp + 2));
+        if (a.mode == 0) st->eig_fast_iters = 0;
+    }
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -742,11 +1118,10 @@ EigPlan make_eig_plan(int n, int npad) {
 
 int launch_eig(const EigPlan& p, const double* G, const double* comm_max, EigBuffers b, DevState* st, int mode,
                int k_override, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0;      // one bit per device: the attribute is per (function, device)
+    if (first_call_on_device(&attr_devs)) {
         BSUB_CUDA_CHECK(cudaFuncSetAttribute(eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
         BSUB_CUDA_CHECK(cudaFuncSetAttribute(eig_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        attr_set = true;
     }
     if (p.smem_bytes > 225 * 1024) { set_error("eig: n=%d needs %zu B of shared memory", p.n, p.smem_bytes); return -1; }
     EigArgs a;
@@ -763,6 +1138,8 @@ int launch_eig(const EigPlan& p, const double* G, const double* comm_max, EigBuf
     a.dotbuf = w; w += 32;
     a.iw_smem_doubles = (p.smem_bytes / sizeof(double)) - (2 * (size_t)p.n + 64) - (3 * (size_t)p.n + 4 * EIG_THREADS + EIG_THREADS / 2);
     a.lam = b.lam; a.Z = b.Z; a.Vr = b.Vr; a.VC = b.VC; a.vstride = b.vstride; a.st = st;
+    a.fast_ok = (mode == 1 && getenv("BSUB_NO_EIG_FAST") == nullptr) ? 1 : 0;
+    a.smem_total = p.smem_bytes;
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.C); cfg.blockDim = dim3(EIG_THREADS); cfg.dynamicSmemBytes = p.smem_bytes; cfg.stream = stream;

@@ -230,10 +230,9 @@ int make_gram_maps(const GramPlan& p, const float* D, const float* S, const floa
 
 int launch_gram(const GramPlan& p, const GramMaps& maps, bool combo, const int2* dev_tasks, const DevState* st,
                 float inv_mu_override, double* partial, double* G, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0;      // one bit per device: the attribute is per (function, device)
+    if (first_call_on_device(&attr_devs)) {
         BSUB_CUDA_CHECK(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM_CAP));
-        attr_set = true;
     }
     if (p.smem_bytes > GR_SMEM_CAP) { set_error("gram: n=%d too large for the shared-memory tiles", p.n); return -1; }
     if (combo && maps.narr != 3) { set_error("gram: S/Y tensor maps missing"); return -1; }

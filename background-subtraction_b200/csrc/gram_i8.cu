@@ -549,10 +549,9 @@ int make_gram_i8_map(const GramI8Plan& p, const signed char* Wq, CUtensorMap* ma
 int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const CUtensorMap& map_last, const int4* cta_info_dev, int ncta, const int* blk_n_dev,
                    unsigned long long* Gint, double* G, int npad, const DevState* st, double scale_override, int require_mode,
                    cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0;      // one bit per device: the attribute is per (function, device)
+    if (first_call_on_device(&attr_devs)) {
         BSUB_CUDA_CHECK(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
-        attr_set = true;
     }
     const size_t gbytes = sizeof(unsigned long long) * (size_t)p.nblk * 128 * p.nblk * 128;
     BSUB_CUDA_CHECK(cudaMemsetAsync(Gint, 0, gbytes, stream));

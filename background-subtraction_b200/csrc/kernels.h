@@ -78,6 +78,8 @@ struct ShrinkBuffers {
     float* part_max;
     float* part_wmax;          // [stream grid] max |W_next| written with the int8 slices (nullptr: slices off)
     int implied_first = 0;     // shrink_stream only: iteration 1 derives S0 = 0, Y0 = D / dual_norm from D (init_Y skipped)
+    const float* Tt = nullptr; // shrink_stream only: T regrouped per tile by project.cu; when the planes of this W exist
+                               // (DevState::gram_mode == 1) the kernel skips its own projection pass and streams every tile once
 };
 int launch_shrink(const ShrinkPlan& p, ShrinkBuffers b, const DevState* st, int mode, cudaStream_t stream);
 
@@ -109,6 +111,13 @@ int make_shrink_stream_qmap(const ShrinkStreamPlan& p, signed char* Wq, ShrinkTm
 int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, ShrinkBuffers b, const DevState* st, int mode,
                          cudaStream_t stream);
 
+// ---------------------------------------------------------------- project.cu (T = Vr^T W from the int8 digit planes)
+struct ProjectPlan { int n, NW, DEPTH, slot_bytes, grid; long long ldq; size_t smem_bytes; };
+bool make_project_plan(int n, int R, long long ldq, int num_sms, ProjectPlan* out);
+// T: [kcap][ld] pixel order; Tt: [ntiles][16][4R] regrouped per tile / 3x3 group for shrink_stream's phase B
+int launch_project(const ProjectPlan& p, const signed char* Wq, const float* Vr, int vstride, float* T, long long ld, float* Tt, int rows,
+                   int cols, int R, int ntile_r, long long ntiles, int kcap, const DevState* st, cudaStream_t stream);
+
 // ---------------------------------------------------------------- elementwise.cu
 int launch_rowsum_max(const float* D, long long ld, long long m, int n, double* comm_max, cudaStream_t s);
 int launch_init_Y(const float* D, float* Y, float* S, long long ld, int n, const DevState* st, cudaStream_t s);
@@ -134,8 +143,10 @@ int launch_dual_update(const float* D, const float* Snew, float* S, float* Y, co
 // ---------------------------------------------------------------- mask.cu
 int launch_absmax(const float* S, long long ld, long long m, int n, double* out_max, cudaStream_t s);
 int launch_maxS_from_state(const DevState* st, double* out_max, cudaStream_t s);
+// scratch: mask_stats_scratch_doubles() doubles, zero before the first use (per-CTA partials + a ticket counter)
+size_t mask_stats_scratch_doubles();
 int launch_mask_stats(const float* D, const float* L, const float* S, long long ld, long long m, int n,
-                      const double* absmax, double* stats /*[3]: count, sum, sumsq*/, cudaStream_t s);
+                      const double* absmax, double* stats /*[3]: count, sum, sumsq*/, double* scratch, cudaStream_t s);
 int launch_mask_write(const float* S, long long ld, long long m, int n, const double* stats, double sigmas,
                       unsigned char* mask, long long mask_ld, cudaStream_t s);
 

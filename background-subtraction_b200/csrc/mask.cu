@@ -37,9 +37,12 @@ int launch_absmax(const float* S, long long ld, long long m, int n, double* out_
     return 0;
 }
 
+// Statistics in a fixed order (bit-reproducible threshold): every CTA writes its three fp64 partials, the last CTA to
+// finish (ticket counter) adds them up in CTA order and stores stats[0..2].  scratch: [3 * grid] doubles + one counter.
 __global__ void mask_stats_kernel(const float* __restrict__ D, const float* __restrict__ L, const float* __restrict__ S,
-                                  long long total4, const double* absmax, double* stats) {
+                                  long long total4, const double* absmax, double* stats, double* scratch) {
     __shared__ double red[32];
+    __shared__ int is_last;
     const float half_m = 0.5f * (float)absmax[0];
     double cnt = 0.0, sum = 0.0, sq = 0.0;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (long long)gridDim.x * blockDim.x) {
@@ -53,19 +56,39 @@ __global__ void mask_stats_kernel(const float* __restrict__ D, const float* __re
         }
         cnt += (double)c4; sum += s4; sq += q4;
     }
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + 3 * (size_t)gridDim.x);
     double a = block_sum(cnt, red);
-    if (threadIdx.x == 0) atomicAdd(stats + 0, a);
+    if (threadIdx.x == 0) scratch[3 * (size_t)blockIdx.x + 0] = a;
     double b = block_sum(sum, red);
-    if (threadIdx.x == 0) atomicAdd(stats + 1, b);
+    if (threadIdx.x == 0) scratch[3 * (size_t)blockIdx.x + 1] = b;
     double c = block_sum(sq, red);
-    if (threadIdx.x == 0) atomicAdd(stats + 2, c);
+    if (threadIdx.x == 0) {
+        scratch[3 * (size_t)blockIdx.x + 2] = c;
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+        t0 += __ldcg(scratch + 3 * (size_t)i); t1 += __ldcg(scratch + 3 * (size_t)i + 1); t2 += __ldcg(scratch + 3 * (size_t)i + 2);
+    }
+    t0 = block_sum(t0, red);
+    if (threadIdx.x == 0) stats[0] = t0;
+    t1 = block_sum(t1, red);
+    if (threadIdx.x == 0) stats[1] = t1;
+    t2 = block_sum(t2, red);
+    if (threadIdx.x == 0) { stats[2] = t2; *ticket = 0u; }
 }
 
+size_t mask_stats_scratch_doubles() { return (size_t)3 * 148 * 8 + 2; }
+
 int launch_mask_stats(const float* D, const float* L, const float* S, long long ld, long long m, int n, const double* absmax,
-                      double* stats, cudaStream_t s) {
+                      double* stats, double* scratch, cudaStream_t s) {
     (void)m;
     const long long total4 = ld * n / 4;   // pad columns: D = L = 0 -> Delta = 0 -> excluded
-    mask_stats_kernel<<<mk_grid(total4), MK_THREADS, 0, s>>>(D, L, S, total4, absmax, stats);
+    mask_stats_kernel<<<mk_grid(total4), MK_THREADS, 0, s>>>(D, L, S, total4, absmax, stats, scratch);
     BSUB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -373,10 +373,9 @@ ShrinkPlan make_shrink_plan(int n, int rows, int cols, long long ld, int num_sms
 }
 
 int launch_shrink(const ShrinkPlan& p, ShrinkBuffers b, const DevState* st, int mode, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0;      // one bit per device: the attribute is per (function, device)
+    if (first_call_on_device(&attr_devs)) {
         BSUB_CUDA_CHECK(cudaFuncSetAttribute(shrink_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
     }
     if (p.smem_bytes > 200 * 1024) { set_error("shrink: tile does not fit shared memory (n=%d)", p.n); return -1; }
     ShrinkArgs a;

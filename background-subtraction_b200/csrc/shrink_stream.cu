@@ -45,6 +45,7 @@ struct ShrinkStreamArgs {
     int Pq;                                // = P (a multiple of 16 when the slices are on): bytes per frame of a tile
     int kcap;                              // ranks <= kcap (= SS_KC) are handled here; larger ones by the fallback kernel
     int implied_first;                     // iteration 1 takes S = 0, Y = D / dual_norm from D instead of reading them (no init pass)
+    const float* Tt;                       // [ntiles][SS_KC][4R]: T of every tile from project.cu (nullptr: always project here)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -53,6 +54,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 #define SS_CE(i, j) { const float hi_ = fmaxf(u[i], u[j]), lo_ = fminf(u[i], u[j]); u[i] = hi_; u[j] = lo_; }
 // clip level of the l1-ball projection of 9 non-negative values (25-comparator sorting network, descending)
@@ -321,7 +326,7 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
         tma_prefetch_desc(&mapD); tma_prefetch_desc(&mapS); tma_prefetch_desc(&mapY); tma_prefetch_desc(&mapOut);
         tma_prefetch_desc(&mapVr); tma_prefetch_desc(&mapVC);
     }
-    for (int idx = threadIdx.x; idx < SS_KC * 4 * R; idx += blockDim.x) Tp[idx] = 0.f;   // rows >= svp stay zero
+    for (int idx = threadIdx.x; idx < SS_KC * 4 * R; idx += blockDim.x) { Tp[idx] = 0.f; if (NFL * SS_KRED * P >= SS_KC * 4 * R) scr[idx] = 0.f; }   // rows >= svp stay zero (scr: second T buffer)
     __syncthreads();
 
     auto tile_origin = [&](long long tl, int& j0, int& i0) {
@@ -329,7 +334,10 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
         j0 = 3 * tcx; i0 = trx * R;
     };
     const int ncf = a.nchunkf;                              // frame chunks per tile
-    const bool phaseA = r > 0;                              // rank 0: L = 0, no T needed
+    // T already projected from the digit planes of this W (project.cu ran just before): one pass per tile
+    const bool scr_ok = NFL * SS_KRED * P >= SS_KC * 4 * R;    // the reduction scratch doubles as the second T buffer
+    const bool proj = (a.Tt != nullptr) && scr_ok && (st->gram_mode == 1) && !first && r > 0;
+    const bool phaseA = r > 0 && !proj;                     // rank 0: L = 0, no T needed
     const int chunks_per_tile = (phaseA ? ncf : 0) + ncf;
 
     double zz_acc = 0.0;
@@ -403,9 +411,20 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
         const bool tact = fl < NFL;
         const int NG = R / 3, RQ = R / 4;
         long long q = 0;
+        // projected T of a tile: r rows of 4R floats, fetched with cp.async into one of two buffers (Tp, and the reduction
+        // scratch, which is idle in this mode) one tile ahead
+        const int tpieces = r * R;                          // 16-byte pieces (r rows x 4R floats)
+        auto fetch_T = [&](long long tile, float* dst) {
+            const float* src = a.Tt + (size_t)tile * SS_KC * (4 * R);
+            for (int pc = ct; pc < tpieces; pc += NTC) cp_async16(dst + 4 * pc, src + 4 * pc);
+        };
+        int tpar = 0;
+        if (proj && (long long)blockIdx.x < a.ntiles) { fetch_T(blockIdx.x, Tp); cp_async_wait_all(); named_bar_sync(1, NTC); }
         for (long long tl = blockIdx.x; tl < a.ntiles; tl += gridDim.x) {
             int j0, i0;
             tile_origin(tl, j0, i0);
+            const float* Tcur = (proj && tpar) ? scr : Tp;
+            if (proj && tl + gridDim.x < a.ntiles) fetch_T(tl + gridDim.x, tpar ? Tp : scr);
             if (phaseA) {
                 float acc[SS_KC][4];
 #pragma unroll
@@ -452,8 +471,9 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
                 }
             }
             // phase B
-            SS_DISPATCH_K(r, (ss_phase_b<K_, NTC>(a, ring, stage_floats, Tp, Vst, full, done, q, ct, lane, NG, R, P, FC, BS, QS, VSS, NS, ncf, wq, inv_mu,
+            SS_DISPATCH_K(r, (ss_phase_b<K_, NTC>(a, ring, stage_floats, Tcur, Vst, full, done, q, ct, lane, NG, R, P, FC, BS, QS, VSS, NS, ncf, wq, inv_mu,
                                                   mu_f, lamq, inv_mu_next, Qf, zz_acc, nnz_acc, max_acc, wmax_acc, sat_acc, first, inv_dual)));
+            if (proj) { cp_async_wait_all(); named_bar_sync(1, NTC); tpar ^= 1; }     // next tile's T has landed, this tile's buffer is free
         }
     }
     __syncthreads();
@@ -558,10 +578,9 @@ int make_shrink_stream_qmap(const ShrinkStreamPlan& p, signed char* Wq, ShrinkTm
 
 template <int NCW, int RT, int FCT>
 static int launch_ss(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, const ShrinkStreamArgs& a, int mode, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0;      // one bit per device: the attribute is per (function, device)
+    if (first_call_on_device(&attr_devs)) {
         BSUB_CUDA_CHECK(cudaFuncSetAttribute(shrink_stream_kernel<NCW, RT, FCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_SMEM_CAP));
-        attr_set = true;
     }
     const CUtensorMap& outmap = (mode == SHRINK_SPILL) ? maps.U : maps.S;
     shrink_stream_kernel<NCW, RT, FCT><<<p.grid, 32 * (NCW + 2), p.smem_bytes, stream>>>(maps.D, maps.S, maps.Y, outmap, maps.Q, maps.Vr,
@@ -579,6 +598,7 @@ int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, S
     a.nchunkf = p.nchunkf; a.ntile_r = p.ntile_r; a.ntiles = p.ntiles; a.st = st; a.part_zz = b.part_zz; a.part_nnz = b.part_nnz;
     a.part_max = b.part_max; a.part_wmax = b.part_wmax; a.mode = mode;
     a.wq = (maps.has_Q && b.part_wmax != nullptr) ? 1 : 0; a.Pq = p.P; a.implied_first = b.implied_first; a.kcap = p.kcap;
+    a.Tt = (mode != SHRINK_SPILL) ? b.Tt : nullptr;
     a.QS = (int)(((size_t)p.FC * p.P + 127) / 128 * 128);
     if (p.NCW == 16) return launch_ss<16, 0, 0>(p, maps, a, mode, stream);
     if (p.R == 48 && p.FC == 28) return launch_ss<8, 48, 28>(p, maps, a, mode, stream);

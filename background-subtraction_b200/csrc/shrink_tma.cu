@@ -450,10 +450,9 @@ int make_shrink_tma_maps(const ShrinkTmaPlan& p, const float* D, float* S, float
 
 template <int NT, int MINB>
 static int launch_st(const ShrinkTmaPlan& p, const ShrinkTmaMaps& maps, const ShrinkTmaArgs& a, int mode, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0;      // one bit per device: the attribute is per (function, device)
+    if (first_call_on_device(&attr_devs)) {
         BSUB_CUDA_CHECK(cudaFuncSetAttribute(shrink_tma_kernel<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM_CAP));
-        attr_set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.grid_clusters * p.Cf); cfg.blockDim = dim3(NT);

@@ -53,6 +53,8 @@ struct bsub_solver {
     // int8 tcgen05 Gram from the W slices written by the streamed shrink pass
     bool use_i8 = false; signed char* Wq = nullptr; unsigned long long* Gint = nullptr; GramI8Plan gip; CUtensorMap gimap, gimap_last;
     int4* gi_info = nullptr; int* gi_blkn = nullptr; int gi_ncta = 0; float* part_wmax = nullptr;
+    // T = Vr^T W from the digit planes (project.cu): lets the streamed shrink kernel read every tile once
+    bool use_proj = false; ProjectPlan pjp; float* Tt = nullptr;
     float* tpart = nullptr; double* part_zz = nullptr; unsigned long long* part_nnz = nullptr;
     float* part_max = nullptr;
     int shrink_mode = SHRINK_FLAT3;
@@ -63,6 +65,9 @@ struct bsub_solver {
     // l2 blocks
     unsigned char* labels_dev = nullptr; double* lam_table = nullptr; double* bsums = nullptr; int nlab = 0; bool blocks_set = false;
     unsigned char* mask_stage = nullptr;      // bsub_mask_host staging
+    double* mask_scratch = nullptr;           // per-CTA partials of the mask statistics (fixed-order reduction)
+    double* stage64 = nullptr; size_t stage64_doubles = 0;   // fp64 staging of bsub_load_D_f64_host / bsub_download_f64 (allocated once)
+    cudaStream_t last_stream = nullptr; bool stream_seen = false;
     bool implied_first = false;               // see bsub_step_init_finish
     bool loaded = false, finalized = false, initialised = false;
     cudaEvent_t ev[kRunAhead + 1];
@@ -70,6 +75,29 @@ struct bsub_solver {
 };
 
 static cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static cudaStream_t use_stream(bsub_solver* s, void* stream) {
+    s->last_stream = as_stream(stream); s->stream_seen = true;
+    return s->last_stream;
+}
+static int ensure_stage64(bsub_solver* s, size_t doubles) {
+    if (s->stage64_doubles >= doubles) return 0;
+    if (s->stage64) { cudaFree(s->stage64); s->stage64 = nullptr; s->stage64_doubles = 0; }
+    BSUB_CUDA_CHECK(cudaMalloc((void**)&s->stage64, sizeof(double) * doubles));
+    s->stage64_doubles = doubles;
+    return 0;
+}
+// frees whatever a stand-alone operator allocated, on every return path
+struct DevScope {
+    std::vector<void*> ptrs;
+    ~DevScope() { for (void* p : ptrs) if (p) cudaFree(p); }
+    template <typename T> int alloc(T** out, size_t bytes) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError())); return -1; }
+        ptrs.push_back(p);
+        *out = reinterpret_cast<T*>(p);
+        return 0;
+    }
+};
 
 static int round_half_even_005(int d) {
     // Python round(0.05 * d) -- banker's rounding on the double product
@@ -94,16 +122,21 @@ void bsub_default_config(bsub_config* c) {
 
 int bsub_destroy(bsub_solver* s) {
     if (!s) return 0;
-    cudaSetDevice(s->device);
-    cudaDeviceSynchronize();
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != s->device) cudaSetDevice(s->device);
+    // only this solver's work has to drain: a device-wide synchronise would stall the other clips in flight
+    if (s->stream_seen) cudaStreamSynchronize(s->last_stream); else cudaDeviceSynchronize();
     void* ptrs[] = {s->D, s->S, s->Y, s->T, s->L, s->U, s->st, s->log, s->comm_sum, s->comm_max, s->tasks_dev, s->gram_partial,
                     s->eb.work, s->eb.lam, s->eb.Z, s->eb.Vr, s->eb.VC, s->tpart, s->part_zz, s->part_nnz, s->part_max, s->gptr,
                     s->gidx, s->eta_dev, s->xi, s->tot, s->sweeps_dev, s->labels_dev, s->lam_table, s->bsums, s->Wq, s->Gint,
-                    s->gi_info, s->gi_blkn, s->part_wmax, s->mask_stage};
+                    s->gi_info, s->gi_blkn, s->part_wmax, s->mask_stage, s->mask_scratch, s->stage64, s->Tt};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->mirror) cudaFreeHost((void*)s->mirror);
     for (int i = 0; i <= kRunAhead; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    const int own = s->device;
     delete s;
+    if (cur != own) cudaSetDevice(cur);
     return 0;
 }
 
@@ -144,6 +177,8 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
         ALLOC(s->st, sizeof(DevState)); ALLOC(s->log, sizeof(IterLog) * kMaxIterLog);
         ALLOC(s->comm_sum, sizeof(double) * ((size_t)s->npad * s->npad + kCommTail));
         ALLOC(s->comm_max, sizeof(double) * 8);
+        ALLOC(s->mask_scratch, sizeof(double) * mask_stats_scratch_doubles());
+        cudaMemset(s->mask_scratch, 0, sizeof(double) * mask_stats_scratch_doubles());
         cudaMemset(s->comm_sum, 0, sizeof(double) * ((size_t)s->npad * s->npad + kCommTail));
         cudaMemset(s->comm_max, 0, sizeof(double) * 8);
         cudaMemset(s->log, 0, sizeof(IterLog) * kMaxIterLog);
@@ -207,6 +242,12 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
             cudaMemset(s->part_wmax, 0, sizeof(float) * s->ssp.grid);
             if (make_gram_i8_map(s->gip, s->Wq, &s->gimap, 128) != 0) { rc = -1; break; }
             if (make_gram_i8_map(s->gip, s->Wq, &s->gimap_last, gram_i8_last_block_n(s->gip)) != 0) { rc = -1; break; }
+            s->use_proj = (getenv("BSUB_NO_PROJ") == nullptr) && make_project_plan(s->n, s->ssp.R, ldq, s->num_sms, &s->pjp);
+            if (s->use_proj) {
+                const size_t tt = sizeof(float) * (size_t)s->ssp.ntiles * 16 * 4 * s->ssp.R;
+                ALLOC(s->Tt, tt);
+                cudaMemset(s->Tt, 0, tt);
+            }
         }
         for (int i = 0; i <= kRunAhead; ++i)
             if (cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming) != cudaSuccess) { set_error("bsub_create: event"); rc = -1; break; }
@@ -263,6 +304,7 @@ int bsub_set_flat_groups(bsub_solver* s, const int32_t* g) {
     CK(cudaMemcpy(s->gidx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
     s->ngroups = gmax;
     s->shrink_mode = SHRINK_SPILL;
+    s->implied_first = false;      // the two-phase path reads Y from HBM: init_Y must store Y0 = D / dual_norm
     s->stmaps_ready = false;
     const size_t mat = sizeof(float) * (size_t)s->ld * s->n;
     if (!s->U) { CK(cudaMalloc((void**)&s->U, mat)); CK(cudaMemset(s->U, 0, mat)); }
@@ -343,7 +385,7 @@ int bsub_load_D_f32_dev(bsub_solver* s, const float* D, int64_t ld, void* stream
 
 int bsub_load_D_f32_host(bsub_solver* s, const float* D, int64_t ld, void* stream) {
     if (!s || !D || ld < s->m) { set_error("bsub_load_D_f32_host: bad argument"); return -1; }
-    cudaStream_t st = as_stream(stream);
+    cudaStream_t st = use_stream(s, stream);
     if (s->ld != s->m) CK(cudaMemsetAsync(s->D, 0, sizeof(float) * (size_t)s->ld * s->n, st));
     if (ld == s->m && s->ld == s->m) CK(cudaMemcpyAsync(s->D, D, sizeof(float) * (size_t)s->m * s->n, cudaMemcpyHostToDevice, st));
     else CK(cudaMemcpy2DAsync(s->D, sizeof(float) * s->ld, D, sizeof(float) * ld, sizeof(float) * s->m, s->n, cudaMemcpyHostToDevice, st));
@@ -352,23 +394,37 @@ int bsub_load_D_f32_host(bsub_solver* s, const float* D, int64_t ld, void* strea
 
 int bsub_load_D_f64_host(bsub_solver* s, const double* D, int64_t ld, void* stream) {
     if (!s || !D || ld < s->m) { set_error("bsub_load_D_f64_host: bad argument"); return -1; }
-    cudaStream_t st = as_stream(stream);
-    // stage through the (not yet used) T buffer: it holds ld*n floats = ld*n/2 doubles -> two halves of the frames
-    double* stage = reinterpret_cast<double*>(s->T);
-    const long long cap_frames = std::max<long long>(1, ((long long)s->ld * s->n / 2) / s->m);
-    for (long long f0 = 0; f0 < s->n; f0 += cap_frames) {
-        const int nf = (int)std::min<long long>(cap_frames, s->n - f0);
-        CK(cudaMemcpy2DAsync(stage, sizeof(double) * s->m, D + (size_t)f0 * ld, sizeof(double) * ld, sizeof(double) * s->m, nf,
-                             cudaMemcpyHostToDevice, st));
-        RET_IF(launch_convert_f64(stage, s->m, s->D + (size_t)f0 * s->ld, s->ld, s->m, nf, st));
+    cudaStream_t st = use_stream(s, stream);
+    // narrow on the device through a staging buffer that is allocated once: two halves alternate so that the conversion
+    // of one batch overlaps the copy of the next; a batch is a whole number of frames, or a piece of one long frame
+    const size_t half = (size_t)4 << 20;                       // doubles per half (32 MB)
+    RET_IF(ensure_stage64(s, 2 * half));
+    if (s->ld != s->m) CK(cudaMemsetAsync(s->D, 0, sizeof(float) * (size_t)s->ld * s->n, st));
+    int flip = 0;
+    if ((size_t)s->m <= half) {
+        const long long cap_frames = (long long)(half / (size_t)s->m);
+        for (long long f0 = 0; f0 < s->n; f0 += cap_frames, flip ^= 1) {
+            const int nf = (int)std::min<long long>(cap_frames, s->n - f0);
+            double* stage = s->stage64 + (size_t)flip * half;
+            CK(cudaMemcpy2DAsync(stage, sizeof(double) * s->m, D + (size_t)f0 * ld, sizeof(double) * ld, sizeof(double) * s->m, nf,
+                                 cudaMemcpyHostToDevice, st));
+            RET_IF(launch_convert_f64(stage, s->m, s->D + (size_t)f0 * s->ld, s->ld, s->m, nf, st));
+        }
+    } else {
+        for (long long f = 0; f < s->n; ++f)
+            for (long long p0 = 0; p0 < s->m; p0 += (long long)half, flip ^= 1) {
+                const long long np = std::min<long long>((long long)half, s->m - p0);
+                double* stage = s->stage64 + (size_t)flip * half;
+                CK(cudaMemcpyAsync(stage, D + (size_t)f * ld + p0, sizeof(double) * np, cudaMemcpyHostToDevice, st));
+                RET_IF(launch_convert_f64(stage, np, s->D + (size_t)f * s->ld + p0, s->ld, np, 1, st));
+            }
     }
-    CK(cudaMemsetAsync(s->T, 0, sizeof(float) * (size_t)s->ld * s->n, st));     // T was the staging buffer
     return after_load(s);
 }
 
 int bsub_load_u8_host(bsub_solver* s, const uint8_t* frames, double* lo, double* hi, double* mean_raw, int force, void* stream) {
     if (!s || !frames) { set_error("bsub_load_u8_host: bad argument"); return -1; }
-    cudaStream_t st = as_stream(stream);
+    cudaStream_t st = use_stream(s, stream);
     unsigned char* stage = reinterpret_cast<unsigned char*>(s->T);
     const long long count = (long long)s->m * s->n;
     CK(cudaMemcpyAsync(stage, frames, (size_t)count, cudaMemcpyHostToDevice, st));
@@ -435,7 +491,7 @@ static int check_ready(bsub_solver* s) {
 
 int bsub_step_init_local(bsub_solver* s, void* stream) {
     RET_IF(check_ready(s));
-    cudaStream_t st = as_stream(stream);
+    cudaStream_t st = use_stream(s, stream);
     RET_IF(upload_state(s, st));
     CK(cudaMemsetAsync(s->comm_max, 0, sizeof(double) * 8, st));
     CK(cudaMemsetAsync(s->comm_sum + (size_t)s->npad * s->npad, 0, sizeof(double) * kCommTail, st));
@@ -455,7 +511,7 @@ int bsub_step_init_local(bsub_solver* s, void* stream) {
 
 int bsub_step_init_finish(bsub_solver* s, void* stream) {
     RET_IF(check_ready(s));
-    cudaStream_t st = as_stream(stream);
+    cudaStream_t st = use_stream(s, stream);
     RET_IF(launch_eig(s->ep, s->comm_sum, s->comm_max, s->eb, s->st, 0, 1, st));
     // S0 = 0 and Y0 = D / dual_norm are only materialised when some kernel of iteration 1 reads them: with the int8 path
     // iteration 1 has no Gram pass and the streamed shrink kernel forms both from D on the fly
@@ -466,6 +522,7 @@ int bsub_step_init_finish(bsub_solver* s, void* stream) {
 
 int bsub_step_gram(bsub_solver* s, void* stream) {
     if (!s || !s->initialised) { set_error("bsub_step_gram: solver not initialised"); return -1; }
+    use_stream(s, stream);
     // both Gram kernels are enqueued; DevState.gram_mode (set on the device) decides which one does the work
     RET_IF(launch_gram(s->gp, s->gmaps, true, s->tasks_dev, s->st, 0.f, s->gram_partial, s->comm_sum, as_stream(stream)));
     if (s->use_i8)
@@ -481,12 +538,14 @@ int bsub_step_solve(bsub_solver* s, void* stream) {
 
 int bsub_step_shrink(bsub_solver* s, void* stream) {
     if (!s || !s->initialised) { set_error("bsub_step_shrink: solver not initialised"); return -1; }
-    cudaStream_t st = as_stream(stream);
+    cudaStream_t st = use_stream(s, stream);
     ShrinkBuffers b;
     b.D = s->D; b.S = s->S; b.Y = s->Y; b.T = s->T; b.U = s->U; b.tpart = s->tpart; b.Vr = s->eb.Vr; b.VC = s->eb.VC;
     b.vstride = s->eb.vstride; b.part_zz = s->part_zz; b.part_nnz = s->part_nnz; b.part_max = s->part_max;
     b.part_wmax = s->use_i8 ? s->part_wmax : nullptr;
     b.implied_first = s->implied_first ? 1 : 0;
+    const bool proj = s->use_proj && s->use_stream && s->use_i8 && s->shrink_mode != SHRINK_SPILL;
+    b.Tt = proj ? s->Tt : nullptr;
     int nparts = s->sp.nparts;
     if (s->use_tma) {
         if (!s->stmaps_ready) {
@@ -498,6 +557,9 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
         }
         int off = 0, min_rank = 0;
         if (s->use_stream) {          // rank <= 16: streamed kernel; larger ranks fall through to the cluster kernel
+            if (proj)                 // T = Vr^T W from the planes the Gram just read (skips itself when they do not exist)
+                RET_IF(launch_project(s->pjp, s->Wq, s->eb.Vr, s->eb.vstride, s->T, s->ld, s->Tt, s->ssp.rows, s->ssp.cols, s->ssp.R,
+                                      s->ssp.ntile_r, s->ssp.ntiles, s->ssp.kcap, s->st, st));
             RET_IF(launch_shrink_stream(s->ssp, s->ssmaps, b, s->st, s->shrink_mode, st));
             off = s->ssp.nparts; min_rank = s->ssp.kcap + 1;
         }
@@ -537,7 +599,7 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
 
 int bsub_step_finish_iter(bsub_solver* s, void* stream) {
     if (!s || !s->initialised) { set_error("bsub_step_finish_iter: solver not initialised"); return -1; }
-    cudaStream_t st = as_stream(stream);
+    cudaStream_t st = use_stream(s, stream);
     RET_IF(launch_control_post(s->st, s->part_zz, s->part_nnz, s->part_max, 0, s->comm_sum + (size_t)s->npad * s->npad, s->log,
                                s->mirror_dev, 2, nullptr, 0, st));
     CK(cudaEventRecord(s->ev[s->iters_enqueued % (kRunAhead + 1)], st));
@@ -624,23 +686,31 @@ int bsub_download_f32(bsub_solver* s, int which, float* dst, int64_t ld, void* s
 
 int bsub_download_f64(bsub_solver* s, int which, double* dst, int64_t ld, void* stream) {
     if (!s || !dst || ld < s->m) { set_error("bsub_download_f64: bad argument"); return -1; }
-    cudaStream_t st = as_stream(stream);
+    cudaStream_t st = use_stream(s, stream);
     if (which == 0 && !s->finalized) RET_IF(bsub_finalize(s, stream));
     float* src = pick(s, which);
     if (!src) { set_error("bsub_download_f64: bad selector %d", which); return -1; }
-    // widen on the device in frame batches through the tpart / gram scratch would be fragile: use a dedicated buffer
-    const long long batch = std::max<long long>(1, std::min<long long>(s->n, (64ll << 20) / std::max<long long>(1, s->m)));
-    double* stage = nullptr;
-    CK(cudaMalloc((void**)&stage, sizeof(double) * (size_t)batch * s->m));
-    int rc = 0;
-    for (long long f0 = 0; f0 < s->n && rc == 0; f0 += batch) {
-        const int nf = (int)std::min<long long>(batch, s->n - f0);
-        rc = launch_export_f64(src + (size_t)f0 * s->ld, s->ld, stage, s->m, s->m, nf, st);
-        if (rc == 0 && cudaMemcpy2DAsync(dst + (size_t)f0 * ld, sizeof(double) * ld, stage, sizeof(double) * s->m, sizeof(double) * s->m,
-                                         nf, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("bsub_download_f64: copy failed"); rc = -1; }
-        if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_download_f64: sync failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    // widen on the device in batches through the staging buffer (allocated once, no per-call cudaMalloc and a single
+    // synchronise at the end); stream order keeps a half from being overwritten before its copy has left
+    const size_t half = (size_t)4 << 20;
+    RET_IF(ensure_stage64(s, 2 * half));
+    int rc = 0, flip = 0;
+    auto piece = [&](const float* from, long long from_ld, double* to, long long to_ld, long long np, int nf) {
+        double* stage = s->stage64 + (size_t)flip * half;
+        if (rc == 0) rc = launch_export_f64(from, from_ld, stage, np, np, nf, st);
+        if (rc == 0 && cudaMemcpy2DAsync(to, sizeof(double) * to_ld, stage, sizeof(double) * np, sizeof(double) * np, nf, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("bsub_download_f64: copy failed"); rc = -1; }
+        flip ^= 1;
+    };
+    if ((size_t)s->m <= half) {
+        const long long batch = (long long)(half / (size_t)s->m);
+        for (long long f0 = 0; f0 < s->n && rc == 0; f0 += batch)
+            piece(src + (size_t)f0 * s->ld, s->ld, dst + (size_t)f0 * ld, ld, s->m, (int)std::min<long long>(batch, s->n - f0));
+    } else {
+        for (long long f = 0; f < s->n && rc == 0; ++f)
+            for (long long p0 = 0; p0 < s->m && rc == 0; p0 += (long long)half)
+                piece(src + (size_t)f * s->ld + p0, s->ld, dst + (size_t)f * ld + p0, ld, std::min<long long>((long long)half, s->m - p0), 1);
     }
-    cudaFree(stage);
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == 0) { set_error("bsub_download_f64: sync failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
     return rc;
 }
 
@@ -648,7 +718,8 @@ int bsub_debug_info(bsub_solver* s, int32_t* o) {
     if (!s || !o) { set_error("bsub_debug_info: null argument"); return -1; }
     o[0] = s->use_tma; o[1] = s->use_stream; o[2] = s->use_i8; o[3] = s->use_stream ? s->ssp.R : 0; o[4] = s->use_stream ? s->ssp.FC : 0;
     o[5] = s->use_stream ? s->ssp.NS : 0; o[6] = s->gp.ntype; o[7] = s->gp.kc; o[8] = s->ep.C; o[9] = s->use_tma ? s->stp.R : s->sp.R;
-    o[10] = s->use_tma ? s->stp.Cf : s->sp.Cf; o[11] = (int32_t)s->ld;
+    o[10] = s->use_tma ? s->stp.Cf : s->sp.Cf; o[11] = (int32_t)s->ld; o[12] = s->use_proj ? 1 : 0; o[13] = s->use_proj ? s->pjp.NW : 0;
+    o[14] = s->use_proj ? s->pjp.DEPTH : 0; o[15] = 0;
     return 0;
 }
 
@@ -657,6 +728,16 @@ int bsub_debug_eig_cycles(bsub_solver* s, int64_t* out16) {
     DevState h;
     CK(cudaMemcpy(&h, s->st, sizeof(h), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 16; ++i) out16[i] = (int64_t)h.eig_clk[i];
+    return 0;
+}
+
+int bsub_debug_counters(bsub_solver* s, int64_t* out8) {
+    if (!s || !out8) { set_error("bsub_debug_counters: null argument"); return -1; }
+    DevState h;
+    CK(cudaMemcpy(&h, s->st, sizeof(h), cudaMemcpyDeviceToHost));
+    memset(out8, 0, sizeof(int64_t) * 8);
+    out8[0] = h.eig_fast_iters; out8[1] = h.eig_p; out8[2] = h.eig_info & 0xff; out8[3] = (int64_t)(h.eig_gb * 1e6);
+    out8[4] = h.gram_mode; out8[5] = h.wq_saturated;
     return 0;
 }
 
@@ -679,7 +760,7 @@ int bsub_get_log(bsub_solver* s, bsub_iter_log* out, int32_t cap, int32_t* count
 // foreground mask on the solver's own buffers -------------------------------------------------------------------
 int bsub_mask_stats_local(bsub_solver* s, int phase, void* stream) {
     if (!s || !s->initialised) { set_error("bsub_mask_stats_local: nothing has been solved"); return -1; }
-    cudaStream_t st = as_stream(stream);
+    cudaStream_t st = use_stream(s, stream);
     if (!s->finalized) RET_IF(bsub_finalize(s, stream));
     double* tail = s->comm_sum + (size_t)s->npad * s->npad;
     if (phase == 0) {
@@ -691,7 +772,7 @@ int bsub_mask_stats_local(bsub_solver* s, int phase, void* stream) {
         return launch_absmax(s->S, s->ld, s->m, s->n, s->comm_max + 1, st);
     }
     CK(cudaMemsetAsync(tail + 4, 0, sizeof(double) * 3, st));
-    return launch_mask_stats(s->D, s->L, s->S, s->ld, s->m, s->n, s->comm_max + 1, tail + 4, st);
+    return launch_mask_stats(s->D, s->L, s->S, s->ld, s->m, s->n, s->comm_max + 1, tail + 4, s->mask_scratch, st);
 }
 
 int bsub_mask_dev(bsub_solver* s, double sigmas, uint8_t* mask_dev, void* stream) {
@@ -702,7 +783,7 @@ int bsub_mask_dev(bsub_solver* s, double sigmas, uint8_t* mask_dev, void* stream
 
 int bsub_mask_host(bsub_solver* s, double sigmas, uint8_t* mask_host, void* stream) {
     if (!s || !mask_host) { set_error("bsub_mask_host: null argument"); return -1; }
-    cudaStream_t st = as_stream(stream);
+    cudaStream_t st = use_stream(s, stream);
     RET_IF(bsub_mask_stats_local(s, 0, stream));
     RET_IF(bsub_mask_stats_local(s, 1, stream));
     // device staging buffer, allocated once (a cudaMalloc/cudaFree per call would synchronise the whole device)
@@ -719,15 +800,16 @@ int bsub_foreground_mask_dev(const float* D, const float* L, const float* S, int
                              uint8_t* mask, void* stream) {
     if (!D || !L || !S || !mask || ld < m || (ld % 4) != 0) { set_error("bsub_foreground_mask_dev: bad argument (ld must be a multiple of 4, pad columns zero)"); return -1; }
     cudaStream_t st = as_stream(stream);
+    DevScope mem;
     double* buf = nullptr;
-    CK(cudaMalloc((void**)&buf, sizeof(double) * 4));
-    CK(cudaMemsetAsync(buf, 0, sizeof(double) * 4, st));
-    int rc = launch_absmax(S, ld, m, n, buf, st);
-    if (rc == 0) rc = launch_mask_stats(D, L, S, ld, m, n, buf, buf + 1, st);
-    if (rc == 0) rc = launch_mask_write(S, ld, m, n, buf + 1, sigmas, mask, m, st);
-    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_foreground_mask_dev: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
-    cudaFree(buf);
-    return rc;
+    const size_t nd = 4 + mask_stats_scratch_doubles();
+    RET_IF(mem.alloc(&buf, sizeof(double) * nd));
+    CK(cudaMemsetAsync(buf, 0, sizeof(double) * nd, st));
+    RET_IF(launch_absmax(S, ld, m, n, buf, st));
+    RET_IF(launch_mask_stats(D, L, S, ld, m, n, buf, buf + 1, buf + 4, st));
+    RET_IF(launch_mask_write(S, ld, m, n, buf + 1, sigmas, mask, m, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
 }
 
 int bsub_prox_flat3_dev(const float* U, float* V, int64_t ld, int32_t rows, int32_t cols, int32_t n, double lambda1, void* stream) {
@@ -735,26 +817,36 @@ int bsub_prox_flat3_dev(const float* U, float* V, int64_t ld, int32_t rows, int3
     return launch_prox_flat3(U, V, ld, rows, cols, n, (float)lambda1, as_stream(stream));
 }
 
-int bsub_prox_flat_groups_dev(const float* U, float* V, int64_t ld, int64_t m, int32_t n, const int32_t* g, double lambda1, void* stream) {
-    if (!U || !V || !g || ld < m) { set_error("bsub_prox_flat_groups_dev: bad argument"); return -1; }
+// CSR of the group ids >= 1 (ptr[k] .. ptr[k+1]: pixels of group k+1); returns the largest id
+static int groups_to_csr(const int32_t* g, long long m, std::vector<int>& start, std::vector<int>& idx) {
     int gmax = 0;
-    for (long long p = 0; p < m; ++p) { if (g[p] < 0) { set_error("bsub_prox_flat_groups_dev: negative group id"); return -1; } gmax = std::max(gmax, (int)g[p]); }
-    std::vector<int> cnt((size_t)gmax + 1, 0), start((size_t)gmax + 1, 0);
+    for (long long p = 0; p < m; ++p) { if (g[p] < 0) return -1; gmax = std::max(gmax, (int)g[p]); }
+    std::vector<int> cnt((size_t)gmax + 1, 0);
+    start.assign((size_t)gmax + 1, 0);
     for (long long p = 0; p < m; ++p) if (g[p] > 0) cnt[g[p]]++;
     int acc = 0;
     for (int k = 1; k <= gmax; ++k) { start[k - 1] = acc; acc += cnt[k]; }
     start[gmax] = acc;
-    std::vector<int> idx((size_t)std::max(acc, 1)), fill(start.begin(), start.end());
+    idx.assign((size_t)std::max(acc, 1), 0);
+    std::vector<int> fill(start.begin(), start.end());
     for (long long p = 0; p < m; ++p) if (g[p] > 0) idx[fill[g[p] - 1]++] = (int)p;
+    return gmax;
+}
+
+int bsub_prox_flat_groups_dev(const float* U, float* V, int64_t ld, int64_t m, int32_t n, const int32_t* g, double lambda1, void* stream) {
+    if (!U || !V || !g || ld < m) { set_error("bsub_prox_flat_groups_dev: bad argument"); return -1; }
+    std::vector<int> start, idx;
+    const int gmax = groups_to_csr(g, m, start, idx);
+    if (gmax < 0) { set_error("bsub_prox_flat_groups_dev: negative group id"); return -1; }
+    DevScope mem;
     int *gptr = nullptr, *gidx = nullptr;
-    CK(cudaMalloc((void**)&gptr, sizeof(int) * ((size_t)gmax + 1)));
-    CK(cudaMalloc((void**)&gidx, sizeof(int) * idx.size()));
+    RET_IF(mem.alloc(&gptr, sizeof(int) * ((size_t)gmax + 1)));
+    RET_IF(mem.alloc(&gidx, sizeof(int) * idx.size()));
     CK(cudaMemcpy(gptr, start.data(), sizeof(int) * ((size_t)gmax + 1), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(gidx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice));
-    int rc = launch_prox_groups_csr(U, V, ld, m, n, gptr, gidx, gmax, (float)lambda1, nullptr, as_stream(stream));
-    if (rc == 0 && cudaStreamSynchronize(as_stream(stream)) != cudaSuccess) { set_error("bsub_prox_flat_groups_dev: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
-    cudaFree(gptr); cudaFree(gidx);
-    return rc;
+    RET_IF(launch_prox_groups_csr(U, V, ld, m, n, gptr, gidx, gmax, (float)lambda1, nullptr, as_stream(stream)));
+    CK(cudaStreamSynchronize(as_stream(stream)));
+    return 0;
 }
 
 int bsub_prox_graph3_dev(const float* U, float* V, int64_t ld, int32_t rows, int32_t cols, int32_t n, double lambda1,
@@ -762,24 +854,24 @@ int bsub_prox_graph3_dev(const float* U, float* V, int64_t ld, int32_t rows, int
     if (!U || !V || (long long)rows * cols > ld) { set_error("bsub_prox_graph3_dev: bad argument"); return -1; }
     cudaStream_t st = as_stream(stream);
     const long long nwi = rows - std::min(3, rows) + 1, nwj = cols - std::min(3, cols) + 1, nw = nwi * nwj;
+    DevScope mem;
     float *xi = nullptr, *tot = nullptr, *eta = nullptr; int* sw = nullptr;
-    CK(cudaMalloc((void**)&xi, sizeof(float) * (size_t)n * nw * 9));
-    CK(cudaMalloc((void**)&tot, sizeof(float) * (size_t)n * ld));
-    CK(cudaMalloc((void**)&sw, sizeof(int) * 4));
+    RET_IF(mem.alloc(&xi, sizeof(float) * (size_t)n * nw * 9));
+    RET_IF(mem.alloc(&tot, sizeof(float) * (size_t)n * ld));
+    RET_IF(mem.alloc(&sw, sizeof(int) * 4));
     if (eta_host) {
         std::vector<float> ef((size_t)nw);
         for (long long i = 0; i < nw; ++i) ef[i] = (float)eta_host[i];
-        CK(cudaMalloc((void**)&eta, sizeof(float) * nw));
+        RET_IF(mem.alloc(&eta, sizeof(float) * nw));
         CK(cudaMemcpy(eta, ef.data(), sizeof(float) * nw, cudaMemcpyHostToDevice));
     }
-    int rc = launch_prox_graph3(U, V, xi, tot, eta, ld, rows, cols, n, (float)lambda1, max_sweeps > 0 ? max_sweeps : 4000, (float)tol, sw,
-                                nullptr, st);
+    RET_IF(launch_prox_graph3(U, V, xi, tot, eta, ld, rows, cols, n, (float)lambda1, max_sweeps > 0 ? max_sweeps : 4000, (float)tol, sw,
+                              nullptr, st));
     int sw_h = 0;
-    if (rc == 0 && cudaMemcpyAsync(&sw_h, sw, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
-    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_prox_graph3_dev: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    CK(cudaMemcpyAsync(&sw_h, sw, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     if (sweeps_used) *sweeps_used = sw_h;
-    cudaFree(xi); cudaFree(tot); cudaFree(sw); if (eta) cudaFree(eta);
-    return rc;
+    return 0;
 }
 
 int bsub_prox_center3_dev(const float* U, float* V, int64_t ld, int32_t rows, int32_t cols, int32_t n, double lambda1,
@@ -787,20 +879,20 @@ int bsub_prox_center3_dev(const float* U, float* V, int64_t ld, int32_t rows, in
     if (!U || !V || !eta_host || (long long)rows * cols > ld) { set_error("bsub_prox_center3_dev: bad argument"); return -1; }
     cudaStream_t st = as_stream(stream);
     const long long m = (long long)rows * cols;
+    DevScope mem;
     float *xi = nullptr, *tot = nullptr, *eta = nullptr; int* sw = nullptr;
-    CK(cudaMalloc((void**)&xi, sizeof(float) * (size_t)n * m * 9));          // one candidate window per pixel and frame
-    CK(cudaMalloc((void**)&tot, sizeof(float) * (size_t)n * ld));
-    CK(cudaMalloc((void**)&eta, sizeof(float) * (size_t)n * m));
-    CK(cudaMalloc((void**)&sw, sizeof(int) * 4));
+    RET_IF(mem.alloc(&xi, sizeof(float) * (size_t)n * m * 9));          // one candidate window per pixel and frame
+    RET_IF(mem.alloc(&tot, sizeof(float) * (size_t)n * ld));
+    RET_IF(mem.alloc(&eta, sizeof(float) * (size_t)n * m));
+    RET_IF(mem.alloc(&sw, sizeof(int) * 4));
     CK(cudaMemcpy(eta, eta_host, sizeof(float) * (size_t)n * m, cudaMemcpyHostToDevice));
-    int rc = launch_prox_graph3(U, V, xi, tot, eta, ld, rows, cols, n, (float)lambda1, max_sweeps > 0 ? max_sweeps : 4000, (float)tol, sw,
-                                nullptr, st, 1, m);
+    RET_IF(launch_prox_graph3(U, V, xi, tot, eta, ld, rows, cols, n, (float)lambda1, max_sweeps > 0 ? max_sweeps : 4000, (float)tol, sw,
+                              nullptr, st, 1, m));
     int sw_h = 0;
-    if (rc == 0 && cudaMemcpyAsync(&sw_h, sw, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = -1;
-    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_prox_center3_dev: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    CK(cudaMemcpyAsync(&sw_h, sw, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     if (sweeps_used) *sweeps_used = sw_h;
-    cudaFree(xi); cudaFree(tot); cudaFree(eta); cudaFree(sw);
-    return rc;
+    return 0;
 }
 
 int bsub_block_shrink_dev(const float* G, float* R, int64_t ld, int64_t m, int32_t n, const uint8_t* labels, const int32_t* lam_ptr,
@@ -813,17 +905,17 @@ int bsub_block_shrink_dev(const float* G, float* R, int64_t ld, int64_t m, int32
     std::vector<double> table((size_t)n * nlab, 0.0);
     for (int f = 0; f < n; ++f)
         for (int b = 0; b < lam_ptr[f + 1] - lam_ptr[f]; ++b) table[(size_t)f * nlab + b + 1] = lam[lam_ptr[f] + b];
+    DevScope mem;
     unsigned char* lab_d = nullptr; double *tab_d = nullptr, *sums = nullptr;
-    CK(cudaMalloc((void**)&lab_d, (size_t)n * m));
-    CK(cudaMalloc((void**)&tab_d, sizeof(double) * table.size()));
-    CK(cudaMalloc((void**)&sums, sizeof(double) * table.size()));
+    RET_IF(mem.alloc(&lab_d, (size_t)n * m));
+    RET_IF(mem.alloc(&tab_d, sizeof(double) * table.size()));
+    RET_IF(mem.alloc(&sums, sizeof(double) * table.size()));
     CK(cudaMemcpy(lab_d, labels, (size_t)n * m, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(tab_d, table.data(), sizeof(double) * table.size(), cudaMemcpyHostToDevice));
-    int rc = launch_block_l2_sums(G, lab_d, ld, m, n, nlab, sums, nullptr, st);
-    if (rc == 0) rc = launch_block_l2_apply(G, R, lab_d, ld, m, n, nlab, sums, tab_d, nullptr, mu, non_block_lambda, st);
-    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_block_shrink_dev: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
-    cudaFree(lab_d); cudaFree(tab_d); cudaFree(sums);
-    return rc;
+    RET_IF(launch_block_l2_sums(G, lab_d, ld, m, n, nlab, sums, nullptr, st));
+    RET_IF(launch_block_l2_apply(G, R, lab_d, ld, m, n, nlab, sums, tab_d, nullptr, mu, non_block_lambda, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
 }
 
 int bsub_gram_dev(const float* D, const float* S, const float* Y, int64_t ld, int64_t m, int32_t n, double mu, double* G_host,
@@ -837,18 +929,18 @@ int bsub_gram_dev(const float* D, const float* S, const float* Y, int64_t ld, in
     GramPlan gp = make_gram_plan(n, ld, sms);
     std::vector<int2> tasks(gp.ntasks);
     fill_gram_tasks(gp, tasks.data());
+    DevScope mem;
     int2* tasks_d = nullptr; double *partial = nullptr, *G = nullptr;
-    CK(cudaMalloc((void**)&tasks_d, sizeof(int2) * gp.ntasks));
-    CK(cudaMalloc((void**)&partial, sizeof(double) * gp.partial_elems));
-    CK(cudaMalloc((void**)&G, sizeof(double) * (size_t)gp.npad * gp.npad));
+    RET_IF(mem.alloc(&tasks_d, sizeof(int2) * gp.ntasks));
+    RET_IF(mem.alloc(&partial, sizeof(double) * gp.partial_elems));
+    RET_IF(mem.alloc(&G, sizeof(double) * (size_t)gp.npad * gp.npad));
     CK(cudaMemcpy(tasks_d, tasks.data(), sizeof(int2) * gp.ntasks, cudaMemcpyHostToDevice));
     GramMaps gm;
-    int rc = make_gram_maps(gp, D, S, Y, ld, &gm);
-    if (rc == 0) rc = launch_gram(gp, gm, S != nullptr, tasks_d, nullptr, (float)(S ? 1.0 / mu : 0.0), partial, G, st);
-    if (rc == 0 && cudaMemcpy2DAsync(G_host, sizeof(double) * n, G, sizeof(double) * gp.npad, sizeof(double) * n, n, cudaMemcpyDeviceToHost, st) != cudaSuccess) { set_error("bsub_gram_dev: copy failed"); rc = -1; }
-    if (rc == 0 && cudaStreamSynchronize(st) != cudaSuccess) { set_error("bsub_gram_dev: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
-    cudaFree(tasks_d); cudaFree(partial); cudaFree(G);
-    return rc;
+    RET_IF(make_gram_maps(gp, D, S, Y, ld, &gm));
+    RET_IF(launch_gram(gp, gm, S != nullptr, tasks_d, nullptr, (float)(S ? 1.0 / mu : 0.0), partial, G, st));
+    CK(cudaMemcpy2DAsync(G_host, sizeof(double) * n, G, sizeof(double) * gp.npad, sizeof(double) * n, n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
 }
 
 int bsub_gram_i8_test(const int8_t* slices_host, int32_t n, int64_t ldq, int64_t* G_host) {
@@ -861,14 +953,15 @@ int bsub_gram_i8_test(const int8_t* slices_host, int32_t n, int64_t ldq, int64_t
     GramI8Plan gp = make_gram_i8_plan(n, ldq, sms);
     std::vector<int4> info; std::vector<int> blkn;
     fill_gram_i8_tables(gp, info, blkn);
+    DevScope mem;
     signed char* q = nullptr; int4* info_d = nullptr; int* blkn_d = nullptr; unsigned long long* Gint = nullptr; double* G = nullptr;
     const size_t qbytes = (size_t)4 * n * ldq, gn = (size_t)gp.nblk * 128;
     const int npad = ((n + 31) / 32) * 32;
-    CK(cudaMalloc((void**)&q, qbytes));
-    CK(cudaMalloc((void**)&info_d, sizeof(int4) * info.size()));
-    CK(cudaMalloc((void**)&blkn_d, sizeof(int) * blkn.size()));
-    CK(cudaMalloc((void**)&Gint, sizeof(unsigned long long) * gn * gn));
-    CK(cudaMalloc((void**)&G, sizeof(double) * (size_t)npad * npad));
+    RET_IF(mem.alloc(&q, qbytes));
+    RET_IF(mem.alloc(&info_d, sizeof(int4) * info.size()));
+    RET_IF(mem.alloc(&blkn_d, sizeof(int) * blkn.size()));
+    RET_IF(mem.alloc(&Gint, sizeof(unsigned long long) * gn * gn));
+    RET_IF(mem.alloc(&G, sizeof(double) * (size_t)npad * npad));
     {   // repack [4][n][ldq] (row-major, as the caller gives it) into the k-block-major layout [4][ldq/16][n][16]
         std::vector<signed char> packed(qbytes);
         for (int sl = 0; sl < 4; ++sl)
@@ -880,21 +973,18 @@ int bsub_gram_i8_test(const int8_t* slices_host, int32_t n, int64_t ldq, int64_t
     CK(cudaMemcpy(info_d, info.data(), sizeof(int4) * info.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(blkn_d, blkn.data(), sizeof(int) * blkn.size(), cudaMemcpyHostToDevice));
     CUtensorMap map, map_last;
-    int rc = make_gram_i8_map(gp, q, &map, 128);
-    if (rc == 0) rc = make_gram_i8_map(gp, q, &map_last, gram_i8_last_block_n(gp));
-    if (rc == 0) rc = launch_gram_i8(gp, map, map_last, info_d, (int)info.size(), blkn_d, Gint, G, npad, nullptr, 1.0, 1, 0);
-    if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) { set_error("bsub_gram_i8_test: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
-    if (rc == 0) {
-        std::vector<long long> tmp(gn * gn);
-        cudaMemcpy(tmp.data(), Gint, sizeof(long long) * gn * gn, cudaMemcpyDeviceToHost);
-        for (int i = 0; i < n; ++i)
-            for (int j = 0; j < n; ++j) {
-                const int r = (i / 128 <= j / 128) ? i : j, c = (i / 128 <= j / 128) ? j : i;
-                G_host[(size_t)i * n + j] = tmp[(size_t)r * gn + c];
-            }
-    }
-    cudaFree(q); cudaFree(info_d); cudaFree(blkn_d); cudaFree(Gint); cudaFree(G);
-    return rc;
+    RET_IF(make_gram_i8_map(gp, q, &map, 128));
+    RET_IF(make_gram_i8_map(gp, q, &map_last, gram_i8_last_block_n(gp)));
+    RET_IF(launch_gram_i8(gp, map, map_last, info_d, (int)info.size(), blkn_d, Gint, G, npad, nullptr, 1.0, 1, 0));
+    CK(cudaDeviceSynchronize());
+    std::vector<long long> tmp(gn * gn);
+    CK(cudaMemcpy(tmp.data(), Gint, sizeof(long long) * gn * gn, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            const int r = (i / 128 <= j / 128) ? i : j, c = (i / 128 <= j / 128) ? j : i;
+            G_host[(size_t)i * n + j] = tmp[(size_t)r * gn + c];
+        }
+    return 0;
 }
 
 int bsub_eig_topk(const double* G_host, int32_t n, int32_t k, double* lam_host, double* vec_host) {
@@ -903,24 +993,22 @@ int bsub_eig_topk(const double* G_host, int32_t n, int32_t k, double* lam_host, 
     EigPlan ep = make_eig_plan(n, npad);
     EigBuffers eb;
     memset(&eb, 0, sizeof(eb));
+    DevScope mem;
     double* G = nullptr; DevState* st = nullptr;
-    CK(cudaMalloc((void**)&G, sizeof(double) * (size_t)npad * npad));
+    RET_IF(mem.alloc(&G, sizeof(double) * (size_t)npad * npad));
     CK(cudaMemset(G, 0, sizeof(double) * (size_t)npad * npad));
     CK(cudaMemcpy2D(G, sizeof(double) * npad, G_host, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice));
-    CK(cudaMalloc((void**)&eb.work, sizeof(double) * ep.work_doubles));
-    CK(cudaMalloc((void**)&eb.lam, sizeof(double) * n));
-    CK(cudaMalloc((void**)&eb.Z, sizeof(double) * (size_t)n * n));
-    CK(cudaMalloc((void**)&st, sizeof(DevState)));
+    RET_IF(mem.alloc(&eb.work, sizeof(double) * ep.work_doubles));
+    RET_IF(mem.alloc(&eb.lam, sizeof(double) * n));
+    RET_IF(mem.alloc(&eb.Z, sizeof(double) * (size_t)n * n));
+    RET_IF(mem.alloc(&st, sizeof(DevState)));
     CK(cudaMemset(st, 0, sizeof(DevState)));
     eb.vstride = n;
-    int rc = launch_eig(ep, G, nullptr, eb, st, 2, k, 0);
-    if (rc == 0 && cudaDeviceSynchronize() != cudaSuccess) { set_error("bsub_eig_topk: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
-    if (rc == 0) {
-        cudaMemcpy(lam_host, eb.lam, sizeof(double) * k, cudaMemcpyDeviceToHost);
-        if (vec_host) cudaMemcpy(vec_host, eb.Z, sizeof(double) * (size_t)k * n, cudaMemcpyDeviceToHost);
-    }
-    cudaFree(G); cudaFree(eb.work); cudaFree(eb.lam); cudaFree(eb.Z); cudaFree(st);
-    return rc;
+    RET_IF(launch_eig(ep, G, nullptr, eb, st, 2, k, 0));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(lam_host, eb.lam, sizeof(double) * k, cudaMemcpyDeviceToHost));
+    if (vec_host) CK(cudaMemcpy(vec_host, eb.Z, sizeof(double) * (size_t)k * n, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 }  // extern "C"

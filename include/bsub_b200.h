@@ -140,7 +140,11 @@ int bsub_get_log(bsub_solver* s, bsub_iter_log* out, int32_t cap, int32_t* count
 /* diagnostics: SM clock at the phase boundaries of the last eigensolve (load, tridiag, eigenvalues, vectors, reorth, back-transform) */
 int bsub_debug_eig_cycles(bsub_solver* s, int64_t* out16);
 /* diagnostics: kernel paths chosen for this solver: use_tma, use_stream, use_i8, stream R/FC/NS, gram types/kc, eig cluster, tma R/Cf, ld */
-int bsub_debug_info(bsub_solver* s, int32_t* out12);
+int bsub_debug_info(bsub_solver* s, int32_t* out16);   /* ..., [12] plane projection on, [13] its warps, [14] its slot depth */
+/* diagnostics: [0] iterations of the last solve whose eigenpairs came from the warm-started subspace path (eig.cu), [1] vectors
+ * kept for the next warm start, [2] subspace steps of the last call, [3] 1e6 * last certificate ||G - X theta X^T||_F mu^2,
+ * [4] Gram mode of the next iteration (0 fp64 DMMA, 1 int8 tcgen05), [5] last digit pass saturated */
+int bsub_debug_counters(bsub_solver* s, int64_t* out8);
 /* foreground_mask(D, L, S, sigmas) of utils.py:139-149 on the solver's own D, L, S; mask uint8[n][m] on the host */
 int bsub_mask_stats_local(bsub_solver* s, int phase /*0: max|S|, 1: count/sum/sumsq*/, void* stream);
 int bsub_mask_host(bsub_solver* s, double sigmas, uint8_t* mask_host, void* stream);
