@@ -361,13 +361,13 @@ class Decomposition:
         out = (ctypes.c_int32 * 16)()
         C.check(self.lib.bsub_debug_info(self.h, out))
         keys = ["use_tma", "use_stream", "use_i8", "stream_R", "stream_FC", "stream_NS", "gram_types", "gram_kc", "eig_cluster",
-                "tma_R", "tma_Cf", "ld", "use_proj", "proj_warps", "proj_depth"]
+                "tma_R", "tma_Cf", "ld", "use_proj", "proj_warps", "proj_depth", "flat_stages"]
         return dict(zip(keys, [int(v) for v in out]))
 
     def counters(self):
         out = (ctypes.c_int64 * 8)()
         C.check(self.lib.bsub_debug_counters(self.h, out))
-        keys = ["eig_fast_iters", "eig_p", "eig_fast_steps", "eig_gb_ppm", "gram_mode", "wq_saturated"]
+        keys = ["eig_fast_iters", "eig_p", "eig_fast_steps", "eig_gb_ppm", "gram_mode", "wq_saturated", "force_dmma", "gram_err_ppm"]
         return dict(zip(keys, [int(v) for v in out]))
 
     def eig_fast_count(self):

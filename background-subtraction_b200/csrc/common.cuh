@@ -25,6 +25,7 @@ struct DevState {
     double rho, tol, mu_scale;
     // evolving
     double mu;              // mu_k used by the current iteration
+    double mu_iter;         // mu of the iteration whose shrink pass ran last (mu itself has already been advanced)
     double thresh;          // 1/mu
     double zz;              // sum Z^2 of the last shrink pass
     double err;
@@ -51,7 +52,18 @@ struct DevState {
     int eig_p;
     int eig_fast_iters;     // iterations of this solve that took the warm-started path
     double eig_gb;          // last certificate: ||G - X theta X^T||_F * mu^2  (must be < 1)
+    // accuracy bookkeeping of the int8 Gram: once the bound of its truncation error (all-reduced with the Gram) stops being small
+    // against the threshold (1/mu)^2, the rest of the solve uses the fp64 Gram
+    double gram_err;        // last bound seen by the eigensolver, relative to (1/mu)^2
+    int force_dmma;
 };
+
+// which iterations the single-pass kernel of shrink_flat.cu takes (evaluated identically by it and by the kernels it relieves):
+// the digit planes of this W exist (so project.cu has produced T), not the first iteration, rank <= 8
+constexpr int kFlatMaxRank = 8;
+__device__ __forceinline__ bool shrink_flat_takes(const DevState* st) {
+    return st->gram_mode == 1 && st->iter > 1 && st->svp <= kFlatMaxRank;
+}
 
 struct IterLog {
     int iter, svp, sv, pad;

@@ -110,6 +110,7 @@ __device__ void eig_control(const EigArgs& a, DevState* st, int K, double mu, do
             // int8 Gram path: W_1 = c D, so iteration 1 reuses this eigen-decomposition (gram_mode 2);
             // |W_1| <= 1.08 max|D| (Y0/mu0 <= D/12.5)
             st->gram_mode = st->use_i8 ? 2 : 0; st->wq_saturated = 0; st->wmax = 1.08 * a.comm_max[2];
+            st->force_dmma = 0; st->gram_err = 0.0;
             st->wq_scale = 0.0;
             st->wq_scale_next = (a.comm_max[2] > 0.0) ? exp2(ceil(log2(4.0 * 1.08 * a.comm_max[2]))) : 1.0;
             if (!(norm_two > 0.0)) { st->done = 4; }       // all-zero input
@@ -119,6 +120,11 @@ __device__ void eig_control(const EigArgs& a, DevState* st, int K, double mu, do
     // mode 1
     const double thresh = 1.0 / mu;
     if (tid == 0) {
+        // truncation-error bound of the int8 Gram (gram_i8.cu; summed over the ranks by the all-reduce, 0 for the fp64 Gram):
+        // beyond 0.3 (1/mu)^2 a singular value a little above the threshold could be lost, so the solve continues on gram.cu
+        const double ge = a.G[(size_t)a.npad * a.npad + 8] / (thresh * thresh);
+        st->gram_err = ge;
+        if (ge > 0.3) st->force_dmma = 1;
         int svp = 0;
         for (int k = 0; k < K; ++k) {
             double sig = sqrt(fmax((a.lam[k] * lam_scale), 0.0));

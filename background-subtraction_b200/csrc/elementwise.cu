@@ -68,7 +68,8 @@ int launch_init_Y(const float* D, float* Y, float* S, long long ld, int n, const
 // ---- per-iteration control after the shrink pass (/root/reference/inexact_alm_lsd.py:164-177).
 // phase bit 1: gather this rank's per-CTA partials (fixed order) into the communication buffer
 //              comm_tail[0] = sum Z^2, comm_tail[1] = nnz(S), comm_tail[2] = max |S| (local)
-// phase bit 2: finish the iteration from the (all-reduced) communication buffer.
+// phase bit 4: advance mu and the digit-plane bookkeeping (local quantities only).
+// phase bit 2: finish the iteration from the (all-reduced) communication buffer: err, log line, stop flags.
 __global__ void control_post_kernel(DevState* st, const double* part_zz, const unsigned long long* part_nnz,
                                     const float* part_max, int nparts, double* comm_tail, IterLog* log,
                                     HostMirror* mirror, int phase, const float* part_wmax, int nwmax) {
@@ -99,18 +100,11 @@ __global__ void control_post_kernel(DevState* st, const double* part_zz, const u
     }
     if (lane != 0) return;
     if (!st->done) {
-        if (phase & 2) {
-            const double zz = comm_tail[0];
-            const double err = sqrt(zz / st->normD2);
-            st->zz = zz; st->err = err;
-            st->nnzS = (unsigned long long)(comm_tail[1] + 0.5);
-            st->maxS = (float)comm_tail[2];
-            st->svp_L = st->svp;
-            const int it = st->iter;
-            if (it >= 1 && it <= kMaxIterLog) {
-                IterLog& l = log[it - 1];
-                l.iter = it; l.svp = st->svp; l.sv = st->sv_used; l.pad = 0; l.err = err; l.mu = st->mu; l.nnz = st->nnzS;
-            }
+        if (phase & 4) {
+            // bookkeeping that does not need the reduced residual: mu <- rho mu (inexact_alm_lsd.py:164) and the fixed-point
+            // scale of the digit planes.  A pixel-sharded run enqueues the next Gram right after this, so that the 4 scalars of
+            // this iteration travel in the same all-reduce message as the next Gram.
+            st->mu_iter = st->mu;
             st->mu = fmin(st->mu * st->rho, st->mu * 1e7);
             if (st->use_i8) {
                 const double wm = st->wm_local;
@@ -123,6 +117,20 @@ __global__ void control_post_kernel(DevState* st, const double* part_zz, const u
                     st->gram_mode = 0; st->wq_saturated = (wm >= 1.0e38);
                     if (wm >= 1.0e38) st->wq_scale_next = st->wq_scale_next * 16.0;
                 }
+                if (st->force_dmma) st->gram_mode = 0;            // the int8 Gram has become too coarse for the shrinking threshold (eig.cu)
+            }
+        }
+        if (phase & 2) {
+            const double zz = comm_tail[0];
+            const double err = sqrt(zz / st->normD2);
+            st->zz = zz; st->err = err;
+            st->nnzS = (unsigned long long)(comm_tail[1] + 0.5);
+            st->maxS = (float)comm_tail[2];
+            st->svp_L = st->svp;
+            const int it = st->iter;
+            if (it >= 1 && it <= kMaxIterLog) {
+                IterLog& l = log[it - 1];
+                l.iter = it; l.svp = st->svp; l.sv = st->sv_used; l.pad = 0; l.err = err; l.mu = st->mu_iter; l.nnz = st->nnzS;
             }
             if (err < st->tol) { st->done = 1; st->converged = 1; }
             else if (it >= st->max_iter) { st->done = 2; }

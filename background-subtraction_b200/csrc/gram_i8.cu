@@ -471,16 +471,22 @@ int launch_quantize_D(const float* D, long long ld, int n, long long ldq, signed
 
 // G[i][j] (double, [npad][npad], symmetric) = Gint * scale   with  scale = S^2 * 2^-38
 __global__ void gram_i8_finish_kernel(const unsigned long long* __restrict__ Gint, int nblk, int n, int npad, double* __restrict__ G,
-                                      const DevState* st, double scale_override, int require_mode) {
-    if (st != nullptr && (st->done || st->gram_mode != require_mode)) return;
+                                      const DevState* st, double scale_override, int require_mode, double diag_bias, double err_units,
+                                      double* err_slot) {
+    const bool runs = !(st != nullptr && (st->done || st->gram_mode != require_mode));
     const double scale = (st != nullptr) ? st->wq_scale * st->wq_scale * 0x1p-38 : scale_override;
+    // bound of what the dropped digit classes may have taken from an eigenvalue of this rank's partial Gram (0 when the fp64
+    // Gram did the work); it travels with the Gram through the all-reduce, so every rank sees the same total (eig.cu)
+    if (err_slot != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && !(st != nullptr && st->done)) *err_slot = runs ? 2.0 * err_units * scale : 0.0;
+    if (!runs) return;
     const size_t ldg = (size_t)nblk * 128;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < npad * npad; idx += gridDim.x * blockDim.x) {
         const int i = idx / npad, j = idx - i * npad;
         double v = 0.0;
         if (i < n && j < n) {
             const int r = (i / 128 <= j / 128) ? i : j, c = (i / 128 <= j / 128) ? j : i;     // upper block triangle holds the data
-            v = (double)(long long)Gint[(size_t)r * ldg + c] * scale;
+            // diag_bias: expected value of the digit products the kernel drops (classes i + j <= 2), see launch_gram_i8
+            v = ((double)(long long)Gint[(size_t)r * ldg + c] + ((i == j) ? diag_bias : 0.0)) * scale;
         }
         G[idx] = v;
     }
@@ -489,7 +495,7 @@ __global__ void gram_i8_finish_kernel(const unsigned long long* __restrict__ Gin
 // -------------------------------------------------------------------------------------------------------------
 GramI8Plan make_gram_i8_plan(int n, long long ldq, int num_sms) {
     GramI8Plan p;
-    p.n = n; p.ldq = ldq;
+    p.n = n; p.ldq = ldq; p.m_real = 0;
     p.nblk = (n + 127) / 128;
     p.nkb = (int)(ldq / GI_KB);          // ldq = pixels per frame in the slice matrix, a multiple of 64
     p.smem_bytes = (size_t)GI_STAGES * GI_STAGE_BYTES + 256 + 1024;
@@ -553,6 +559,24 @@ int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const CUtensorMa
     if (first_call_on_device(&attr_devs)) {
         BSUB_CUDA_CHECK(cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes));
     }
+    // The kernel keeps the digit-pair classes i + j >= 3 of q_f q_g = sum 256^(i+j) d_i(f) d_j(g).  With q = A 2^16 + B
+    // (B = d0 + 256 d1, the low 16 bits as a balanced number) the dropped part is B_f B_g + 2^16 (d0_f d2_g + d2_f d0_g):
+    //   * on the diagonal its mean is E_d = E[d0^2] + 512 E[d0] E[d1] + 65536 E[d1^2] + 2^17 E[d0] E[d2] per pixel for uniformly
+    //     distributed low digits (d uniform on -128..127: E[d] = -1/2, E[d^2] = 5461.5), i.e. the raw sums are too SMALL by
+    //     m E_d: every eigenvalue sits ~1e-10 lambda_1 too low -- the size of (1/mu)^2 after ~20 ALM iterations;
+    //   * off the diagonal it is a zero-mean sum over the pixels: a random symmetric matrix with entry deviation
+    //     sqrt(m) E_o (E_o^2 = E[B^2]^2 + 2 (65536 sd(d0) sd(d2))^2) and spectral norm ~ 2 sqrt(n m) E_o.
+    //   * worse, the d0 x d2 part is COHERENT: the third digit of a pixel is nearly the same in every frame (static background),
+    //     so sum_p d0_f d2_g ~ r_f for all g: a rank-2 perturbation r 1^T + 1 r^T of norm <= n sqrt(m) 65536 sd(d0) max|d2|.
+    // Adding back m E_d alone would centre this noise on zero and let it push cluster eigenvalues ABOVE the threshold in late
+    // iterations (seen: rank inflation at iteration 21+ of WaterSurface delta = 1, iteration 20 of a 48x60x600 clip).  So the
+    // diagonal gets m E_d - err with err = sqrt(m) (n + 3 sqrt(n)) E_o, a bound of the noise norm: the Gram then errs LOW by
+    // at most 2 err -- it can never invent rank.  2 err (in the units of G) is handed to the eigensolver, which switches the
+    // solve to the fp64 Gram (gram.cu) once that bound stops being small against the threshold (1/mu)^2 (eig.cu, force_dmma).
+    // m_real = 0 (operator test) keeps the raw integer sums.  (The int64 accumulators hold the kept classes / 256^3: 2^-24.)
+    const double E_d = 5461.5 + 128.0 + 65536.0 * 5461.5 + 131072.0 * 0.25, E_o = 6.2e8;
+    const double err_units = (p.m_real > 0) ? sqrt((double)p.m_real) * ((double)p.n + 3.0 * sqrt((double)p.n)) * E_o * 0x1p-24 : 0.0;
+    const double diag_bias = (p.m_real > 0) ? (double)p.m_real * E_d * 0x1p-24 - err_units : 0.0;
     const size_t gbytes = sizeof(unsigned long long) * (size_t)p.nblk * 128 * p.nblk * 128;
     BSUB_CUDA_CHECK(cudaMemsetAsync(Gint, 0, gbytes, stream));
     // three frame blocks: the 3-CTA multicast clusters (gram_i8_c3_kernel); anything else: independent CTAs
@@ -580,7 +604,8 @@ int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const CUtensorMa
             c.Gint = Gint; c.st = st; c.require_mode = require_mode;
             cfg.gridDim = dim3(3 * c3_clusters);
             BSUB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_c3_kernel, map, c));
-            gram_i8_finish_kernel<<<64, 256, 0, stream>>>(Gint, p.nblk, p.n, npad, G, st, scale_override, require_mode);
+            gram_i8_finish_kernel<<<64, 256, 0, stream>>>(Gint, p.nblk, p.n, npad, G, st, scale_override, require_mode, diag_bias, err_units,
+                                                          (st != nullptr) ? G + (size_t)npad * npad + 8 : nullptr);
             BSUB_CUDA_CHECK(cudaGetLastError());
             return 0;
         }
@@ -589,7 +614,8 @@ int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const CUtensorMa
     a.n = p.n; a.nblk = p.nblk; a.nkb = p.nkb; a.cta_info = cta_info_dev; a.blk_n = blk_n_dev; a.Gint = Gint; a.st = st; a.require_mode = require_mode;
     gram_i8_kernel<<<ncta, GI_THREADS, p.smem_bytes, stream>>>(map, map_last, a);
     BSUB_CUDA_CHECK(cudaGetLastError());
-    gram_i8_finish_kernel<<<64, 256, 0, stream>>>(Gint, p.nblk, p.n, npad, G, st, scale_override, require_mode);
+    gram_i8_finish_kernel<<<64, 256, 0, stream>>>(Gint, p.nblk, p.n, npad, G, st, scale_override, require_mode, diag_bias, err_units,
+                                                          (st != nullptr) ? G + (size_t)npad * npad + 8 : nullptr);
     BSUB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -24,7 +24,8 @@ int launch_gram(const GramPlan& p, const GramMaps& maps, bool combo, const int2*
                 float inv_mu_override, double* partial, double* G, cudaStream_t stream);
 
 // ---------------------------------------------------------------- gram_i8.cu (tcgen05 int8 Gram from the W slices)
-struct GramI8Plan { int n, nblk, nkb, grid; long long ldq; size_t smem_bytes; };
+struct GramI8Plan { int n, nblk, nkb, grid; long long ldq; size_t smem_bytes;
+                    long long m_real; };   // pixels that hold real data (0: no correction of the dropped digit classes)
 GramI8Plan make_gram_i8_plan(int n, long long ldq, int num_sms);
 void fill_gram_i8_tables(const GramI8Plan& p, std::vector<int4>& cta_info, std::vector<int>& blk_n);
 int make_gram_i8_map(const GramI8Plan& p, const signed char* Wq, CUtensorMap* map, int box_frames);
@@ -78,6 +79,7 @@ struct ShrinkBuffers {
     float* part_max;
     float* part_wmax;          // [stream grid] max |W_next| written with the int8 slices (nullptr: slices off)
     int implied_first = 0;     // shrink_stream only: iteration 1 derives S0 = 0, Y0 = D / dual_norm from D (init_Y skipped)
+    int have_flat = 0;         // shrink_stream only: shrink_flat.cu is launched too and takes the iterations it can (DevState decides)
     const float* Tt = nullptr; // shrink_stream only: T regrouped per tile by project.cu; when the planes of this W exist
                                // (DevState::gram_mode == 1) the kernel skips its own projection pass and streams every tile once
 };
@@ -110,6 +112,16 @@ int make_shrink_stream_vmaps(const ShrinkStreamPlan& p, const float* Vr, const f
 int make_shrink_stream_qmap(const ShrinkStreamPlan& p, signed char* Wq, ShrinkTmaMaps* m);
 int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, ShrinkBuffers b, const DevState* st, int mode,
                          cudaStream_t stream);
+
+// ---------------------------------------------------------------- shrink_flat.cu (single-pass streamed shrink, rank <= 8, T from project.cu)
+struct ShrinkFlatPlan { int n, rows, cols, FC, NS, nchunkf, ntile_r, grid; long long ld, ntiles; size_t smem_bytes; };
+struct ShrinkFlatMaps { CUtensorMap D, S, Y, Q, VC; };
+bool make_shrink_flat_plan(int n, int rows, int cols, long long ld, int num_sms, const ShrinkStreamPlan& sp, ShrinkFlatPlan* out);
+int make_shrink_flat_maps(const ShrinkFlatPlan& p, const float* D, float* S, float* Y, signed char* Wq, long long ldq, const float* VC, int vstride,
+                          ShrinkFlatMaps* m);
+// part_*: [p.grid] partial results of this kernel (zeros when it leaves the iteration to a fallback kernel)
+int launch_shrink_flat(const ShrinkFlatPlan& p, const ShrinkFlatMaps& maps, const float* Tt, const DevState* st, int mode, double* part_zz,
+                       unsigned long long* part_nnz, float* part_max, float* part_wmax, cudaStream_t stream);
 
 // ---------------------------------------------------------------- project.cu (T = Vr^T W from the int8 digit planes)
 struct ProjectPlan { int n, NW, DEPTH, slot_bytes, grid; long long ldq; size_t smem_bytes; };

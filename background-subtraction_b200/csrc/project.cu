@@ -85,25 +85,27 @@ __device__ __forceinline__ void pj_unit(const ProjectArgs& a, const unsigned cha
             v += __shfl_xor_sync(0xffffffffu, v, 16);
             acc[k][i] = v * sc;
         }
-    // lanes 0..3 (frame lane 0) hold the totals of their 4 pixels; spread the ranks over the 8 frame lanes for the stores
-    const int bpt = (3 * a.R) / 16, bpc = a.R / 16;             // k16 blocks per tile / per tile column
+    // every lane holds the totals of its 4 pixels (xor butterfly); the ranks are spread over the 8 frame lanes for the stores.
+    // Pixel order inside a tile (shrink_stream.cu / shrink_flat.cu): position = e * NG + g for entry e = 3 c + dr of the 3x3
+    // group g, so a k16 block holds 16 consecutive groups of one entry.
+    const int NG = a.R / 3, bpt = (3 * a.R) / 16;               // groups per tile, k16 blocks per tile
     const long long tl = unit / bpt;
     const int kb = (int)(unit - tl * bpt);
     if (tl >= a.ntiles) return;
-    const int c = kb / bpc, rl0 = 16 * (kb - c * bpc) + 4 * quad;
+    const int pos0 = 16 * kb + 4 * quad;                        // 4 consecutive positions: same entry (NG % 4 == 0), groups g0 .. g0+3
+    const int e = pos0 / NG, g0 = pos0 - e * NG, c = e / 3, dr = e - 3 * c;
     const int tcx = (int)(tl / a.ntile_r), trx = (int)(tl - (long long)tcx * a.ntile_r);
-    const int j = 3 * tcx + c, row = trx * a.R + rl0;
+    const int j = 3 * tcx + c, row0 = trx * a.R + 3 * g0 + dr;
     float* tt = a.Tt + (size_t)tl * 16 * (4 * a.R);
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
         if ((k & 7) == f8 && k < r) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int rl = rl0 + i, g = rl / 3, dr = rl - 3 * g;
-                tt[(size_t)k * (4 * a.R) + g * 12 + 3 * c + dr] = acc[k][i];
+                tt[(size_t)k * (4 * a.R) + (g0 + i) * 12 + e] = acc[k][i];
+                const int row = row0 + 3 * i;
+                if (j < a.cols && row < a.rows) a.T[(size_t)k * a.ld + (long long)j * a.rows + row] = acc[k][i];
             }
-            if (j < a.cols && row < a.rows)
-                stg4(a.T + (size_t)k * a.ld + (long long)j * a.rows + row, make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]));
         }
     }
 }
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(32 * PJ_MAXW, 1) project_planes_kernel(Project
 }
 
 bool make_project_plan(int n, int R, long long ldq, int num_sms, ProjectPlan* out) {
-    if (R % 16 != 0 || ldq <= 0) return false;
+    if (R % 48 != 0 || ldq <= 0) return false;          // whole k16 blocks per entry: (R / 3) % 16 == 0
     ProjectPlan p;
     p.n = n; p.ldq = ldq;
     p.slot_bytes = 64 * n;

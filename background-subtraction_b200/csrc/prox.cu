@@ -115,10 +115,30 @@ __global__ void prox_groups_csr_kernel(const float* __restrict__ U, float* __res
     }
 }
 
+// V <- U unless the solve has already stopped (the host enqueues a few iterations ahead of the device-side stop flag: an
+// unconditional copy would overwrite the final S with the last G_S)
+__global__ void prox_copy_through_kernel(const float* __restrict__ U, float* __restrict__ V, long long total4, const DevState* st) {
+    if (st != nullptr && st->done) return;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total4; q += (long long)gridDim.x * blockDim.x)
+        stg4(V + 4 * q, ldg4_stream(U + 4 * q));
+}
+
 int launch_prox_groups_csr(const float* U, float* V, long long ld, long long m, int n, const int* gptr, const int* gidx,
                            int ngroups, float lam, const DevState* st, cudaStream_t s) {
     (void)m;
-    if (U != V) BSUB_CUDA_CHECK(cudaMemcpyAsync(V, U, sizeof(float) * (size_t)ld * n, cudaMemcpyDeviceToDevice, s));
+    if (U != V) {
+        if ((ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(U) | reinterpret_cast<uintptr_t>(V)) & 15) == 0) {
+            const long long total4 = ld * n / 4;
+            long long gb = (total4 + PX_THREADS * 4 - 1) / (PX_THREADS * 4);
+            if (gb > 148 * 8) gb = 148 * 8;
+            if (gb < 1) gb = 1;
+            prox_copy_through_kernel<<<(unsigned)gb, PX_THREADS, 0, s>>>(U, V, total4, st);
+            BSUB_CUDA_CHECK(cudaGetLastError());
+        } else {
+            if (st != nullptr) { set_error("prox_groups_csr: unaligned matrices inside a solve"); return -1; }
+            BSUB_CUDA_CHECK(cudaMemcpyAsync(V, U, sizeof(float) * (size_t)ld * n, cudaMemcpyDeviceToDevice, s));
+        }
+    }
     int gx = (ngroups + PX_THREADS - 1) / PX_THREADS;
     if (gx > 2048) gx = 2048;
     if (gx < 1) gx = 1;

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tma.cuh"
+#include "prox9.cuh"
 
 namespace bsub {
 
@@ -46,6 +47,7 @@ struct ShrinkStreamArgs {
     int kcap;                              // ranks <= kcap (= SS_KC) are handled here; larger ones by the fallback kernel
     int implied_first;                     // iteration 1 takes S = 0, Y = D / dual_norm from D instead of reading them (no init pass)
     const float* Tt;                       // [ntiles][SS_KC][4R]: T of every tile from project.cu (nullptr: always project here)
+    int have_flat;                         // shrink_flat.cu runs too: leave it the iterations it takes
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -58,30 +60,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-#define SS_CE(i, j) { const float hi_ = fmaxf(u[i], u[j]), lo_ = fminf(u[i], u[j]); u[i] = hi_; u[j] = lo_; }
-// clip level of the l1-ball projection of 9 non-negative values (25-comparator sorting network, descending)
-__device__ __forceinline__ float ss_clip_level9(const float* a_in, float z) {
-    float u[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) u[i] = a_in[i];
-    SS_CE(0, 3) SS_CE(1, 7) SS_CE(2, 5) SS_CE(4, 8)
-    SS_CE(0, 7) SS_CE(2, 4) SS_CE(3, 8) SS_CE(5, 6)
-    SS_CE(0, 2) SS_CE(1, 3) SS_CE(4, 5) SS_CE(7, 8)
-    SS_CE(1, 4) SS_CE(3, 6) SS_CE(5, 7)
-    SS_CE(0, 1) SS_CE(2, 4) SS_CE(3, 5) SS_CE(6, 8)
-    SS_CE(2, 3) SS_CE(4, 5) SS_CE(6, 7)
-    SS_CE(1, 2) SS_CE(3, 4) SS_CE(5, 6)
-    const float inv[9] = {1.f, 0.5f, 1.f / 3.f, 0.25f, 0.2f, 1.f / 6.f, 1.f / 7.f, 0.125f, 1.f / 9.f};
-    float cs = 0.f, theta = 0.f;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        cs += u[k];
-        const float t = (cs - z) * inv[k];
-        if (u[k] > t) theta = t;
-    }
-    return theta;
-}
 
 // phase A, one stage: T partial of this thread's pixel quad over its frames of the stage
 template <int KCNT>
@@ -121,7 +99,9 @@ __device__ __forceinline__ void ss_accumulate(float (&acc)[SS_KC][4], const floa
 // phase B, one 3x3 group of one frame: L from T, prox, dual update, in place in the stage
 // W of the next iteration, exactly as the next pass will form it from the stored S and Y, as 32-bit fixed point
 // q = rint(W * Q) split into four balanced base-256 digits (one byte plane each).  Stage layout per plane:
-// [k16 block of the tile][frame][16 B]  (k-block-major, see gram_i8.cu)
+// [k16 block of the tile][frame][16 B]  (k-block-major, see gram_i8.cu).  Pixel order inside a tile (the Gram is a sum over
+// pixels and does not care, project.cu and shrink_flat.cu use the same): position = e * NG + g for entry e = 3 c + dr of the
+// 3x3 group g -- the 16 groups of a 48-row tile fill one k16 block per entry.
 __device__ __forceinline__ void ss_emit_q(unsigned char* qb, int QS, int pix, int kstep, float d, float s_new, float y_new,
                                           float inv_mu_next, float Qf, float& wmax_acc) {
     const float wn = fmaf(y_new, inv_mu_next, d - s_new);
@@ -139,7 +119,7 @@ __device__ __forceinline__ void ss_emit_q(unsigned char* qb, int QS, int pix, in
 template <int KCNT>
 __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg, int tk_stride, const float* vc, int R, int P, float inv_mu,
                                          float mu_f, float lamq, int mode, double& zz_acc, unsigned int& nnz_acc, float& max_acc,
-                                         unsigned char* qb, int QS, int o0, int kstep, float inv_mu_next, float Qf, float& wmax_acc,
+                                         unsigned char* qb, int QS, int o0, int qng, int kstep, float inv_mu_next, float Qf, float& wmax_acc,
                                          int& sat_acc, bool first, double inv_dual) {
     float vv[SS_KC];
 #pragma unroll
@@ -185,7 +165,7 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
                     dsp[o] = 0.f;
                     ysp[o] = yn;
                     zl = fmaf(av[e], av[e], zl);
-                    if (qb != nullptr) ss_emit_q(qb, QS, o0 + o, kstep, dv[e], 0.f, yn, inv_mu_next, Qf, wmax_acc);
+                    if (qb != nullptr) ss_emit_q(qb, QS, e * qng + o0, kstep, dv[e], 0.f, yn, inv_mu_next, Qf, wmax_acc);
                 }
         } else {
             const float theta = ss_clip_level9(ax, lamq);
@@ -202,7 +182,7 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
                     zl = fmaf(z, z, zl);
                     nnz_acc += (sv != 0.f);
                     max_acc = fmaxf(max_acc, fabsf(sv));
-                    if (qb != nullptr) ss_emit_q(qb, QS, o0 + o, kstep, dv[e], sv, yn, inv_mu_next, Qf, wmax_acc);
+                    if (qb != nullptr) ss_emit_q(qb, QS, e * qng + o0, kstep, dv[e], sv, yn, inv_mu_next, Qf, wmax_acc);
                 }
         }
         zz_acc += (double)zl;
@@ -220,7 +200,7 @@ __device__ __forceinline__ void ss_group(float* dsp, float* ysp, const float* Tg
                 zl = fmaf(z, z, zl);
                 nnz_acc += (sv != 0.f);
                 max_acc = fmaxf(max_acc, fabsf(sv));
-                if (qb != nullptr) ss_emit_q(qb, QS, o0 + o, kstep, dv[e], sv, yn, inv_mu_next, Qf, wmax_acc);
+                if (qb != nullptr) ss_emit_q(qb, QS, e * qng + o0, kstep, dv[e], sv, yn, inv_mu_next, Qf, wmax_acc);
             }
         zz_acc += (double)zl;
     } else {                                              // SHRINK_SPILL: hand G_S to a separate prox
@@ -266,7 +246,7 @@ __device__ __forceinline__ void ss_phase_b(const ShrinkStreamArgs& a, float* rin
             float* ysp = b + (size_t)2 * BS + (size_t)f * P + 3 * g;
             unsigned char* qb = wq ? (reinterpret_cast<unsigned char*>(b + (size_t)BS) + (size_t)f * 16) : nullptr;
             ss_group<KCNT>(dsp, ysp, Tp + 12 * g, 12 * NG, Vst_all + (size_t)s * VSS + f * SS_KC, R, P, inv_mu, mu_f, lamq, a.mode, zz_acc, nnz_acc,
-                           max_acc, qb, QS, 3 * g, FC * 16, inv_mu_next, Qf, wmax_acc, sat_acc, first, inv_dual);
+                           max_acc, qb, QS, g, NG, FC * 16, inv_mu_next, Qf, wmax_acc, sat_acc, first, inv_dual);
         }
         fence_proxy_async_smem();                   // my writes -> visible to the storer's TMA stores
         __syncwarp();
@@ -287,6 +267,10 @@ shrink_stream_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_cons
     const DevState* st = a.st;
     if (st->done) return;
     const int r = st->svp;
+    if (a.have_flat && shrink_flat_takes(st)) {            // the single-pass kernel (shrink_flat.cu) does this iteration
+        if (threadIdx.x == 0) { a.part_zz[blockIdx.x] = 0.0; a.part_nnz[blockIdx.x] = 0ull; a.part_max[blockIdx.x] = 0.f; if (a.part_wmax != nullptr) a.part_wmax[blockIdx.x] = 0.f; }
+        return;
+    }
     if (r > a.kcap) {                                      // large ranks take the fallback kernel launched next
         if (threadIdx.x == 0) { a.part_zz[blockIdx.x] = 0.0; a.part_nnz[blockIdx.x] = 0ull; a.part_max[blockIdx.x] = 0.f; if (a.part_wmax != nullptr) a.part_wmax[blockIdx.x] = -1.f; }
         return;
@@ -599,6 +583,7 @@ int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, S
     a.part_max = b.part_max; a.part_wmax = b.part_wmax; a.mode = mode;
     a.wq = (maps.has_Q && b.part_wmax != nullptr) ? 1 : 0; a.Pq = p.P; a.implied_first = b.implied_first; a.kcap = p.kcap;
     a.Tt = (mode != SHRINK_SPILL) ? b.Tt : nullptr;
+    a.have_flat = (mode != SHRINK_SPILL) ? b.have_flat : 0;
     a.QS = (int)(((size_t)p.FC * p.P + 127) / 128 * 128);
     if (p.NCW == 16) return launch_ss<16, 0, 0>(p, maps, a, mode, stream);
     if (p.R == 48 && p.FC == 28) return launch_ss<8, 48, 28>(p, maps, a, mode, stream);

@@ -55,6 +55,7 @@ struct bsub_solver {
     int4* gi_info = nullptr; int* gi_blkn = nullptr; int gi_ncta = 0; float* part_wmax = nullptr;
     // T = Vr^T W from the digit planes (project.cu): lets the streamed shrink kernel read every tile once
     bool use_proj = false; ProjectPlan pjp; float* Tt = nullptr;
+    bool use_flat = false, sfmaps_ready = false; ShrinkFlatPlan sfp; ShrinkFlatMaps sfmaps;     // single-pass shrink (shrink_flat.cu)
     float* tpart = nullptr; double* part_zz = nullptr; unsigned long long* part_nnz = nullptr;
     float* part_max = nullptr;
     int shrink_mode = SHRINK_FLAT3;
@@ -218,7 +219,7 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
         s->use_stream = s->use_tma && (getenv("BSUB_NO_STREAM") == nullptr) &&
                         make_shrink_stream_plan(s->n, rows, cols, s->ld, s->num_sms, cfg->tile_rows, &s->ssp);
         ALLOC(s->tpart, sizeof(float) * std::max(s->sp.tpart_floats, s->use_tma ? s->stp.tpart_floats : (size_t)0));
-        int nparts = std::max(std::max(s->sp.nparts, (s->use_tma ? s->stp.nparts : 0) + (s->use_stream ? s->ssp.nparts : 0)), s->num_sms * 8);
+        int nparts = std::max(std::max(s->sp.nparts, (s->use_tma ? s->stp.nparts : 0) + (s->use_stream ? s->ssp.nparts : 0) + s->num_sms), s->num_sms * 8);
         ALLOC(s->part_zz, sizeof(double) * nparts); ALLOC(s->part_nnz, sizeof(unsigned long long) * nparts);
         ALLOC(s->part_max, sizeof(float) * nparts);
         cudaMemset(s->part_zz, 0, sizeof(double) * nparts); cudaMemset(s->part_nnz, 0, sizeof(unsigned long long) * nparts);
@@ -228,6 +229,7 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
         if (s->use_i8) {
             const long long ldq = shrink_stream_ldq(s->ssp);
             s->gip = make_gram_i8_plan(s->n, ldq, s->num_sms);
+            s->gip.m_real = (getenv("BSUB_NO_GRAM_BIAS") == nullptr) ? s->m : 0;
             std::vector<int4> info; std::vector<int> blkn;
             fill_gram_i8_tables(s->gip, info, blkn);
             s->gi_ncta = (int)info.size();
@@ -236,10 +238,10 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
             ALLOC(s->Gint, sizeof(unsigned long long) * (size_t)s->gip.nblk * 128 * s->gip.nblk * 128);
             ALLOC(s->gi_info, sizeof(int4) * info.size());
             ALLOC(s->gi_blkn, sizeof(int) * blkn.size());
-            ALLOC(s->part_wmax, sizeof(float) * s->ssp.grid);
+            ALLOC(s->part_wmax, sizeof(float) * (s->ssp.grid + s->num_sms));
             cudaMemcpy(s->gi_info, info.data(), sizeof(int4) * info.size(), cudaMemcpyHostToDevice);
             cudaMemcpy(s->gi_blkn, blkn.data(), sizeof(int) * blkn.size(), cudaMemcpyHostToDevice);
-            cudaMemset(s->part_wmax, 0, sizeof(float) * s->ssp.grid);
+            cudaMemset(s->part_wmax, 0, sizeof(float) * (s->ssp.grid + s->num_sms));
             if (make_gram_i8_map(s->gip, s->Wq, &s->gimap, 128) != 0) { rc = -1; break; }
             if (make_gram_i8_map(s->gip, s->Wq, &s->gimap_last, gram_i8_last_block_n(s->gip)) != 0) { rc = -1; break; }
             s->use_proj = (getenv("BSUB_NO_PROJ") == nullptr) && make_project_plan(s->n, s->ssp.R, ldq, s->num_sms, &s->pjp);
@@ -247,6 +249,7 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
                 const size_t tt = sizeof(float) * (size_t)s->ssp.ntiles * 16 * 4 * s->ssp.R;
                 ALLOC(s->Tt, tt);
                 cudaMemset(s->Tt, 0, tt);
+                s->use_flat = (getenv("BSUB_NO_FLAT") == nullptr) && make_shrink_flat_plan(s->n, s->ssp.rows, s->ssp.cols, s->ld, s->num_sms, s->ssp, &s->sfp);
             }
         }
         for (int i = 0; i <= kRunAhead; ++i)
@@ -545,7 +548,9 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
     b.part_wmax = s->use_i8 ? s->part_wmax : nullptr;
     b.implied_first = s->implied_first ? 1 : 0;
     const bool proj = s->use_proj && s->use_stream && s->use_i8 && s->shrink_mode != SHRINK_SPILL;
+    const bool flat = proj && s->use_flat;
     b.Tt = proj ? s->Tt : nullptr;
+    b.have_flat = flat ? 1 : 0;
     int nparts = s->sp.nparts;
     if (s->use_tma) {
         if (!s->stmaps_ready) {
@@ -562,6 +567,15 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
                                       s->ssp.ntile_r, s->ssp.ntiles, s->ssp.kcap, s->st, st));
             RET_IF(launch_shrink_stream(s->ssp, s->ssmaps, b, s->st, s->shrink_mode, st));
             off = s->ssp.nparts; min_rank = s->ssp.kcap + 1;
+            if (flat) {               // rank <= 8 from the second iteration on: the single-pass kernel (the one above then exits at once)
+                if (!s->sfmaps_ready) {
+                    RET_IF(make_shrink_flat_maps(s->sfp, s->D, s->S, s->Y, s->Wq, s->gip.ldq, s->eb.VC, s->eb.vstride, &s->sfmaps));
+                    s->sfmaps_ready = true;
+                }
+                RET_IF(launch_shrink_flat(s->sfp, s->sfmaps, s->Tt, s->st, s->shrink_mode, s->part_zz + off, s->part_nnz + off, s->part_max + off,
+                                          s->part_wmax + s->ssp.grid, st));
+                off += s->sfp.grid;
+            }
         }
         ShrinkBuffers b2 = b;
         b2.part_zz += off; b2.part_nnz += off; b2.part_max += off;
@@ -593,7 +607,8 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
                                   s->part_nnz, s->part_max, nparts, st));
     }
     RET_IF(launch_control_post(s->st, s->part_zz, s->part_nnz, s->part_max, nparts, s->comm_sum + (size_t)s->npad * s->npad, s->log,
-                               s->mirror_dev, 1, (s->use_i8 && s->use_stream) ? s->part_wmax : nullptr, s->use_i8 ? s->ssp.grid : 0, st));
+                               s->mirror_dev, 1 | 4, (s->use_i8 && s->use_stream) ? s->part_wmax : nullptr,
+                               s->use_i8 ? s->ssp.grid + (flat ? s->sfp.grid : 0) : 0, st));
     return 0;
 }
 
@@ -719,7 +734,7 @@ int bsub_debug_info(bsub_solver* s, int32_t* o) {
     o[0] = s->use_tma; o[1] = s->use_stream; o[2] = s->use_i8; o[3] = s->use_stream ? s->ssp.R : 0; o[4] = s->use_stream ? s->ssp.FC : 0;
     o[5] = s->use_stream ? s->ssp.NS : 0; o[6] = s->gp.ntype; o[7] = s->gp.kc; o[8] = s->ep.C; o[9] = s->use_tma ? s->stp.R : s->sp.R;
     o[10] = s->use_tma ? s->stp.Cf : s->sp.Cf; o[11] = (int32_t)s->ld; o[12] = s->use_proj ? 1 : 0; o[13] = s->use_proj ? s->pjp.NW : 0;
-    o[14] = s->use_proj ? s->pjp.DEPTH : 0; o[15] = 0;
+    o[14] = s->use_proj ? s->pjp.DEPTH : 0; o[15] = s->use_flat ? s->sfp.NS : 0;
     return 0;
 }
 
@@ -737,7 +752,7 @@ int bsub_debug_counters(bsub_solver* s, int64_t* out8) {
     CK(cudaMemcpy(&h, s->st, sizeof(h), cudaMemcpyDeviceToHost));
     memset(out8, 0, sizeof(int64_t) * 8);
     out8[0] = h.eig_fast_iters; out8[1] = h.eig_p; out8[2] = h.eig_info & 0xff; out8[3] = (int64_t)(h.eig_gb * 1e6);
-    out8[4] = h.gram_mode; out8[5] = h.wq_saturated;
+    out8[4] = h.gram_mode; out8[5] = h.wq_saturated; out8[6] = h.force_dmma; out8[7] = (int64_t)(h.gram_err * 1e6);
     return 0;
 }
 

@@ -2,11 +2,16 @@
 
 The path shards by image columns (pixel index p = j*rows + i, so a block of whole columns is a contiguous pixel
 range of every frame): rank r owns the column triples [t0, t1) so that no 3x3 tile straddles two ranks
-(SURVEY.md section 8e).  Per ALM iteration the only exchanges are
-  * all-reduce(SUM) of the frames x frames fp64 Gram partial (+ nothing else in that message),
-  * all-reduce(SUM) of 3 doubles after the shrink pass (sum Z^2, ||S||_0, -),
-plus at init all-reduce(SUM) Gram(D), all-reduce(MAX) of the row-sum maximum, and at the end all-reduce(MAX/SUM) of
-the foreground-mask statistics.  The eigensolve is replicated (bit-identical inputs after the all-reduce), so no
+(SURVEY.md section 8e).  Per ALM iteration there is ONE exchange: an all-reduce(SUM) of a single buffer that holds the
+frames x frames fp64 Gram partial of iteration k+1 followed by the 4 scalars of iteration k (sum Z^2, ||S||_0, ...).  The
+shrink pass of iteration k advances mu itself (local data only), the Gram of k+1 is enqueued right behind it, and the
+residual / stop test of iteration k is evaluated after the joint message has arrived; an iteration that turns out to be
+the last one has then cost one surplus Gram pass.  At init: all-reduce(SUM) Gram(D) and all-reduce(MAX) of the row-sum
+maximum; at the end all-reduce(MAX), then (SUM) of the foreground-mask statistics.
+The stop decision is identical on every rank by construction: a rank leaves the loop at the first loop index `it` for
+which the device-written status says "done at iteration k" with k <= it - run_ahead, where the fence of iteration
+it - run_ahead has completed -- never on a flag it merely happened to see early (ranks that left at different indices
+would issue different numbers of collectives).  The eigensolve is replicated (bit-identical inputs after the all-reduce), so no
 broadcast is needed.  The same driver runs world_size == 1 without any collective.
 
 The numerical work is done by a *step solver* object; the product one is `CudaStepSolver` (libbsub_b200.so through
@@ -99,15 +104,27 @@ class CudaStepSolver:
     def tail_view(self):
         return self.sum_buf[self.ngram:self.ngram + 4]
 
+    def sum_view(self):
+        """Gram partial + the 4 scalars of the previous iteration (+ the error bound of the int8 Gram in slot 8): one
+        all-reduce message per ALM iteration."""
+        return self.sum_buf[:self.ngram + 9]
+
     def mask_tail_view(self):
         return self.sum_buf[self.ngram + 4:self.ngram + 8]
 
     def max_view(self):
         return self.max_buf
 
+    needs_fence = True          # the status word is written by the device: only look at it behind a fence
+
     def done(self):
         """Non-blocking look at the device-written status word."""
         return self.dec.poll().done != 0
+
+    def done_by(self, k):
+        """True iff the solve stopped at an iteration <= k (the caller has fenced iteration k)."""
+        st = self.dec.poll()
+        return st.done != 0 and st.iter <= k
 
     def wait_iter(self, k):
         pass
@@ -133,8 +150,11 @@ class ShardedLSD:
     hooks[name](phase) with phase in {'begin', 'end'} around 'gram', 'solve', 'shrink' for timing."""
 
     def __init__(self, solver, comm, run_ahead=3, max_iter=500, fence=None):
-        self.s, self.comm, self.run_ahead, self.max_iter = solver, comm, run_ahead, max_iter
-        self.fence = fence            # callable(iteration) -> object with .synchronize(); bounds host run-ahead
+        self.s, self.comm, self.run_ahead, self.max_iter = solver, comm, max(1, int(run_ahead)), max_iter
+        # callable(iteration) -> object with .synchronize(); bounds host run-ahead.  Mandatory for a device-side solver.
+        if fence is None and getattr(solver, "needs_fence", False):
+            fence = cuda_fence
+        self.fence = fence
         self.iters_enqueued = 0
 
     def solve(self, hooks=None):
@@ -146,15 +166,21 @@ class ShardedLSD:
         s.init_finish()
         fences = []
         self.iters_enqueued = 0
-        for it in range(self.max_iter):
+        # body `it` (0-based): Gram of iteration it+1 | all-reduce(Gram + scalars of iteration it) | stop test of iteration it |
+        # eigensolve and shrink of iteration it+1.  One more body than iterations: the last one only closes iteration max_iter.
+        for it in range(self.max_iter + 1 + self.run_ahead):
             if it >= self.run_ahead:
+                closed = it - self.run_ahead            # iterations whose stop test is known to have run
                 if self.fence is not None:
-                    fences[it - self.run_ahead].synchronize()
-                if s.done():
+                    fences[closed].synchronize()
+                if closed >= 1 and s.done_by(closed):
                     break
-            hk('gram', 'begin'); s.gram(); comm.all_reduce_sum(s.gram_view()); hk('gram', 'end')
+            hk('gram', 'begin'); s.gram(); comm.all_reduce_sum(s.sum_view())
+            if it >= 1:
+                s.finish_iter()
+            hk('gram', 'end')
             hk('solve', 'begin'); s.solve(); hk('solve', 'end')
-            hk('shrink', 'begin'); s.shrink(); comm.all_reduce_sum(s.tail_view()); s.finish_iter(); hk('shrink', 'end')
+            hk('shrink', 'begin'); s.shrink(); hk('shrink', 'end')
             if self.fence is not None:
                 fences.append(self.fence(it))
             self.iters_enqueued += 1

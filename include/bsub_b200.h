@@ -143,7 +143,8 @@ int bsub_debug_eig_cycles(bsub_solver* s, int64_t* out16);
 int bsub_debug_info(bsub_solver* s, int32_t* out16);   /* ..., [12] plane projection on, [13] its warps, [14] its slot depth */
 /* diagnostics: [0] iterations of the last solve whose eigenpairs came from the warm-started subspace path (eig.cu), [1] vectors
  * kept for the next warm start, [2] subspace steps of the last call, [3] 1e6 * last certificate ||G - X theta X^T||_F mu^2,
- * [4] Gram mode of the next iteration (0 fp64 DMMA, 1 int8 tcgen05), [5] last digit pass saturated */
+ * [4] Gram mode of the next iteration (0 fp64 DMMA, 1 int8 tcgen05), [5] last digit pass saturated, [6] the solve has switched
+ * to the fp64 Gram for accuracy, [7] 1e6 * bound of the int8 Gram's truncation error relative to (1/mu)^2 */
 int bsub_debug_counters(bsub_solver* s, int64_t* out8);
 /* foreground_mask(D, L, S, sigmas) of utils.py:139-149 on the solver's own D, L, S; mask uint8[n][m] on the host */
 int bsub_mask_stats_local(bsub_solver* s, int phase /*0: max|S|, 1: count/sum/sumsq*/, void* stream);

@@ -23,6 +23,7 @@ class NumpyStepSolver:
     # -- views used by the driver's all-reduces
     def gram_view(self): return self.sum_buf[:self.ngram]
     def tail_view(self): return self.sum_buf[self.ngram:self.ngram + 4]
+    def sum_view(self): return self.sum_buf[:self.ngram + 9]
     def mask_tail_view(self): return self.sum_buf[self.ngram + 4:self.ngram + 8]
     def max_view(self): return self.max_buf
 
@@ -65,16 +66,19 @@ class NumpyStepSolver:
         self.Y = self.Y + self.mu * Z
         self.sum_buf[self.ngram:self.ngram + 4] = torch.tensor([float((Z * Z).sum()), float(np.count_nonzero(self.S)), 0.0, 0.0],
                                                               dtype=torch.float64)
+        self.mu *= self.rho                      # like the device solver: mu advances with the shrink pass (local data only)
 
     def finish_iter(self):
+        """Stop test of the iteration whose scalars arrived with the last all-reduce (the Gram of the NEXT iteration has
+        already been formed by then, exactly as in the device solver)."""
         if self.done_flag: return
         err = float(np.sqrt(float(self.sum_buf[self.ngram]) / self.normD2))
         self.log.append((self.iter, self.svp, err))
-        self.mu *= self.rho
         if err < self.tol: self.done_flag, self.converged = 1, True
         elif self.iter >= self.max_iter: self.done_flag = 2
 
     def done(self): return self.done_flag != 0
+    def done_by(self, k): return self.done_flag != 0 and self.iter <= k
     def finalize(self): pass
 
     def mask_stats(self, phase):
