@@ -21,7 +21,7 @@ class Config(ctypes.Structure):
                 ("use_sv_prediction", ctypes.c_int32), ("break_on_rank0", ctypes.c_int32),
                 ("non_block_lambda_scale", ctypes.c_double), ("d_global", ctypes.c_int32),
                 ("graph_max_sweeps", ctypes.c_int32), ("graph_tol", ctypes.c_double), ("tile_rows", ctypes.c_int32),
-                ("cluster_frames", ctypes.c_int32), ("reserved", ctypes.c_int32 * 6)]
+                ("cluster_frames", ctypes.c_int32), ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32 * 5)]
 
 
 class Status(ctypes.Structure):
@@ -36,6 +36,7 @@ class IterLog(ctypes.Structure):
 
 
 PROX_FLAT_LINF, PROX_GRAPH_LINF, PROX_BLOCK_L2, PROX_L1, PROX_GRAPH_CENTER_BG = 0, 1, 2, 3, 4
+FLAG_ALWAYS_STORE_S = 1
 
 # every symbol include/bsub_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -54,11 +55,13 @@ SIGNATURES = {
     "bsub_load_D_f32_dev": (ctypes.c_int, [vp, vp, ctypes.c_int64, vp]),
     "bsub_load_u8_host": (ctypes.c_int, [vp, vp, c_double_p, c_double_p, c_double_p, ctypes.c_int, vp]),
     "bsub_run": (ctypes.c_int, [vp, vp]),
+    "bsub_set_always_store_S": (ctypes.c_int, [vp, ctypes.c_int]),
     "bsub_comm_buffers": (ctypes.c_int, [vp, ctypes.POINTER(vp), c_int64_p, ctypes.POINTER(vp), c_int64_p]),
     "bsub_step_init_local": (ctypes.c_int, [vp, vp]),
     "bsub_step_init_finish": (ctypes.c_int, [vp, vp]),
     "bsub_step_gram": (ctypes.c_int, [vp, vp]),
     "bsub_step_solve": (ctypes.c_int, [vp, vp]),
+    "bsub_step_project": (ctypes.c_int, [vp, vp]),
     "bsub_step_shrink": (ctypes.c_int, [vp, vp]),
     "bsub_step_finish_iter": (ctypes.c_int, [vp, vp]),
     "bsub_poll": (ctypes.c_int, [vp, ctypes.POINTER(Status)]),

@@ -398,7 +398,7 @@ class Decomposition:
         fn = {'L': self.lib.bsub_get_L_f32_dev, 'S': self.lib.bsub_get_S_f32_dev, 'D': self.lib.bsub_get_D_f32_dev,
               'Y': self.lib.bsub_get_Y_f32_dev}[which]
         p, ld = ctypes.c_void_p(), ctypes.c_int64(0)
-        if which == 'L':
+        if which in ('L', 'S'):
             self.finalize()
         C.check(fn(self.h, ctypes.byref(p), ctypes.byref(ld)))
         return _wrap_device(p.value, (self.n, ld.value), torch.float32)[:, :self.m]
@@ -422,7 +422,7 @@ def _wrap_device(ptr, shape, dtype):
 
 def make_config(m, n, prox, rows=0, cols=0, delta=10, mu_scale=12.5, rho=1.6, tol=1e-7, max_iter=500, sv0=10,
                 use_sv_prediction=True, break_on_rank0=False, m_global=0, d_global=0, tile_rows=0, cluster_frames=0,
-                graph_max_sweeps=0, graph_tol=0.0):
+                graph_max_sweeps=0, graph_tol=0.0, flags=0):
     cfg = C.Config()
     C.load().bsub_default_config(ctypes.byref(cfg))
     cfg.m, cfg.n, cfg.prox, cfg.rows, cfg.cols = int(m), int(n), int(prox), int(rows), int(cols)
@@ -432,6 +432,7 @@ def make_config(m, n, prox, rows=0, cols=0, delta=10, mu_scale=12.5, rho=1.6, to
     cfg.m_global, cfg.d_global = int(m_global), int(d_global)
     cfg.tile_rows, cfg.cluster_frames = int(tile_rows), int(cluster_frames)
     cfg.graph_max_sweeps, cfg.graph_tol = int(graph_max_sweeps), float(graph_tol)
+    cfg.flags = int(flags)
     return cfg
 
 

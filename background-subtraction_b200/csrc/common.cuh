@@ -56,6 +56,9 @@ struct DevState {
     // against the threshold (1/mu)^2, the rest of the solve uses the fp64 Gram
     double gram_err;        // last bound seen by the eigensolver, relative to (1/mu)^2
     int force_dmma;
+    // shrink_flat.cu skips the store of S in iterations that cannot be the last one (S is not part of the recursion there: it
+    // can be rebuilt from D, Y and the digit planes of W_next).  s_stale: S in HBM is older than the state.
+    int s_stale, s_stale_next;
 };
 
 // which iterations the single-pass kernel of shrink_flat.cu takes (evaluated identically by it and by the kernels it relieves):

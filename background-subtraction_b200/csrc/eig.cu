@@ -456,7 +456,11 @@ __device__ int eig_fast_path(const EigArgs& a, DevState* st, int K, double mu, d
     }
     if (!converged) return 0;
 
-    // ---- certificate: gb = || G - X diag(theta) X^T ||_F (rows dealt as in the matvec) and the orthonormality defect of X
+    // ---- certificate: gb = || G - X diag(theta) X^T + s (I - X X^T) ||_F (rows dealt as in the matvec) and the orthonormality
+    // defect of X.  s >= 0 is the known downward bias of the int8 Gram on everything outside the leading pairs (half of the bound
+    // in the error slot, see gram_i8.cu): the deflated matrix is re-centred before its norm is taken, and
+    //     lambda_{p+1}(G) <= lambda_max(G - X theta X^T) <= gb - s.
+    const double sshift = 0.5 * a.G[(size_t)a.npad * a.npad + 8];
     {
         const int row0 = c * L.RB, nrows = max(0, min(n, row0 + L.RB) - row0);
         const int rg = warp % L.RG, jc = warp / L.RG, rl = rg * 32 + lane, i = row0 + rl;
@@ -464,10 +468,10 @@ __device__ int eig_fast_path(const EigArgs& a, DevState* st, int K, double mu, d
         if (jc < L.NJ && rl < nrows) {
             double xt[EIG_PMAX];
 #pragma unroll
-            for (int k = 0; k < EIG_PMAX; ++k) xt[k] = (k < p && th[k] > 0.0) ? th[k] * Xs[(size_t)i * PM + k] : 0.0;
+            for (int k = 0; k < EIG_PMAX; ++k) xt[k] = (k < p && th[k] > 0.0) ? (th[k] + sshift) * Xs[(size_t)i * PM + k] : 0.0;
             const int j1 = min(n, (jc + 1) * L.JW);
             for (int j = jc * L.JW; j < j1; ++j) {
-                double g = __ldg(a.G + (size_t)j * a.npad + i);
+                double g = __ldg(a.G + (size_t)j * a.npad + i) + ((i == j) ? sshift : 0.0);
                 const double* xr = Xs + (size_t)j * PM;
 #pragma unroll
                 for (int k = 0; k < EIG_PMAX; ++k) if (k < p) g = fma(-xt[k], xr[k], g);
@@ -482,12 +486,12 @@ __device__ int eig_fast_path(const EigArgs& a, DevState* st, int K, double mu, d
     if (tid == 0) {
         double gb2 = 0.0;
         for (int q = 0; q < C; ++q) gb2 += gbp[q];
-        const double gb = sqrt(gb2);
+        const double gb = fmax(sqrt(gb2) - sshift, 0.0);
         double orth = 0.0;
         for (int r = 0; r < p; ++r)
             for (int cc = 0; cc < p; ++cc) orth = fmax(orth, fabs(Ts[r * PM + cc] - (r == cc ? 1.0 : 0.0)));
         const double slack = (8.0 * n * DBL_EPSILON + 2.0 * orth) * th[0];
-        int ok = (gb * (1.0 + 1e-6) + slack < tau) && (gb == gb);
+        int ok = (gb * (1.0 + 1e-6) + slack < tau) && (gb2 == gb2);
         for (int k = 0; k < p; ++k) {
             if (th[k] > 0.5 * tau) { if (fabs(th[k] - tau) <= fmax(4.0 * res[k], 1e-13 * th[0])) ok = 0; }   // knife edge: let the full path decide
             else if (!(th[k] + gb + slack < tau)) ok = 0;                                                    // unconverged pair must be certainly below

@@ -106,6 +106,7 @@ __global__ void control_post_kernel(DevState* st, const double* part_zz, const u
             // this iteration travel in the same all-reduce message as the next Gram.
             st->mu_iter = st->mu;
             st->mu = fmin(st->mu * st->rho, st->mu * 1e7);
+            st->s_stale = st->s_stale_next; st->s_stale_next = 0;      // did this iteration's shrink pass leave S in HBM untouched?
             if (st->use_i8) {
                 const double wm = st->wm_local;
                 if (wm >= 0.0 && wm < 1.0e38 && wm > 0.0) {          // slices written, nothing clipped
@@ -118,6 +119,9 @@ __global__ void control_post_kernel(DevState* st, const double* part_zz, const u
                     if (wm >= 1.0e38) st->wq_scale_next = st->wq_scale_next * 16.0;
                 }
                 if (st->force_dmma) st->gram_mode = 0;            // the int8 Gram has become too coarse for the shrinking threshold (eig.cu)
+                // a clipped digit pass leaves neither valid planes nor (if the store was skipped) a current S: the host restarts the
+                // solve with S stored in every iteration (solver.cu, bsub_run)
+                if (st->wq_saturated && st->s_stale) st->done = 5;
             }
         }
         if (phase & 2) {

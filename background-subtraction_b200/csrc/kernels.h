@@ -120,8 +120,11 @@ bool make_shrink_flat_plan(int n, int rows, int cols, long long ld, int num_sms,
 int make_shrink_flat_maps(const ShrinkFlatPlan& p, const float* D, float* S, float* Y, signed char* Wq, long long ldq, const float* VC, int vstride,
                           ShrinkFlatMaps* m);
 // part_*: [p.grid] partial results of this kernel (zeros when it leaves the iteration to a fallback kernel)
-int launch_shrink_flat(const ShrinkFlatPlan& p, const ShrinkFlatMaps& maps, const float* Tt, const DevState* st, int mode, double* part_zz,
+int launch_shrink_flat(const ShrinkFlatPlan& p, const ShrinkFlatMaps& maps, const float* Tt, DevState* st, int mode, int force_S, double* part_zz,
                        unsigned long long* part_nnz, float* part_max, float* part_wmax, cudaStream_t stream);
+// S <- D + Y/mu - W_q from the digit planes when DevState::s_stale says the last passes skipped the store of S
+int launch_rebuild_S(const ShrinkFlatPlan& p, const float* D, const float* Y, float* S, const signed char* Wq, long long ldq, DevState* st,
+                     int min_rank, cudaStream_t stream);
 
 // ---------------------------------------------------------------- project.cu (T = Vr^T W from the int8 digit planes)
 struct ProjectPlan { int n, NW, DEPTH, slot_bytes, grid; long long ldq; size_t smem_bytes; };

@@ -21,7 +21,7 @@
 
 namespace bsub {
 
-constexpr int PJ_MAXW = 8;
+constexpr int PJ_MAXW = 12;
 
 struct ProjectArgs {
     const signed char* Wq; long long ldq; int n;
@@ -45,12 +45,7 @@ __device__ __forceinline__ void pj_unit(const ProjectArgs& a, const unsigned cha
 #pragma unroll
     for (int k = 0; k < KC; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
     const size_t pstride = (size_t)n * 16;
-    for (int f = f8; f < n; f += 8) {
-        const unsigned char* p = slot + (size_t)f * 16 + quad * 4;
-        const unsigned int a0 = *reinterpret_cast<const unsigned int*>(p);
-        const unsigned int a1 = *reinterpret_cast<const unsigned int*>(p + pstride);
-        const unsigned int a2 = *reinterpret_cast<const unsigned int*>(p + 2 * pstride);
-        const unsigned int a3 = *reinterpret_cast<const unsigned int*>(p + 3 * pstride);
+    auto one_frame = [&](int f, unsigned int a0, unsigned int a1, unsigned int a2, unsigned int a3) {
         // 4 x 4 byte transpose: word i of the result holds the four digits of pixel i (digit k = byte k)
         const unsigned int t0 = __byte_perm(a0, a1, 0x5140), t1 = __byte_perm(a2, a3, 0x5140);
         const unsigned int t2 = __byte_perm(a0, a1, 0x7362), t3 = __byte_perm(a2, a3, 0x7362);
@@ -74,6 +69,21 @@ __device__ __forceinline__ void pj_unit(const ProjectArgs& a, const unsigned cha
                 acc[k][2] = fmaf(vv[kk], q[2], acc[k][2]); acc[k][3] = fmaf(vv[kk], q[3], acc[k][3]);
             }
         }
+    };
+    int f = f8;
+    for (; f + 8 < n; f += 16) {                       // two frames per trip: eight independent loads in flight
+        const unsigned char* p = slot + (size_t)f * 16 + quad * 4;
+        const unsigned int a0 = *reinterpret_cast<const unsigned int*>(p), b0 = *reinterpret_cast<const unsigned int*>(p + 128);
+        const unsigned int a1 = *reinterpret_cast<const unsigned int*>(p + pstride), b1 = *reinterpret_cast<const unsigned int*>(p + pstride + 128);
+        const unsigned int a2 = *reinterpret_cast<const unsigned int*>(p + 2 * pstride), b2 = *reinterpret_cast<const unsigned int*>(p + 2 * pstride + 128);
+        const unsigned int a3 = *reinterpret_cast<const unsigned int*>(p + 3 * pstride), b3 = *reinterpret_cast<const unsigned int*>(p + 3 * pstride + 128);
+        one_frame(f, a0, a1, a2, a3);
+        one_frame(f + 8, b0, b1, b2, b3);
+    }
+    if (f < n) {
+        const unsigned char* p = slot + (size_t)f * 16 + quad * 4;
+        one_frame(f, *reinterpret_cast<const unsigned int*>(p), *reinterpret_cast<const unsigned int*>(p + pstride),
+                  *reinterpret_cast<const unsigned int*>(p + 2 * pstride), *reinterpret_cast<const unsigned int*>(p + 3 * pstride));
     }
 #pragma unroll
     for (int k = 0; k < KC; ++k)
@@ -172,8 +182,11 @@ bool make_project_plan(int n, int R, long long ldq, int num_sms, ProjectPlan* ou
     const size_t cap = 225 * 1024;
     if (vs + (size_t)p.slot_bytes > cap) return false;
     const int nslots = (int)((cap - vs) / p.slot_bytes);
-    if (nslots >= 4) { p.DEPTH = 2; p.NW = std::min(PJ_MAXW, nslots / 2); }
-    else { p.DEPTH = 1; p.NW = nslots; }
+    // the per-block arithmetic (~2400 warp instructions for n = 300) outweighs the load: many warps with one slot each beat few
+    // warps with a prefetch slot; two slots per warp only when shared memory holds them for a full set of warps
+    if (nslots >= 2 * PJ_MAXW) { p.DEPTH = 2; p.NW = PJ_MAXW; }
+    else { p.DEPTH = 1; p.NW = std::min(PJ_MAXW, nslots); }
+    if (const char* e = getenv("BSUB_PROJ_WARPS")) { const int w = atoi(e); if (w >= 1 && w <= PJ_MAXW && w * p.DEPTH <= nslots) p.NW = w; }
     p.smem_bytes = vs + (size_t)p.NW * p.DEPTH * p.slot_bytes;
     const long long nunits = ldq / 16;
     p.grid = (int)std::max<long long>(1, std::min<long long>(num_sms, (nunits + p.NW - 1) / p.NW));

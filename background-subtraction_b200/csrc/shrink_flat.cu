@@ -37,6 +37,8 @@ struct ShrinkFlatArgs {
     const float* Tt;                       // [ntiles][16][4R] from project.cu
     int n, rows, cols, FC, NS, nchunkf, ntile_r; long long ntiles;
     const DevState* st;
+    int* s_stale_next;                     // &DevState::s_stale_next (set when this launch leaves S in HBM untouched)
+    int force_S;                           // always store S (pixel-sharded drivers, restart after a saturated digit pass)
     double* part_zz; unsigned long long* part_nnz; float* part_max; float* part_wmax;
     int mode;
     int probe;                             // BSUB_FLAT_PROBE (measurement only, results are wrong): 1 = data movement without compute
@@ -201,6 +203,12 @@ shrink_flat_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_consta
     const int r = st->svp;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int FC = a.FC, NS = a.NS, ncf = a.nchunkf;
+    // S is an output, not a state variable of this pass (G_S needs D, L and Y only), and it can be rebuilt from D, Y and the
+    // digit planes of W_next = D - S + Y/mu_next (rebuild_S_kernel).  It is stored when this iteration may be the last one
+    // (the residual of the previous iteration is within 8x of the tolerance, or max_iter is reached), when the next Gram
+    // will read it (fp64 Gram), or when the caller insists; otherwise 4 of the 20 bytes per element stay on the chip.
+    const bool write_S = a.force_S || st->force_dmma || !(st->err > 8.0 * st->tol) || st->iter >= st->max_iter;
+    if (!write_S && blockIdx.x == 0 && threadIdx.x == 0) *a.s_stale_next = 1;
     const double mu_d = st->mu;
     SfScal sc;
     sc.inv_mu = (float)(1.0 / mu_d); sc.mu_f = (float)mu_d; sc.lamq = (float)(st->lambda / mu_d);
@@ -269,7 +277,7 @@ shrink_flat_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_consta
                     const int s = (int)(q % NS);
                     mbar_wait(&done[s], (uint32_t)((q / NS) & 1));
                     unsigned char* b = ring + (size_t)s * stage_bytes;
-                    tma_store_3d_hint(&mapS, b, i0, j0, c * FC, pol);
+                    if (write_S) tma_store_3d_hint(&mapS, b, i0, j0, c * FC, pol);
                     tma_store_3d_hint(&mapY, b + slot, i0, j0, c * FC, pol);
                     for (int sl = 0; sl < 4; ++sl) tma_store_3d(&mapQ, b + 2 * slot + (size_t)sl * 9 * FC * 16, 2 * c * FC, (int)(tl * 9), sl);
                     tma_store_commit();
@@ -374,6 +382,51 @@ int make_shrink_flat_maps(const ShrinkFlatPlan& p, const float* D, float* S, flo
     return 0;
 }
 
+// S = D + Y/mu - W_q: undo W_next = D - S + Y/mu_next from the digit planes the last pass wrote (mu has been advanced since, so
+// DevState::mu IS that mu_next, and wq_scale is the scale of the planes that exist).  Runs only when DevState::s_stale is set.
+// Natural pixel order for D, Y, S (coalesced); the four digit bytes of a pixel are gathered from the tile-major planes.
+__global__ void __launch_bounds__(256) rebuild_S_kernel(const float* __restrict__ D, const float* __restrict__ Y, float* __restrict__ S,
+                                                        const signed char* __restrict__ Wq, long long ld, long long ldq, int n, int rows, int cols,
+                                                        int ntile_r, DevState* st, int min_rank) {
+    if (!st->s_stale || st->svp < min_rank) return;
+    const float inv_mu = (float)(1.0 / st->mu);
+    const float sc = (float)(st->wq_scale * (1.0 / 2147483648.0));
+    const size_t plane = (size_t)ldq * n;
+    const long long m = (long long)rows * cols;
+    // a small persistent grid: this kernel is launched every iteration and nearly always returns at the first line
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < m * n; w += (long long)gridDim.x * blockDim.x) {
+        {
+            const int f = (int)(w / m);
+            const long long p = w - (long long)f * m;
+            const int j = (int)(p / rows), i = (int)(p - (long long)j * rows);
+            const int tcx = j / 3, c = j - 3 * tcx, trx = i / SF_R, il = i - trx * SF_R, g = il / 3, dr = il - 3 * g;
+            const int pos = (3 * c + dr) * SF_NG + g;
+            const long long unit = ((long long)tcx * ntile_r + trx) * 9 + (pos >> 4);
+            const signed char* q0 = Wq + ((size_t)unit * n + f) * 16 + (pos & 15);
+            const unsigned int u = (unsigned int)(unsigned char)q0[0] | ((unsigned int)(unsigned char)q0[plane] << 8) |
+                                   ((unsigned int)(unsigned char)q0[2 * plane] << 16) | ((unsigned int)(unsigned char)q0[3 * plane] << 24);
+            const float wq = (float)(int)((u ^ 0x00808080u) - 0x00808080u) * sc;
+            const size_t off = (size_t)f * ld + p;
+            S[off] = fmaf(Y[off], inv_mu, D[off]) - wq;
+        }
+    }
+}
+__global__ void rebuild_S_done_kernel(DevState* st, int min_rank) { if (threadIdx.x == 0 && blockIdx.x == 0 && st->s_stale && st->svp >= min_rank) st->s_stale = 0; }
+
+// min_rank: rebuild only if the rank of the coming shrink pass is at least this (0 = unconditionally when stale)
+int launch_rebuild_S(const ShrinkFlatPlan& p, const float* D, const float* Y, float* S, const signed char* Wq, long long ldq, DevState* st,
+                     int min_rank, cudaStream_t stream) {
+    const long long m = (long long)p.rows * p.cols;
+    long long gx = (m * p.n + 255) / 256;
+    if (gx > 148 * 8) gx = 148 * 8;
+    dim3 g((unsigned)gx);
+    rebuild_S_kernel<<<g, 256, 0, stream>>>(D, Y, S, Wq, p.ld, ldq, p.n, p.rows, p.cols, p.ntile_r, st, min_rank);
+    BSUB_CUDA_CHECK(cudaGetLastError());
+    rebuild_S_done_kernel<<<1, 32, 0, stream>>>(st, min_rank);
+    BSUB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 template <int MODE>
 static int launch_sf(const ShrinkFlatPlan& p, const ShrinkFlatMaps& maps, const ShrinkFlatArgs& a, cudaStream_t stream) {
     static unsigned long long attr_devs = 0;
@@ -384,9 +437,10 @@ static int launch_sf(const ShrinkFlatPlan& p, const ShrinkFlatMaps& maps, const 
     return 0;
 }
 
-int launch_shrink_flat(const ShrinkFlatPlan& p, const ShrinkFlatMaps& maps, const float* Tt, const DevState* st, int mode, double* part_zz,
+int launch_shrink_flat(const ShrinkFlatPlan& p, const ShrinkFlatMaps& maps, const float* Tt, DevState* st, int mode, int force_S, double* part_zz,
                        unsigned long long* part_nnz, float* part_max, float* part_wmax, cudaStream_t stream) {
     ShrinkFlatArgs a;
+    a.s_stale_next = &st->s_stale_next; a.force_S = (force_S || getenv("BSUB_FLAT_ALWAYS_S") != nullptr) ? 1 : 0;
     a.Tt = Tt; a.n = p.n; a.rows = p.rows; a.cols = p.cols; a.FC = p.FC; a.NS = p.NS; a.nchunkf = p.nchunkf; a.ntile_r = p.ntile_r;
     a.ntiles = p.ntiles; a.st = st; a.part_zz = part_zz; a.part_nnz = part_nnz; a.part_max = part_max; a.part_wmax = part_wmax; a.mode = mode;
     { const char* e = getenv("BSUB_FLAT_PROBE"); a.probe = e ? atoi(e) : 0; }

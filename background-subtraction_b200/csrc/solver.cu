@@ -56,6 +56,8 @@ struct bsub_solver {
     // T = Vr^T W from the digit planes (project.cu): lets the streamed shrink kernel read every tile once
     bool use_proj = false; ProjectPlan pjp; float* Tt = nullptr;
     bool use_flat = false, sfmaps_ready = false; ShrinkFlatPlan sfp; ShrinkFlatMaps sfmaps;     // single-pass shrink (shrink_flat.cu)
+    bool force_S = false;                     // store S in every iteration (BSUB_FLAG_ALWAYS_STORE_S, or after a restart)
+    int proj_iter = -1;                       // iteration (iters_enqueued) whose projection has already been launched (bsub_step_project)
     float* tpart = nullptr; double* part_zz = nullptr; unsigned long long* part_nnz = nullptr;
     float* part_max = nullptr;
     int shrink_mode = SHRINK_FLAT3;
@@ -163,6 +165,7 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
     if (s->cfg.graph_tol <= 0) s->cfg.graph_tol = 1e-6;
     if (s->cfg.non_block_lambda_scale <= 0) s->cfg.non_block_lambda_scale = 100.0;
     s->m = cfg->m; s->n = cfg->n;
+    s->force_S = (cfg->flags & BSUB_FLAG_ALWAYS_STORE_S) != 0;
     s->ld = ((cfg->m + 31) / 32) * 32;
     s->npad = ((cfg->n + 31) / 32) * 32;
     int rc = 0;
@@ -474,6 +477,12 @@ static int upload_state(bsub_solver* s, cudaStream_t st) {
     return 0;
 }
 
+int bsub_set_always_store_S(bsub_solver* s, int on) {
+    if (!s) { set_error("bsub_set_always_store_S: null solver"); return -1; }
+    s->force_S = on != 0;
+    return 0;
+}
+
 int bsub_comm_buffers(bsub_solver* s, double** sum_buf, int64_t* sum_count, double** max_buf, int64_t* max_count) {
     if (!s) { set_error("bsub_comm_buffers: null solver"); return -1; }
     if (sum_buf) *sum_buf = s->comm_sum;
@@ -508,6 +517,7 @@ int bsub_step_init_local(bsub_solver* s, void* stream) {
         RET_IF(launch_gram(s->gp, s->gmaps, false, s->tasks_dev, nullptr, 0.f, s->gram_partial, s->comm_sum, st));
     }
     s->iters_enqueued = 0;
+    s->proj_iter = -1;
     s->finalized = false;
     return 0;
 }
@@ -539,6 +549,19 @@ int bsub_step_solve(bsub_solver* s, void* stream) {
     return launch_eig(s->ep, s->comm_sum, s->comm_max, s->eb, s->st, 1, 0, as_stream(stream));
 }
 
+// T = Vr^T W from the digit planes (project.cu) as a step of its own, so that a driver can time it; bsub_step_shrink launches it
+// itself when the driver did not.
+int bsub_step_project(bsub_solver* s, void* stream) {
+    if (!s || !s->initialised) { set_error("bsub_step_project: solver not initialised"); return -1; }
+    cudaStream_t st = use_stream(s, stream);
+    const bool proj = s->use_proj && s->use_stream && s->use_i8 && s->shrink_mode != SHRINK_SPILL;
+    if (!proj || s->proj_iter == s->iters_enqueued) return 0;
+    RET_IF(launch_project(s->pjp, s->Wq, s->eb.Vr, s->eb.vstride, s->T, s->ld, s->Tt, s->ssp.rows, s->ssp.cols, s->ssp.R, s->ssp.ntile_r,
+                          s->ssp.ntiles, s->ssp.kcap, s->st, st));
+    s->proj_iter = s->iters_enqueued;
+    return 0;
+}
+
 int bsub_step_shrink(bsub_solver* s, void* stream) {
     if (!s || !s->initialised) { set_error("bsub_step_shrink: solver not initialised"); return -1; }
     cudaStream_t st = use_stream(s, stream);
@@ -563,8 +586,7 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
         int off = 0, min_rank = 0;
         if (s->use_stream) {          // rank <= 16: streamed kernel; larger ranks fall through to the cluster kernel
             if (proj)                 // T = Vr^T W from the planes the Gram just read (skips itself when they do not exist)
-                RET_IF(launch_project(s->pjp, s->Wq, s->eb.Vr, s->eb.vstride, s->T, s->ld, s->Tt, s->ssp.rows, s->ssp.cols, s->ssp.R,
-                                      s->ssp.ntile_r, s->ssp.ntiles, s->ssp.kcap, s->st, st));
+                RET_IF(bsub_step_project(s, stream));
             RET_IF(launch_shrink_stream(s->ssp, s->ssmaps, b, s->st, s->shrink_mode, st));
             off = s->ssp.nparts; min_rank = s->ssp.kcap + 1;
             if (flat) {               // rank <= 8 from the second iteration on: the single-pass kernel (the one above then exits at once)
@@ -572,9 +594,11 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
                     RET_IF(make_shrink_flat_maps(s->sfp, s->D, s->S, s->Y, s->Wq, s->gip.ldq, s->eb.VC, s->eb.vstride, &s->sfmaps));
                     s->sfmaps_ready = true;
                 }
-                RET_IF(launch_shrink_flat(s->sfp, s->sfmaps, s->Tt, s->st, s->shrink_mode, s->part_zz + off, s->part_nnz + off, s->part_max + off,
-                                          s->part_wmax + s->ssp.grid, st));
+                RET_IF(launch_shrink_flat(s->sfp, s->sfmaps, s->Tt, s->st, s->shrink_mode, s->force_S ? 1 : 0, s->part_zz + off, s->part_nnz + off,
+                                          s->part_max + off, s->part_wmax + s->ssp.grid, st));
                 off += s->sfp.grid;
+                // the rank > 16 fallback below reads S from HBM: bring it up to date if the single-pass kernel has been skipping its store
+                if (!s->force_S) RET_IF(launch_rebuild_S(s->sfp, s->D, s->Y, s->S, s->Wq, s->gip.ldq, s->st, s->ssp.kcap + 1, st));
             }
         }
         ShrinkBuffers b2 = b;
@@ -649,19 +673,28 @@ int bsub_sync_status(bsub_solver* s, bsub_status* out, void* stream) {
 }
 
 int bsub_run(bsub_solver* s, void* stream) {
-    RET_IF(bsub_step_init_local(s, stream));
-    RET_IF(bsub_step_init_finish(s, stream));
-    const int max_iter = s->cfg.max_iter;
-    for (int it = 0; it < max_iter + 1; ++it) {
-        // bounded run-ahead: wait for iteration it - kRunAhead, then look at the mapped stop flag (no device sync)
-        if (it >= kRunAhead) {
-            CK(cudaEventSynchronize(s->ev[(it - kRunAhead) % (kRunAhead + 1)]));
-            if (s->mirror->done) break;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        RET_IF(bsub_step_init_local(s, stream));
+        RET_IF(bsub_step_init_finish(s, stream));
+        const int max_iter = s->cfg.max_iter;
+        for (int it = 0; it < max_iter + 1; ++it) {
+            // bounded run-ahead: wait for iteration it - kRunAhead, then look at the mapped stop flag (no device sync)
+            if (it >= kRunAhead) {
+                CK(cudaEventSynchronize(s->ev[(it - kRunAhead) % (kRunAhead + 1)]));
+                if (s->mirror->done) break;
+            }
+            RET_IF(bsub_step_gram(s, stream));
+            RET_IF(bsub_step_solve(s, stream));
+            RET_IF(bsub_step_shrink(s, stream));
+            RET_IF(bsub_step_finish_iter(s, stream));
         }
-        RET_IF(bsub_step_gram(s, stream));
-        RET_IF(bsub_step_solve(s, stream));
-        RET_IF(bsub_step_shrink(s, stream));
-        RET_IF(bsub_step_finish_iter(s, stream));
+        if (!s->use_flat || s->force_S) return 0;
+        // the single-pass shrink skips the store of S in iterations that cannot be the last; a clipped digit pass in such an
+        // iteration (never seen: the fixed-point scale has 4x head-room) leaves the state unrecoverable -> the device stops with
+        // done == 5 and the solve is repeated with S stored every time.  This needs the final flag: drain the last iterations.
+        CK(cudaEventSynchronize(s->ev[(s->iters_enqueued + kRunAhead) % (kRunAhead + 1)]));
+        if (s->mirror->done != 5) return 0;
+        s->force_S = true;
     }
     return 0;
 }
@@ -671,6 +704,9 @@ int bsub_finalize(bsub_solver* s, void* stream) {
     if (!s || !s->initialised) { set_error("bsub_finalize: nothing has been solved"); return -1; }
     if (s->finalized) return 0;
     if (!s->L) { CK(cudaMalloc((void**)&s->L, sizeof(float) * (size_t)s->ld * s->n)); }
+    // S is an output: if the last shrink passes skipped its store (shrink_flat.cu), rebuild it from D, Y and the digit planes
+    if (s->use_flat && s->iters_enqueued > 0 && !s->force_S)
+        RET_IF(launch_rebuild_S(s->sfp, s->D, s->Y, s->S, s->Wq, s->gip.ldq, s->st, 0, as_stream(stream)));
     RET_IF(launch_materialize_L(s->T, s->eb.VC, s->eb.vstride, s->st, s->L, s->ld, s->m, s->n, as_stream(stream)));
     s->finalized = true;
     return 0;
@@ -683,13 +719,16 @@ int bsub_get_L_f32_dev(bsub_solver* s, float** L, int64_t* ld) {
     if (!s || !s->finalized) { set_error("bsub_get_L_f32_dev: call bsub_finalize first"); return -1; }
     *L = s->L; if (ld) *ld = s->ld; return 0;
 }
-int bsub_get_S_f32_dev(bsub_solver* s, float** S, int64_t* ld) { if (!s) return -1; *S = s->S; if (ld) *ld = s->ld; return 0; }
+int bsub_get_S_f32_dev(bsub_solver* s, float** S, int64_t* ld) {
+    if (!s || (s->iters_enqueued > 0 && !s->finalized)) { set_error("bsub_get_S_f32_dev: call bsub_finalize first"); return -1; }
+    *S = s->S; if (ld) *ld = s->ld; return 0;
+}
 int bsub_get_D_f32_dev(bsub_solver* s, float** D, int64_t* ld) { if (!s) return -1; *D = s->D; if (ld) *ld = s->ld; return 0; }
 int bsub_get_Y_f32_dev(bsub_solver* s, float** Y, int64_t* ld) { if (!s) return -1; *Y = s->Y; if (ld) *ld = s->ld; return 0; }
 
 int bsub_download_f32(bsub_solver* s, int which, float* dst, int64_t ld, void* stream) {
     if (!s || !dst || ld < s->m) { set_error("bsub_download_f32: bad argument"); return -1; }
-    if (which == 0 && !s->finalized) RET_IF(bsub_finalize(s, stream));
+    if (which <= 1 && !s->finalized && s->initialised) RET_IF(bsub_finalize(s, stream));
     float* src = pick(s, which);
     if (!src) { set_error("bsub_download_f32: bad selector %d", which); return -1; }
     if (ld == s->m && s->ld == s->m) CK(cudaMemcpyAsync(dst, src, sizeof(float) * (size_t)s->m * s->n, cudaMemcpyDeviceToHost, as_stream(stream)));
@@ -702,7 +741,7 @@ int bsub_download_f32(bsub_solver* s, int which, float* dst, int64_t ld, void* s
 int bsub_download_f64(bsub_solver* s, int which, double* dst, int64_t ld, void* stream) {
     if (!s || !dst || ld < s->m) { set_error("bsub_download_f64: bad argument"); return -1; }
     cudaStream_t st = use_stream(s, stream);
-    if (which == 0 && !s->finalized) RET_IF(bsub_finalize(s, stream));
+    if (which <= 1 && !s->finalized && s->initialised) RET_IF(bsub_finalize(s, stream));
     float* src = pick(s, which);
     if (!src) { set_error("bsub_download_f64: bad selector %d", which); return -1; }
     // widen on the device in batches through the staging buffer (allocated once, no per-call cudaMalloc and a single

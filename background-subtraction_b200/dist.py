@@ -57,11 +57,15 @@ class TorchComm:
 class CudaStepSolver:
     """Thin object view of the bsub_step_* C entry points for one shard."""
 
-    def __init__(self, rows, cols_local, n, m_global, delta=10, max_iter=500, tile_rows=0, cluster_frames=0):
+    def __init__(self, rows, cols_local, n, m_global, delta=10, max_iter=500, tile_rows=0, cluster_frames=0, store_S_lazily=False):
+        # store_S_lazily: let the single-pass shrink kernel skip the store of S in iterations that cannot be the last (it is
+        # rebuilt at the end).  The restart that covers a clipped digit pass is local to a rank, so ShardedLSD only honours
+        # this for world_size == 1; sharded runs store S in every iteration.
         self.m = rows * cols_local
         cfg = api.make_config(self.m, n, C.PROX_FLAT_LINF, rows, cols_local, delta=delta, m_global=m_global,
                               d_global=min(m_global, n), max_iter=max_iter, tile_rows=tile_rows,
-                              cluster_frames=cluster_frames)
+                              cluster_frames=cluster_frames, flags=0 if store_S_lazily else C.FLAG_ALWAYS_STORE_S)
+        self.lazy_S = bool(store_S_lazily)
         self.dec = api.Decomposition(cfg)
         self.dec.set_flat_groups(api.get_proximal_flat_groups_nonoverlap((rows, cols_local), api.BLOCK_SIZE))
         self.lib, self.h = self.dec.lib, self.dec.h
@@ -91,6 +95,9 @@ class CudaStepSolver:
 
     def solve(self):
         C.check(self.lib.bsub_step_solve(self.h, self._s()))
+
+    def project(self):
+        C.check(self.lib.bsub_step_project(self.h, self._s()))
 
     def shrink(self):
         C.check(self.lib.bsub_step_shrink(self.h, self._s()))
@@ -128,6 +135,14 @@ class CudaStepSolver:
 
     def wait_iter(self, k):
         pass
+
+    def needs_restart(self):
+        """done == 5: a digit pass clipped while S was not being stored (see bsub_set_always_store_S); blocking read."""
+        return self.lazy_S and self.dec.status().done == 5
+
+    def store_S_always(self):
+        self.lazy_S = False
+        C.check(self.lib.bsub_set_always_store_S(self.h, 1))
 
     def status(self):
         return self.dec.status()
@@ -180,10 +195,15 @@ class ShardedLSD:
                 s.finish_iter()
             hk('gram', 'end')
             hk('solve', 'begin'); s.solve(); hk('solve', 'end')
+            if hooks is not None and hasattr(s, 'project'):      # timed runs: the projection as a phase of its own
+                hk('project', 'begin'); s.project(); hk('project', 'end')
             hk('shrink', 'begin'); s.shrink(); hk('shrink', 'end')
             if self.fence is not None:
                 fences.append(self.fence(it))
             self.iters_enqueued += 1
+        if getattr(s, "lazy_S", False) and comm.world == 1 and s.needs_restart():
+            s.store_S_always()
+            return self.solve(hooks)
         return self
 
     def finish(self, sigmas=2.0, want_mask=True):

@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--workload", default="synthetic_1080p_300", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-sample-div", type=int, default=8, help="CPU baseline: keep 1/div of the rows and of the columns")
+    ap.add_argument("--cpu-sample-div", type=int, default=0,
+                    help="CPU baseline: keep rows/div x cols/(2 div) of every frame (0 = 4: a 1/32 window of 1080p, ~20 s of CPU work)")
     ap.add_argument("--tile-rows", type=int, default=0)
     ap.add_argument("--cluster-frames", type=int, default=0)
     return ap.parse_args()
@@ -114,23 +115,36 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_port_solve(D64, rows, cols, threads):
+def cpu_port_solve(D64, rows, cols, threads, keep=False):
     """The oracle port of inexact_alm_lsd (flat 3x3) + foreground_mask on the host cores (float64, NumPy/LAPACK +
-    the OpenMP C prox) -- test/bench infrastructure, not the product."""
+    the OpenMP C prox) -- test/bench infrastructure, not the product.  The thread count is set explicitly: torchrun exports
+    OMP_NUM_THREADS=1, which would otherwise halve the N > 1 reference arm."""
     from oracle import alm_oracle as O
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     groups = O.flat_groups_nonoverlap((rows, cols), (3, 3))
-    t0 = time.perf_counter()
-    L, S, it, conv = O.inexact_alm_lsd(D64, groups=groups)
-    O.foreground_mask(D64, L, S)
-    return time.perf_counter() - t0, it, conv
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=threads)
+    except Exception:                                       # pragma: no cover
+        import contextlib
+        ctx = contextlib.nullcontext()
+    with ctx:
+        t0 = time.perf_counter()
+        L, S, it, conv = O.inexact_alm_lsd(D64, groups=groups)
+        mask = O.foreground_mask(D64, L, S)
+        dt = time.perf_counter() - t0
+    return (dt, it, conv, L, S, mask) if keep else (dt, it, conv)
 
 
 def cpu_sample(video_u8, rows, cols, frames, div):
-    """Bounded sample of the same workload: a (rows/div) x (cols/div) window of every frame (all reference costs are
-    linear in the pixel count -- SURVEY 8d), rows/cols kept multiples of 3 so that the tiling is unchanged."""
-    r = max(3, (rows // div) // 3 * 3)
-    c = max(3, (cols // div) // 3 * 3)
+    """Bounded sample of the same workload: a (rows/div) x (cols/(2 div)) window of every frame (all reference costs are
+    linear in the pixel count -- SURVEY 8d); rows a multiple of 12 and cols of 3, so that the 3x3 tiling is unchanged and the
+    same window also runs through the CUDA fast path for the parity figures."""
+    if div <= 1:
+        r, c = rows, cols
+    else:
+        r = max(12, (rows // div) // 12 * 12)
+        c = max(3, (cols // (2 * div)) // 3 * 3)
     cube = video_u8.reshape(frames, cols, rows)[:, :c, :r]                 # [n][col][row]
     x = cube.astype(np.float64)
     lo, hi = float(video_u8.min()), float(video_u8.max())
@@ -158,7 +172,7 @@ def run_reference(args, rank, world):
     rows, cols, frames, seed, nrect = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
     video = load_video(args.workload)
-    D, r, c = cpu_sample(video, rows, cols, frames, args.cpu_sample_div if rows * cols > 200000 else 1)
+    D, r, c = cpu_sample(video, rows, cols, frames, (args.cpu_sample_div or 4) if rows * cols > 200000 else 1)
     scale = (rows * cols) / float(r * c)
     times = []
     for i in range(args.warmup + args.steps):
@@ -223,14 +237,15 @@ def main():
         Dh[f0:f0 + stepf] = ((shard_u8[f0:f0 + stepf].astype(np.float64) - lo) * scale - mean_n).astype(np.float32)
     t_gen = time.perf_counter() - t_gen
 
-    solver = bdist.CudaStepSolver(rows, cols_local, frames, m, tile_rows=args.tile_rows, cluster_frames=args.cluster_frames)
+    solver = bdist.CudaStepSolver(rows, cols_local, frames, m, tile_rows=args.tile_rows, cluster_frames=args.cluster_frames,
+                                  store_S_lazily=(world == 1))
     solver.load(Dh)
     torch.cuda.synchronize()
     driver = bdist.ShardedLSD(solver, comm, fence=bdist.cuda_fence)
 
     # ---- per-kernel timing hooks (CUDA events on the launching stream) ----
     stream = torch.cuda.current_stream()
-    ev = {"gram": [], "solve": [], "shrink": []}
+    ev = {"gram": [], "solve": [], "project": [], "shrink": []}
     pending = {}
 
     def hooks(name, phase):
@@ -314,14 +329,19 @@ def main():
     use_i8 = bool(info["use_i8"])
     gram_first_ms = float(np.mean([s[0][0].elapsed_time(s[0][1]) for s in ev["gram"] if s])) if ev["gram"] else 0.0
     gram_ms, n_gram = phase_ms("gram", 1 if use_i8 else 0)      # int8 path: iteration 1 has no Gram (W_1 = c D, eigenpairs of the initialisation)
-    solve_ms, n_solve = phase_ms("solve")
-    shrink_ms, n_shrink = phase_ms("shrink")
-    # kernels launched per enqueued iteration: gram_dmma, gram_reduce, (gram_i8, gram_i8_finish), eig, shrink_stream /
-    # shrink_tma / shrink (whichever exist), control_post x2; per step: rowsum, Gram(D) (quantize_D + gram_i8 + finish, or
-    # gram_dmma + reduce), eig, init_Y (not with the int8 path: iteration 1 derives S0, Y0 from D), lowrank, absmax, mask_stats,
-    # mask_write
-    per_iter = 2 + (2 if use_i8 else 0) + 1 + (2 if info["use_stream"] else 1) + 2
-    gpu_launches = int(args.steps * (driver.iters_enqueued * per_iter + (10 if use_i8 else 9)))
+    solve_ms, n_solve = phase_ms("solve", 1 if use_i8 else 0)
+    # from iteration 2 on the shrink pass is project_planes_kernel + shrink_flat_kernel (rank <= 8) when the int8 path is on
+    two_kernel = bool(info.get("use_proj")) and bool(info.get("flat_stages"))
+    proj_ms, n_proj = phase_ms("project", 1)
+    shrink_ms, n_shrink = phase_ms("shrink", 1 if two_kernel else 0)
+    shrink1_ms = float(np.mean([s[0][0].elapsed_time(s[0][1]) for s in ev["shrink"] if s])) if ev["shrink"] else 0.0
+    counters = solver.dec.counters()
+    # kernels launched per enqueued iteration: gram_dmma, gram_reduce, (gram_i8, gram_i8_finish), eig, (project), shrink_stream,
+    # (shrink_flat, rebuild_S x2 when S is stored lazily), shrink_tma, control_post x2; per step: rowsum, Gram(D) (quantize_D + gram_i8 +
+    # finish, or gram_dmma + reduce), eig, init_Y (not with the int8 path), (rebuild_S x2), lowrank, absmax/maxS, mask_stats, mask_write
+    per_iter = 2 + (2 if use_i8 else 0) + 1 + (1 if info.get("use_proj") else 0) + (2 if info["use_stream"] else 1) + \
+        ((1 + (2 if world == 1 else 0)) if two_kernel else 0) + 2
+    gpu_launches = int(args.steps * (driver.iters_enqueued * per_iter + (10 if use_i8 else 9) + (2 if two_kernel and world == 1 else 0)))
 
     # ---- end to end through the public host-buffer API (single GPU only) ----
     # Every clip: H2D of D from pinned memory, bsub_run, D2H of L, S and the mask -- all inside the timed region.  PCIe moves
@@ -336,7 +356,7 @@ def main():
         import ctypes
         from background_subtraction_b200 import _cabi as C
         decs = [solver.dec] + [bdist.CudaStepSolver(rows, cols_local, frames, m, tile_rows=args.tile_rows,
-                                                    cluster_frames=args.cluster_frames).dec for _ in range(nwork - 1)]
+                                                    cluster_frames=args.cluster_frames, store_S_lazily=True).dec for _ in range(nwork - 1)]
         outs = [tuple(torch.empty((frames, m), dtype=dt).pin_memory() for dt in (torch.float32, torch.float32, torch.uint8))
                 for _ in range(nwork)]
 
@@ -401,12 +421,70 @@ def main():
             for tag, t in sorted(tlog, key=lambda x: x[1][0]):
                 sys.stderr.write("e2e worker %d: start %.1f  load %.1f run %.1f L %.1f S %.1f mask %.1f ms\n" % (
                     tag, (t[0] - t0) * 1e3, *[(b_ - a_) * 1e3 for a_, b_ in zip(t[:-1], t[1:])]))
-        return {"value": frames / dt, "unit": "frames/s", "h2d_bytes_per_step": int(4 * frames * m),
+        res = {"value": frames / dt, "unit": "frames/s", "h2d_bytes_per_step": int(4 * frames * m),
                "d2h_bytes_per_step": int(9 * frames * m), "ms_per_step": dt * 1e3, "clips_in_flight": nwork,
                "clips_timed": nwork * nclips_each, "serial_ms_per_step": dt_serial * 1e3, "serial_value": frames / dt_serial,
                "handles_agree": same,
                "what": "pinned float32 D in; float32 L, S and uint8 mask out (bsub_load_D_f32_host, bsub_run, bsub_download_f32 x2, "
                        "bsub_mask_host), %d clips in flight, one solver handle + host thread + stream each" % nwork}
+        # ---- other shapes of the same public call, one clip at a time (latency figures) ----
+        variants = {}
+        dec0, (Lh, Sh, Mh) = decs[0], outs[0]
+        u8_pinned = torch.from_numpy(shard_u8).pin_memory()
+        u8_np = u8_pinned.numpy()
+
+        def timed(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            t_ = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t_) / reps
+
+        def clip_u8_full():                                     # uint8 frames in (device-side LSD() pre-processing), L + S + mask out
+            dec0.load_u8(u8_np, force=(lo, hi, mean))
+            dec0.run()
+            C.check(dec0.lib.bsub_download_f32(dec0.h, 0, ctypes.c_void_p(Lh.data_ptr()), m, dec0.stream()))
+            C.check(dec0.lib.bsub_download_f32(dec0.h, 1, ctypes.c_void_p(Sh.data_ptr()), m, dec0.stream()))
+            C.check(dec0.lib.bsub_mask_host(dec0.h, 2.0, ctypes.c_void_p(Mh.data_ptr()), dec0.stream()))
+
+        def clip_u8_mask():                                     # uint8 frames in, foreground mask out (L, S stay on the device)
+            dec0.load_u8(u8_np, force=(lo, hi, mean))
+            dec0.run()
+            C.check(dec0.lib.bsub_mask_host(dec0.h, 2.0, ctypes.c_void_p(Mh.data_ptr()), dec0.stream()))
+
+        for name, fn, h2d, d2h in (("u8_in_L_S_mask_out", clip_u8_full, frames * m, 9 * frames * m),
+                                   ("u8_in_mask_out", clip_u8_mask, frames * m, frames * m)):
+            try:
+                t_ = timed(fn, max(2, args.steps))
+                variants[name] = {"ms_per_step": t_ * 1e3, "value": frames / t_, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+            except Exception as ex:
+                variants[name] = {"error": str(ex)[:200]}
+        # the reference-shaped call: inexact_alm_lsd(float64 ndarray) -> float64 L, S (pageable memory both ways) + foreground mask
+        try:
+            del decs[1:]
+            gc.collect()
+            D64 = np.asfortranarray(Dh.T.astype(np.float64)) if frames * m <= 700_000_000 else None
+            if D64 is not None:
+                groups_full = B.get_proximal_flat_groups_nonoverlap((rows, cols), (3, 3))
+
+                def dropin():
+                    dec_d = B.lsd_decomposition(D64, groups=groups_full, img_shape=(rows, cols))
+                    L_, S_, it_, cv_ = B.api._finish(dec_d, D64, False)
+                    mk_ = dec_d.mask(2)
+                    dec_d.close()
+                    return L_, S_, mk_
+                t0_ = time.perf_counter()
+                dropin()
+                t_ = time.perf_counter() - t0_
+                variants["dropin_f64_pageable"] = {"ms_per_step": t_ * 1e3, "value": frames / t_, "h2d_bytes_per_step": int(8 * frames * m),
+                                                   "d2h_bytes_per_step": int(17 * frames * m),
+                                                   "what": "inexact_alm_lsd(D float64 ndarray) -> float64 L, S + mask; one cold call incl. handle creation"}
+        except Exception as ex:
+            variants["dropin_f64_pageable"] = {"error": str(ex)[:200]}
+        res["variants"] = variants
+        return res
 
     if not args.no_e2e and world == 1:
         # pinned host buffers (5.6 GB per clip in flight) and one solver handle (~18.5 GB of HBM) per clip: fall back to fewer
@@ -442,45 +520,78 @@ def main():
     # ---- roofline of the dominant kernel (per launch, algorithmic bytes) ----
     peak, peak_src = measured_peaks()
     elems_local = float(frames) * m_local
-    shrink_name = "shrink_stream_kernel" if info["use_stream"] else ("shrink_tma_kernel" if info["use_tma"] else "shrink_kernel")
-    # three 128-frame blocks run the multicast-cluster variant (gram_i8.cu)
     c3 = use_i8 and 256 < frames <= 384 and os.environ.get("BSUB_NO_GRAM_CLUSTER") is None
     gram_name = ("gram_i8_c3_kernel" if c3 else "gram_i8_kernel") if use_i8 else "gram_dmma_kernel"
-    # algorithmic bytes per matrix element: shrink reads D,S,Y and writes S,Y (20 B) plus the four
-    # int8 slices of the next W (4 B) when the tcgen05 Gram is on; the Gram then reads those 4 B instead of D,S,Y (12 B)
-    kern = {
-        shrink_name: {"ms": shrink_ms, "launches": n_shrink, "alg_bytes": (24.0 if use_i8 else 20.0) * elems_local, "bound": "hbm"},
-        gram_name: {"ms": gram_ms, "launches": n_gram, "alg_bytes": (4.0 if use_i8 else 12.0) * elems_local,
-                    "bound": "hbm" if use_i8 else "fp64 tensor pipe"},
-        "eig_kernel": {"ms": solve_ms, "launches": n_solve, "alg_bytes": 8.0 * frames * frames, "bound": "latency"},
-    }
+    if two_kernel:
+        # bytes per matrix element that the kernels are designed to move: projection reads the 4 digit bytes;
+        # the single-pass kernel reads D, Y and writes Y and the 4 digit bytes of the next W, plus S when the iteration may be
+        # the last one (world == 1: lazily, ~4 of 19 iterations; sharded runs store it every time)
+        flat_b = 16.0 + (4.0 if world > 1 else 4.0 * 4 / max(iters, 1))
+        kern = {
+            "shrink_flat_kernel": {"ms": shrink_ms, "launches": n_shrink, "alg_bytes": flat_b * elems_local, "bound": "hbm"},
+            "project_planes_kernel": {"ms": proj_ms, "launches": n_proj, "alg_bytes": 4.0 * elems_local, "bound": "hbm"},
+        }
+        shrink_pass_ms = shrink_ms + proj_ms
+    else:
+        shrink_name = "shrink_stream_kernel" if info["use_stream"] else ("shrink_tma_kernel" if info["use_tma"] else "shrink_kernel")
+        kern = {shrink_name: {"ms": shrink_ms, "launches": n_shrink, "alg_bytes": (24.0 if use_i8 else 20.0) * elems_local, "bound": "hbm"}}
+        shrink_pass_ms = shrink_ms
+    kern[gram_name] = {"ms": gram_ms, "launches": n_gram, "alg_bytes": (4.0 if use_i8 else 12.0) * elems_local,
+                       "bound": "hbm" if use_i8 else "fp64 tensor pipe"}
+    kern["eig_kernel"] = {"ms": solve_ms, "launches": n_solve, "alg_bytes": 8.0 * frames * frames, "bound": "latency",
+                          "warm_started_iterations": counters.get("eig_fast_iters")}
+    if two_kernel:
+        kern["shrink_stream_kernel (iteration 1)"] = {"ms": shrink1_ms, "launches": args.steps, "alg_bytes": 16.0 * elems_local, "bound": "hbm"}
     for k in kern.values():
         k["gbs"] = (k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9) if k["ms"] > 0 else 0.0
         k["share"] = (k["ms"] * k["launches"]) / (ms_step * args.steps) if ms_step > 0 else 0.0
-    dom = max((shrink_name, gram_name), key=lambda n: kern[n]["ms"] * kern[n]["launches"])
+    # The contract's figure for the "shrinkage/update pass" (SURVEY 8d): 20 B per element (read D, S, Y; write S, Y) over the time
+    # of the whole pass -- here projection + single-pass kernel.  What the two kernels really move is in `kernels`.
+    dom = "shrink_flat_kernel" if two_kernel else next(iter(kern))
+    achieved = 20.0 * elems_local / (shrink_pass_ms * 1e-3) / 1e9 if shrink_pass_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get(args.workload, {}).get(dom)
+                traffic = json.load(f).get("%s@%d" % (args.workload, world), {}).get(dom)
         except Exception:
             traffic = None
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["gbs"] / peak, "frac_of_8TBs_spec": kern[dom]["gbs"] / 8000.0, "traffic": traffic,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": kern[dom]["alg_bytes"],
-                "note": "phase time = kernel + its small companions (gram: +reduce, +NCCL all-reduce when N>1; shrink: +2 control launches)"}
+    moved = sum(k["alg_bytes"] for n_, k in kern.items() if n_ in ("shrink_flat_kernel", "project_planes_kernel")) if two_kernel else kern[dom]["alg_bytes"]
+    roofline = {"kernel": dom + (" (+ project_planes_kernel: the shrinkage/update pass)" if two_kernel else ""), "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_8TBs_spec": achieved / 8000.0,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": 20.0 * elems_local,
+                "pass_ms": shrink_pass_ms,
+                "designed_bytes_per_launch": moved, "achieved_designed_bytes": moved / (shrink_pass_ms * 1e-3) / 1e9 if shrink_pass_ms > 0 else 0.0,
+                "frac_designed_bytes": (moved / (shrink_pass_ms * 1e-3) / 1e9 / peak) if shrink_pass_ms > 0 else 0.0,
+                "whole_iteration_frac": (32.0 * elems_local / ((shrink_pass_ms + gram_ms + solve_ms) * 1e-3) / 1e9 / peak)
+                if (shrink_pass_ms + gram_ms + solve_ms) > 0 else 0.0,
+                "note": "achieved = SURVEY 8(d)'s 20 B/element / time of the pass (CUDA events on the launching stream, iterations 2..last); "
+                        "designed_bytes = what the kernels are built to move (DESIGN.md 4.4); whole_iteration_frac = 32 B/element / "
+                        "(pass + Gram + eigensolve)"}
 
     cpu = None
+    parity = None
     if not args.no_cpu_baseline and world == 1:
-        D64, r, c = cpu_sample(video, rows, cols, frames, args.cpu_sample_div if rows * cols > 200000 else 1)
+        D64, r, c = cpu_sample(video, rows, cols, frames, (args.cpu_sample_div or 4) if rows * cols > 200000 else 1)
         threads = os.cpu_count() or 1
-        dt, it_c, conv_c = cpu_port_solve(D64, r, c, threads)
+        dt, it_c, conv_c, L_c, S_c, mask_c = cpu_port_solve(D64, r, c, threads, keep=True)
         sc = (rows * cols) / float(r * c)
         cpu = {"value": frames / (dt * sc), "unit": "frames/s", "cores": threads, "kind": "port",
                "sample": f"{r}x{c} pixel window of every frame ({r * c}/{rows * cols} of the pixels), full solve {dt:.1f} s, scaled x{sc:.1f}",
                "iters": it_c, "converged": bool(conv_c)}
+        # the same window through the CUDA path (same kernels as the timed run when frames > 256): parity next to the numbers
+        try:
+            dec_s = B.lsd_decomposition(D64, groups=B.get_proximal_flat_groups_nonoverlap((r, c), (3, 3)), img_shape=(r, c))
+            st_s = dec_s.status()
+            L_g, S_g, mask_g = dec_s.download('L'), dec_s.download('S'), dec_s.mask(2)
+            rel = lambda a_, b_: float(np.linalg.norm(a_ - b_) / max(np.linalg.norm(b_), 1e-300))    # noqa: E731
+            parity = {"window": f"{r}x{c}x{frames}", "iters_gpu": int(st_s.iter), "iters_oracle": int(it_c), "relF_L": rel(L_g, L_c),
+                      "relF_S": rel(S_g, S_c), "mask_agreement": float((mask_g == mask_c).mean()), "paths": dec_s.debug_info(),
+                      "eig_warm_started_iterations": dec_s.eig_fast_count()}
+            dec_s.close()
+        except Exception as ex:                             # reported, never hidden
+            parity = {"error": str(ex)[:300]}
 
     out = {"metric": "frames/s decomposed", "value": frames / (ms_step * 1e-3), "unit": "frames/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -489,10 +600,12 @@ def main():
            "data": "reference fixture (WaterSurface)" if args.workload == "watersurface" else "synthetic",
            "config": {"workload": args.workload, "rows": rows, "cols": cols, "frames": frames, "prox": "flat 3x3 l_inf (LSD)",
                       "delta": 10, "sharding": f"pixel columns over {world} GPU(s)", "l2": "inputs (2.5 GB/matrix) larger than L2",
-                      "tile_rows": info["stream_R"] if info["use_stream"] else solver.dec.cfg.tile_rows, "paths": info},
+                      "tile_rows": info["stream_R"] if info["use_stream"] else solver.dec.cfg.tile_rows, "paths": info,
+                      "timing": "CUDA events on the launching stream; inputs 2.5 GB per matrix >> 126 MB L2 (no flush needed)"},
            "alm_iters": iters, "converged": bool(st.converged), "rank_L": int(st.svp), "err": float(st.err),
            "mask_fraction": mask_fraction,
-           "kernels": kern, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
+           "kernels": kern, "roofline": roofline, "cpu_baseline": cpu, "parity_vs_oracle": parity, "e2e": e2e, "gpu_launches": gpu_launches,
+           "counters": counters,
            "clocks": clocks, "datagen_s": t_gen, "breakdown_ms": breakdown,
            "iters_enqueued": driver.iters_enqueued}
     print(json.dumps(out), flush=True)

@@ -58,8 +58,15 @@ typedef struct {
     double graph_tol;          /* overlapping prox: stop when the largest dual change of a sweep <= tol*lambda/mu (0 = 1e-6) */
     int32_t tile_rows;         /* tuning: rows per shrink tile (0 = default)                                   */
     int32_t cluster_frames;    /* tuning: CTAs per cluster splitting the frames (0 = default)                  */
-    int32_t reserved[6];
+    int32_t flags;             /* BSUB_FLAG_*                                                                  */
+    int32_t reserved[5];
 } bsub_config;
+
+/* bsub_config.flags */
+enum {
+    BSUB_FLAG_ALWAYS_STORE_S = 1   /* store S in every iteration (default: only when the iteration may be the last; S is rebuilt
+                                      from D, Y and the digit planes of W otherwise).  Set by drivers that use the step interface. */
+};
 
 typedef struct {
     int32_t iter;              /* reference iter_out                                                            */
@@ -119,10 +126,14 @@ int bsub_run(bsub_solver* s, void* stream);
 
 /* ---- step interface for pixel-sharded multi-GPU runs (the caller all-reduces between the steps) -------------- */
 int bsub_comm_buffers(bsub_solver* s, double** sum_buf, int64_t* sum_count, double** max_buf, int64_t* max_count);
+/* step drivers: a status with done == 5 means "a digit pass clipped while S was not being stored" -- switch this on and solve again
+ * (bsub_run does that by itself) */
+int bsub_set_always_store_S(bsub_solver* s, int on);
 int bsub_step_init_local(bsub_solver* s, void* stream);    /* Gram(D) partial + row-sum max partial                */
 int bsub_step_init_finish(bsub_solver* s, void* stream);   /* ||D||_2, mu0, Y0, S0                                  */
 int bsub_step_gram(bsub_solver* s, void* stream);          /* partial Gram of W into sum_buf                        */
 int bsub_step_solve(bsub_solver* s, void* stream);         /* eigensolve + rank logic                               */
+int bsub_step_project(bsub_solver* s, void* stream);       /* optional: T = Vr^T W from the digit planes (else part of _shrink) */
 int bsub_step_shrink(bsub_solver* s, void* stream);        /* fused pass B; leaves sum Z^2 etc. in the sum_buf tail  */
 int bsub_step_finish_iter(bsub_solver* s, void* stream);   /* err, mu update, stop flags                            */
 int bsub_poll(bsub_solver* s, bsub_status* st);            /* non-blocking: host mirror written by the device       */
@@ -131,7 +142,7 @@ int bsub_sync_status(bsub_solver* s, bsub_status* st, void* stream);   /* blocki
 /* ---- results ---------------------------------------------------------------------------------------------- */
 int bsub_finalize(bsub_solver* s, void* stream);           /* materialise L = U (sigma - 1/mu) V^T                  */
 int bsub_get_L_f32_dev(bsub_solver* s, float** L, int64_t* ld);
-int bsub_get_S_f32_dev(bsub_solver* s, float** S, int64_t* ld);
+int bsub_get_S_f32_dev(bsub_solver* s, float** S, int64_t* ld);   /* after bsub_finalize (S may have to be rebuilt)          */
 int bsub_get_D_f32_dev(bsub_solver* s, float** D, int64_t* ld);
 int bsub_get_Y_f32_dev(bsub_solver* s, float** Y, int64_t* ld);
 int bsub_download_f64(bsub_solver* s, int which /*0 L, 1 S, 2 D, 3 Y*/, double* dst_host, int64_t ld, void* stream);
