@@ -59,14 +59,16 @@ __device__ __forceinline__ void pj_unit(const ProjectArgs& a, const unsigned cha
         q[3] = (float)(int)((u3 ^ 0x00808080u) - 0x00808080u);
         const float4* vrow = reinterpret_cast<const float4*>(Vs + (size_t)f * 16);
 #pragma unroll
-        for (int k4 = 0; k4 < KC / 4; ++k4) {
+        for (int k4 = 0; k4 < (KC + 3) / 4; ++k4) {
             const float4 v = vrow[k4];
             const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 const int k = 4 * k4 + kk;
-                acc[k][0] = fmaf(vv[kk], q[0], acc[k][0]); acc[k][1] = fmaf(vv[kk], q[1], acc[k][1]);
-                acc[k][2] = fmaf(vv[kk], q[2], acc[k][2]); acc[k][3] = fmaf(vv[kk], q[3], acc[k][3]);
+                if (k < KC) {
+                    acc[k][0] = fmaf(vv[kk], q[0], acc[k][0]); acc[k][1] = fmaf(vv[kk], q[1], acc[k][1]);
+                    acc[k][2] = fmaf(vv[kk], q[2], acc[k][2]); acc[k][3] = fmaf(vv[kk], q[3], acc[k][3]);
+                }
             }
         }
     };
@@ -163,7 +165,10 @@ __global__ void __launch_bounds__(32 * PJ_MAXW, 1) project_planes_kernel(Project
         const int d = (int)(it % a.DEPTH);
         mbar_wait(&mybar[d], (uint32_t)((it / a.DEPTH) & 1));
         const unsigned char* slot = myslots + (size_t)d * a.slot_bytes;
-        if (r <= 4) pj_unit<4>(a, slot, Vs, u, r, sc, lane);
+        if (r <= 2) pj_unit<2>(a, slot, Vs, u, r, sc, lane);
+        else if (r <= 4) pj_unit<4>(a, slot, Vs, u, r, sc, lane);
+        else if (r == 5) pj_unit<5>(a, slot, Vs, u, r, sc, lane);
+        else if (r == 6) pj_unit<6>(a, slot, Vs, u, r, sc, lane);
         else if (r <= 8) pj_unit<8>(a, slot, Vs, u, r, sc, lane);
         else if (r <= 12) pj_unit<12>(a, slot, Vs, u, r, sc, lane);
         else pj_unit<16>(a, slot, Vs, u, r, sc, lane);

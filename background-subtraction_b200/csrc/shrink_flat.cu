@@ -18,6 +18,11 @@
 //   * W_next leaves as one 32-bit word per pixel into a warp-private staging area; the warp (which holds two complete
 //     frames of the tile) then transposes 4 pixels x 4 digits with byte permutes and writes 32-bit plane words, instead
 //     of four one-byte stores per pixel.
+// Loop order: a CTA owns a contiguous range of tiles and walks it in groups of 6 vertically adjacent tiles; inside a group the
+// FRAME chunk is the outer loop and the tile the inner one, so the 192-byte runs that neighbouring tiles write into the same
+// frame and image column reach L2 within a few microseconds of each other and leave for HBM as one long run.  Measured with
+// scripts/micro/tma_pattern_bench.cu (same boxes, no compute): 4.27 -> 5.08 TB/s for 2 loads + 3 stores, 4.57 -> 5.19 TB/s
+// for 2 + 2.  T of the whole group (6 x r x 768 B) sits in shared memory.
 // Rank > 8, the first iteration (no planes of W yet), the spill modes and image heights that are not a multiple of 4
 // stay on shrink_stream.cu / shrink_tma.cu / shrink.cu; the choice is made on the device from DevState.
 #include <stdlib.h>
@@ -30,7 +35,8 @@
 namespace bsub {
 
 constexpr int SF_R = 48, SF_P = 144, SF_NG = 16, SF_FL = 16, SF_NCW = 8, SF_NTC = 256, SF_KMAX = 8;
-constexpr int SF_TFLOATS = SF_KMAX * 4 * SF_R;        // one T buffer: [8][16 groups][12]
+constexpr int SF_TFLOATS = SF_KMAX * 4 * SF_R;        // T of one tile: [8][16 groups][12]
+constexpr int SF_TG = 6;                              // tiles per group (vertically adjacent): see the loop order below
 constexpr size_t SF_SMEM_CAP = 227 * 1024 - 512;
 
 struct ShrinkFlatArgs {
@@ -133,61 +139,62 @@ __device__ __forceinline__ void sf_item(float* dsp, float* ysp, const float (&T)
     zl_acc += zl;
 }
 
-// consumer side of one tile: T of the group in registers, every stage = FC frames
+// consumer side of one group of gt tiles: for every frame chunk, for every tile of the group: one stage of FC frames
 template <int KR, int MODE>
-__device__ __forceinline__ void sf_tile(const ShrinkFlatArgs& a, const float* Tbuf, unsigned char* ring, size_t stage_bytes, const float* Vst_all,
-                                        unsigned int* ustage, uint64_t* full, uint64_t* done, long long& q, int lane, int cw, const SfScal& sc,
-                                        float& zl_acc, unsigned int& nnz_acc, float& max_acc, float& wmax_acc) {
+__device__ __forceinline__ void sf_group(const ShrinkFlatArgs& a, const float* Tg, int gt, unsigned char* ring, size_t stage_bytes, const float* Vst_all,
+                                         unsigned int* ustage, uint64_t* full, uint64_t* done, long long& q, int lane, int cw, const SfScal& sc,
+                                         float& zl_acc, unsigned int& nnz_acc, float& max_acc, float& wmax_acc) {
     const int g = lane & 15, flh = lane >> 4;
     const int FC = a.FC, NS = a.NS;
-    float T[KR > 0 ? KR : 1][9];
-    if (KR > 0) {
-#pragma unroll
-        for (int k = 0; k < KR; ++k) {
-            const float4* tq = reinterpret_cast<const float4*>(Tbuf + (size_t)k * (4 * SF_R) + 12 * g);
-            const float4 t0 = tq[0], t1 = tq[1], t2 = tq[2];
-            T[k][0] = t0.x; T[k][1] = t0.y; T[k][2] = t0.z; T[k][3] = t0.w; T[k][4] = t1.x; T[k][5] = t1.y; T[k][6] = t1.z; T[k][7] = t1.w;
-            T[k][8] = t2.x;
-        }
-    }
     unsigned int* ust = ustage + flh * SF_P + g;              // this thread's words of the warp's staging area: [frame half][entry][group]
     const size_t slot = (size_t)FC * SF_P * sizeof(float);
-    for (int c = 0; c < a.nchunkf; ++c, ++q) {
-        const int s = (int)(q % NS);
-        mbar_wait(&full[s], (uint32_t)((q / NS) & 1));
-        unsigned char* b = ring + (size_t)s * stage_bytes;
-        float* bD = reinterpret_cast<float*>(b);
-        float* bY = reinterpret_cast<float*>(b + slot);
-        unsigned char* bP = b + 2 * slot;                     // [4 planes][9 k16 blocks][FC frames][16 B]
-        const float* Vst = Vst_all + (size_t)s * FC * SF_KMAX;
-        for (int f0 = 0; f0 < FC && a.probe != 1; f0 += SF_FL) {
-            const int fw = f0 + 2 * cw, f = fw + flh;         // the warp's two frames of this round, and mine
-            sf_item<KR, MODE>(bD + (size_t)f * SF_P + 3 * g, bY + (size_t)f * SF_P + 3 * g, T, Vst + f * SF_KMAX, sc, ust, zl_acc, nnz_acc, max_acc,
-                              wmax_acc);
-            __syncwarp();
-            // 2 frames x 36 position quads: 4 pixels x 4 digits -> one 32-bit word per plane
+    for (int c = 0; c < a.nchunkf; ++c)
+        for (int t = 0; t < gt; ++t, ++q) {
+            float T[KR > 0 ? KR : 1][9];                      // the 3x3 group's T of this tile
+            if (KR > 0) {
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const int qi = lane + 32 * t;
-                if (qi < 72) {
-                    const int fh = qi / 36, pq = qi - 36 * fh;
-                    const uint4 w = *reinterpret_cast<const uint4*>(ustage + fh * SF_P + 4 * pq);
-                    const unsigned int t0 = __byte_perm(w.x, w.y, 0x5140), t1 = __byte_perm(w.z, w.w, 0x5140);
-                    const unsigned int t2 = __byte_perm(w.x, w.y, 0x7362), t3 = __byte_perm(w.z, w.w, 0x7362);
-                    unsigned char* dst = bP + ((size_t)(pq >> 2) * FC + (fw + fh)) * 16 + 4 * (pq & 3);
-                    const size_t pstride = (size_t)9 * FC * 16;
-                    *reinterpret_cast<unsigned int*>(dst) = __byte_perm(t0, t1, 0x5410);
-                    *reinterpret_cast<unsigned int*>(dst + pstride) = __byte_perm(t0, t1, 0x7632);
-                    *reinterpret_cast<unsigned int*>(dst + 2 * pstride) = __byte_perm(t2, t3, 0x5410);
-                    *reinterpret_cast<unsigned int*>(dst + 3 * pstride) = __byte_perm(t2, t3, 0x7632);
+                for (int k = 0; k < KR; ++k) {
+                    const float4* tq = reinterpret_cast<const float4*>(Tg + (size_t)t * SF_TFLOATS + (size_t)k * (4 * SF_R) + 12 * g);
+                    const float4 t0 = tq[0], t1 = tq[1], t2 = tq[2];
+                    T[k][0] = t0.x; T[k][1] = t0.y; T[k][2] = t0.z; T[k][3] = t0.w; T[k][4] = t1.x; T[k][5] = t1.y; T[k][6] = t1.z; T[k][7] = t1.w;
+                    T[k][8] = t2.x;
                 }
             }
+            const int s = (int)(q % NS);
+            mbar_wait(&full[s], (uint32_t)((q / NS) & 1));
+            unsigned char* b = ring + (size_t)s * stage_bytes;
+            float* bD = reinterpret_cast<float*>(b);
+            float* bY = reinterpret_cast<float*>(b + slot);
+            unsigned char* bP = b + 2 * slot;                     // [4 planes][9 k16 blocks][FC frames][16 B]
+            const float* Vst = Vst_all + (size_t)s * FC * SF_KMAX;
+            for (int f0 = 0; f0 < FC && a.probe != 1; f0 += SF_FL) {
+                const int fw = f0 + 2 * cw, f = fw + flh;         // the warp's two frames of this round, and mine
+                sf_item<KR, MODE>(bD + (size_t)f * SF_P + 3 * g, bY + (size_t)f * SF_P + 3 * g, T, Vst + f * SF_KMAX, sc, ust, zl_acc, nnz_acc, max_acc,
+                                  wmax_acc);
+                __syncwarp();
+                // 2 frames x 36 position quads: 4 pixels x 4 digits -> one 32-bit word per plane
+#pragma unroll
+                for (int tt = 0; tt < 3; ++tt) {
+                    const int qi = lane + 32 * tt;
+                    if (qi < 72) {
+                        const int fh = qi / 36, pq = qi - 36 * fh;
+                        const uint4 w = *reinterpret_cast<const uint4*>(ustage + fh * SF_P + 4 * pq);
+                        const unsigned int t0 = __byte_perm(w.x, w.y, 0x5140), t1 = __byte_perm(w.z, w.w, 0x5140);
+                        const unsigned int t2 = __byte_perm(w.x, w.y, 0x7362), t3 = __byte_perm(w.z, w.w, 0x7362);
+                        unsigned char* dst = bP + ((size_t)(pq >> 2) * FC + (fw + fh)) * 16 + 4 * (pq & 3);
+                        const size_t pstride = (size_t)9 * FC * 16;
+                        *reinterpret_cast<unsigned int*>(dst) = __byte_perm(t0, t1, 0x5410);
+                        *reinterpret_cast<unsigned int*>(dst + pstride) = __byte_perm(t0, t1, 0x7632);
+                        *reinterpret_cast<unsigned int*>(dst + 2 * pstride) = __byte_perm(t2, t3, 0x5410);
+                        *reinterpret_cast<unsigned int*>(dst + 3 * pstride) = __byte_perm(t2, t3, 0x7632);
+                    }
+                }
+                __syncwarp();
+            }
+            fence_proxy_async_smem();                             // my writes -> visible to the storer's TMA stores
             __syncwarp();
+            if (lane == 0) sf_mbar_arrive(&done[s]);
         }
-        fence_proxy_async_smem();                             // my writes -> visible to the storer's TMA stores
-        __syncwarp();
-        if (lane == 0) sf_mbar_arrive(&done[s]);
-    }
 }
 
 template <int MODE>
@@ -205,9 +212,9 @@ shrink_flat_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_consta
     const int FC = a.FC, NS = a.NS, ncf = a.nchunkf;
     // S is an output, not a state variable of this pass (G_S needs D, L and Y only), and it can be rebuilt from D, Y and the
     // digit planes of W_next = D - S + Y/mu_next (rebuild_S_kernel).  It is stored when this iteration may be the last one
-    // (the residual of the previous iteration is within 8x of the tolerance, or max_iter is reached), when the next Gram
+    // (the residual of the previous iteration is within 4x of the tolerance, or max_iter is reached), when the next Gram
     // will read it (fp64 Gram), or when the caller insists; otherwise 4 of the 20 bytes per element stay on the chip.
-    const bool write_S = a.force_S || st->force_dmma || !(st->err > 8.0 * st->tol) || st->iter >= st->max_iter;
+    const bool write_S = a.force_S || st->force_dmma || !(st->err > 4.0 * st->tol) || st->iter >= st->max_iter;
     if (!write_S && blockIdx.x == 0 && threadIdx.x == 0) *a.s_stale_next = 1;
     const double mu_d = st->mu;
     SfScal sc;
@@ -221,8 +228,8 @@ shrink_flat_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_consta
     const size_t slot = (size_t)FC * SF_P * sizeof(float), stage_bytes = 3 * slot;
     unsigned char* ring = sf_smem;                                                    // [NS][D | Y | planes]
     float* Vst = reinterpret_cast<float*>(ring + (size_t)NS * stage_bytes);           // [NS][FC][8]   VC rows of the stage's frames
-    float* Tb = Vst + (size_t)NS * FC * SF_KMAX;                                      // [2][8][4R]    T of the current / next tile
-    unsigned int* ustage_all = reinterpret_cast<unsigned int*>(Tb + 2 * SF_TFLOATS);  // [8 warps][2 frames][144]
+    float* Tb = Vst + (size_t)NS * FC * SF_KMAX;                                      // [SF_TG][8][4R]  T of the tiles of the current group
+    unsigned int* ustage_all = reinterpret_cast<unsigned int*>(Tb + SF_TG * SF_TFLOATS);  // [8 warps][2 frames][144]
     uint64_t* full = reinterpret_cast<uint64_t*>(ustage_all + SF_NCW * 2 * SF_P);
     uint64_t* done = full + NS;
     uint64_t* freeb = done + NS;
@@ -233,7 +240,7 @@ shrink_flat_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_consta
         mbar_fence_init();
         tma_prefetch_desc(&mapD); tma_prefetch_desc(&mapS); tma_prefetch_desc(&mapY); tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapVC);
     }
-    for (int idx = threadIdx.x; idx < 2 * SF_TFLOATS; idx += blockDim.x) Tb[idx] = 0.f;        // rows >= svp stay zero
+    for (int idx = threadIdx.x; idx < SF_TG * SF_TFLOATS; idx += blockDim.x) Tb[idx] = 0.f;
     __syncthreads();
 
     auto tile_origin = [&](long long tl, int& j0, int& i0) {
@@ -243,25 +250,29 @@ shrink_flat_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_consta
     float zl_acc = 0.f, max_acc = 0.f, wmax_acc = 0.f;
     unsigned int nnz_acc = 0u;
     double zz_acc = 0.0;
+    // this CTA's tiles: a contiguous range, walked in groups of SF_TG
+    const long long tile0 = (a.ntiles * blockIdx.x) / gridDim.x, tile1 = (a.ntiles * (blockIdx.x + 1)) / gridDim.x;
 
     if (warp == 0) {
         // ===================== loader =====================
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();          // everything is touched once
             long long q = 0;
-            for (long long tl = blockIdx.x; tl < a.ntiles; tl += gridDim.x) {
-                int j0, i0;
-                tile_origin(tl, j0, i0);
-                for (int c = 0; c < ncf; ++c, ++q) {
-                    const int s = (int)(q % NS);
-                    const long long u = q / NS;
-                    if (u > 0) mbar_wait(&freeb[s], (uint32_t)((u - 1) & 1));
-                    unsigned char* b = ring + (size_t)s * stage_bytes;
-                    mbar_expect_tx(&full[s], (uint32_t)(2 * slot) + (uint32_t)(FC * SF_KMAX * sizeof(float)));
-                    tma_load_2d(Vst + (size_t)s * FC * SF_KMAX, &mapVC, &full[s], 0, c * FC);
-                    tma_load_3d_hint(b, &mapD, &full[s], i0, j0, c * FC, pol);
-                    tma_load_3d_hint(b + slot, &mapY, &full[s], i0, j0, c * FC, pol);
-                }
+            for (long long g0 = tile0; g0 < tile1; g0 += SF_TG) {
+                const int gt = (int)min((long long)SF_TG, tile1 - g0);
+                for (int c = 0; c < ncf; ++c)
+                    for (int t = 0; t < gt; ++t, ++q) {
+                        int j0, i0;
+                        tile_origin(g0 + t, j0, i0);
+                        const int s = (int)(q % NS);
+                        const long long u = q / NS;
+                        if (u > 0) mbar_wait(&freeb[s], (uint32_t)((u - 1) & 1));
+                        unsigned char* b = ring + (size_t)s * stage_bytes;
+                        mbar_expect_tx(&full[s], (uint32_t)(2 * slot) + (uint32_t)(FC * SF_KMAX * sizeof(float)));
+                        tma_load_2d(Vst + (size_t)s * FC * SF_KMAX, &mapVC, &full[s], 0, c * FC);
+                        tma_load_3d_hint(b, &mapD, &full[s], i0, j0, c * FC, pol);
+                        tma_load_3d_hint(b + slot, &mapY, &full[s], i0, j0, c * FC, pol);
+                    }
             }
         }
         __syncwarp();
@@ -270,20 +281,23 @@ shrink_flat_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_consta
         if (lane == 0) {
             const uint64_t pol = l2_policy_evict_first();
             long long q = 0;
-            for (long long tl = blockIdx.x; tl < a.ntiles; tl += gridDim.x) {
-                int j0, i0;
-                tile_origin(tl, j0, i0);
-                for (int c = 0; c < ncf; ++c, ++q) {
-                    const int s = (int)(q % NS);
-                    mbar_wait(&done[s], (uint32_t)((q / NS) & 1));
-                    unsigned char* b = ring + (size_t)s * stage_bytes;
-                    if (write_S) tma_store_3d_hint(&mapS, b, i0, j0, c * FC, pol);
-                    tma_store_3d_hint(&mapY, b + slot, i0, j0, c * FC, pol);
-                    for (int sl = 0; sl < 4; ++sl) tma_store_3d(&mapQ, b + 2 * slot + (size_t)sl * 9 * FC * 16, 2 * c * FC, (int)(tl * 9), sl);
-                    tma_store_commit();
-                    tma_store_wait_read<0>();
-                    sf_mbar_arrive(&freeb[s]);
-                }
+            for (long long g0 = tile0; g0 < tile1; g0 += SF_TG) {
+                const int gt = (int)min((long long)SF_TG, tile1 - g0);
+                for (int c = 0; c < ncf; ++c)
+                    for (int t = 0; t < gt; ++t, ++q) {
+                        int j0, i0;
+                        tile_origin(g0 + t, j0, i0);
+                        const int s = (int)(q % NS);
+                        mbar_wait(&done[s], (uint32_t)((q / NS) & 1));
+                        unsigned char* b = ring + (size_t)s * stage_bytes;
+                        if (write_S) tma_store_3d_hint(&mapS, b, i0, j0, c * FC, pol);
+                        tma_store_3d_hint(&mapY, b + slot, i0, j0, c * FC, pol);
+                        for (int sl = 0; sl < 4; ++sl)
+                            tma_store_3d(&mapQ, b + 2 * slot + (size_t)sl * 9 * FC * 16, 2 * c * FC, (int)((g0 + t) * 9), sl);
+                        tma_store_commit();
+                        tma_store_wait_read<0>();
+                        sf_mbar_arrive(&freeb[s]);
+                    }
             }
             tma_store_wait_all<0>();
         }
@@ -292,18 +306,18 @@ shrink_flat_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_consta
         // ===================== consumers =====================
         const int ct = threadIdx.x - 64, cw = ct >> 5;
         unsigned int* ustage = ustage_all + (size_t)cw * 2 * SF_P;
-        const int tpieces = r * SF_R;                              // 16-byte pieces of r rows x 4R floats
-        auto fetch_T = [&](long long tile, float* dst) {
-            const float* src = a.Tt + (size_t)tile * 16 * (4 * SF_R);
-            for (int pc = ct; pc < tpieces; pc += SF_NTC) sf_cp_async16(dst + 4 * pc, src + 4 * pc);
-        };
+        const int tpieces = r * SF_R;                              // 16-byte pieces of r rows x 4R floats (one tile)
         long long q = 0;
-        int par = 0;
-        if ((long long)blockIdx.x < a.ntiles) { fetch_T(blockIdx.x, Tb); sf_cp_async_wait_all(); sf_bar_sync(1, SF_NTC); }
-        for (long long tl = blockIdx.x; tl < a.ntiles; tl += gridDim.x) {
-            const float* Tcur = Tb + par * SF_TFLOATS;
-            if (tl + gridDim.x < a.ntiles) fetch_T(tl + gridDim.x, Tb + (par ^ 1) * SF_TFLOATS);
-#define SF_CALL(KR_) sf_tile<KR_, MODE>(a, Tcur, ring, stage_bytes, Vst, ustage, full, done, q, lane, cw, sc, zl_acc, nnz_acc, max_acc, wmax_acc)
+        for (long long g0 = tile0; g0 < tile1; g0 += SF_TG) {
+            const int gt = (int)min((long long)SF_TG, tile1 - g0);
+            // T of the group's tiles -> shared memory (everyone is done with the previous group: barrier at the end of the loop body)
+            for (int pc = ct; pc < gt * tpieces; pc += SF_NTC) {
+                const int t = pc / tpieces, w = pc - t * tpieces;
+                sf_cp_async16(Tb + (size_t)t * SF_TFLOATS + 4 * w, a.Tt + (size_t)(g0 + t) * 16 * (4 * SF_R) + 4 * w);
+            }
+            sf_cp_async_wait_all();
+            sf_bar_sync(1, SF_NTC);
+#define SF_CALL(KR_) sf_group<KR_, MODE>(a, Tb, gt, ring, stage_bytes, Vst, ustage, full, done, q, lane, cw, sc, zl_acc, nnz_acc, max_acc, wmax_acc)
             switch (r) {
                 case 0: SF_CALL(0); break;
                 case 1: SF_CALL(1); break;
@@ -317,9 +331,7 @@ shrink_flat_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_consta
             }
 #undef SF_CALL
             zz_acc += (double)zl_acc; zl_acc = 0.f;
-            sf_cp_async_wait_all();
-            sf_bar_sync(1, SF_NTC);                               // next tile's T has landed, this tile's buffer is free
-            par ^= 1;
+            sf_bar_sync(1, SF_NTC);                               // the group's T buffer is free again
         }
     }
     __syncthreads();
@@ -337,7 +349,7 @@ shrink_flat_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_consta
 // -------------------------------------------------------------------------------------------------------------
 static size_t sf_smem_bytes(int FC, int NS) {
     const size_t slot = (size_t)FC * SF_P * sizeof(float);
-    return (size_t)NS * 3 * slot + (size_t)NS * FC * SF_KMAX * sizeof(float) + (size_t)2 * SF_TFLOATS * sizeof(float) +
+    return (size_t)NS * 3 * slot + (size_t)NS * FC * SF_KMAX * sizeof(float) + (size_t)SF_TG * SF_TFLOATS * sizeof(float) +
            (size_t)SF_NCW * 2 * SF_P * sizeof(unsigned int) + (size_t)3 * NS * sizeof(uint64_t) + 128;
 }
 
@@ -355,7 +367,7 @@ bool make_shrink_flat_plan(int n, int rows, int cols, long long ld, int num_sms,
     if (p.NS < 3) return false;
     p.nchunkf = (n + p.FC - 1) / p.FC;
     p.ntile_r = sp.ntile_r; p.ntiles = sp.ntiles;
-    p.grid = (int)std::min<long long>(num_sms, p.ntiles);
+    p.grid = (int)std::min<long long>(num_sms, (p.ntiles + SF_TG - 1) / SF_TG);     // every CTA at least one group
     p.smem_bytes = sf_smem_bytes(p.FC, p.NS);
     *out = p;
     return true;

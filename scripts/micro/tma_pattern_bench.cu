@@ -32,7 +32,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-struct Args { int rows, cols, n, R, NC, FC, NS, nin, nout, ntr, ntc, ncf; };
+struct Args { int rows, cols, n, R, NC, FC, NS, nin, nout, ntr, ntc, ncf, order; };
 
 __global__ void __launch_bounds__(96, 1) bench_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB,
                                                       const __grid_constant__ CUtensorMap mC, const __grid_constant__ CUtensorMap mD,
@@ -46,34 +46,53 @@ __global__ void __launch_bounds__(96, 1) bench_kernel(const __grid_constant__ CU
     __syncthreads();
     const long long ntiles = (long long)a.ntr * a.ntc;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t0 = (ntiles * blockIdx.x) / gridDim.x, t1 = (ntiles * (blockIdx.x + 1)) / gridDim.x;
     if (warp == 0 && lane == 0) {
         long long q = 0;
-        for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
-            const int tc = (int)(tl / a.ntr), tr = (int)(tl % a.ntr);
-            for (int c = 0; c < a.ncf; ++c, ++q) {
-                const int s = (int)(q % a.NS);
-                if (q >= a.NS) mbar_wait(&freeb[s], (uint32_t)(((q / a.NS) - 1) & 1));
-                unsigned char* b = smem + (size_t)s * stage;
-                mbar_expect_tx(&full[s], (uint32_t)(a.nin * (size_t)a.R * a.NC * a.FC * 4));
-                tma_load_3d(b, &mA, &full[s], tr * a.R, tc * a.NC, c * a.FC);
-                if (a.nin > 1) tma_load_3d(b + slot, &mB, &full[s], tr * a.R, tc * a.NC, c * a.FC);
+        if (a.order == 0) {
+            for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+                const int tc = (int)(tl / a.ntr), tr = (int)(tl % a.ntr);
+                for (int c = 0; c < a.ncf; ++c, ++q) {
+                    const int s = (int)(q % a.NS);
+                    if (q >= a.NS) mbar_wait(&freeb[s], (uint32_t)(((q / a.NS) - 1) & 1));
+                    unsigned char* b = smem + (size_t)s * stage;
+                    mbar_expect_tx(&full[s], (uint32_t)(a.nin * (size_t)a.R * a.NC * a.FC * 4));
+                    tma_load_3d(b, &mA, &full[s], tr * a.R, tc * a.NC, c * a.FC);
+                    if (a.nin > 1) tma_load_3d(b + slot, &mB, &full[s], tr * a.R, tc * a.NC, c * a.FC);
+                }
             }
+        } else {
+            for (int c = 0; c < a.ncf; ++c)
+                for (long long tl = t0; tl < t1; ++tl, ++q) {
+                    const int tc = (int)(tl / a.ntr), tr = (int)(tl % a.ntr);
+                    const int s = (int)(q % a.NS);
+                    if (q >= a.NS) mbar_wait(&freeb[s], (uint32_t)(((q / a.NS) - 1) & 1));
+                    unsigned char* b = smem + (size_t)s * stage;
+                    mbar_expect_tx(&full[s], (uint32_t)(a.nin * (size_t)a.R * a.NC * a.FC * 4));
+                    tma_load_3d(b, &mA, &full[s], tr * a.R, tc * a.NC, c * a.FC);
+                    if (a.nin > 1) tma_load_3d(b + slot, &mB, &full[s], tr * a.R, tc * a.NC, c * a.FC);
+                }
         }
     } else if (warp == 1 && lane == 0) {
         long long q = 0;
-        for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
-            const int tc = (int)(tl / a.ntr), tr = (int)(tl % a.ntr);
-            for (int c = 0; c < a.ncf; ++c, ++q) {
-                const int s = (int)(q % a.NS);
-                mbar_wait(&full[s], (uint32_t)((q / a.NS) & 1));
-                unsigned char* b = smem + (size_t)s * stage;
-                if (a.nout > 0) tma_store_3d(&mC, b, tr * a.R, tc * a.NC, c * a.FC);
-                if (a.nout > 1) tma_store_3d(&mD, b + slot, tr * a.R, tc * a.NC, c * a.FC);
-                if (a.nout > 2) tma_store_3d(&mE, b + 2 * slot, tr * a.R, tc * a.NC, c * a.FC);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                mbar_arrive(&freeb[s]);
-            }
+        auto one = [&](int tc, int tr, int c) {
+            const int s = (int)(q % a.NS);
+            mbar_wait(&full[s], (uint32_t)((q / a.NS) & 1));
+            unsigned char* b = smem + (size_t)s * stage;
+            if (a.nout > 0) tma_store_3d(&mC, b, tr * a.R, tc * a.NC, c * a.FC);
+            if (a.nout > 1) tma_store_3d(&mD, b + slot, tr * a.R, tc * a.NC, c * a.FC);
+            if (a.nout > 2) tma_store_3d(&mE, b + 2 * slot, tr * a.R, tc * a.NC, c * a.FC);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive(&freeb[s]);
+            ++q;
+        };
+        if (a.order == 0) {
+            for (long long tl = blockIdx.x; tl < ntiles; tl += gridDim.x)
+                for (int c = 0; c < a.ncf; ++c) one((int)(tl / a.ntr), (int)(tl % a.ntr), c);
+        } else {
+            for (int c = 0; c < a.ncf; ++c)
+                for (long long tl = t0; tl < t1; ++tl) one((int)(tl / a.ntr), (int)(tl % a.ntr), c);
         }
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -103,11 +122,10 @@ int main(int argc, char** argv) {
     float* buf[5];
     for (int i = 0; i < 5; ++i) { CK(cudaMalloc(&buf[i], bytes)); CK(cudaMemset(buf[i], i, bytes)); }
     CK(cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    struct Shape { int R, NC, FC, nin, nout; };
+    struct Shape { int R, NC, FC, nin, nout, order; };
     std::vector<Shape> shapes = {
-        {48, 3, 16, 2, 3}, {48, 3, 16, 1, 3}, {48, 3, 16, 2, 2}, {48, 3, 16, 1, 2},
-        {96, 3, 8, 2, 3}, {216, 3, 4, 2, 3}, {216, 3, 4, 1, 3}, {216, 3, 8, 2, 3},
-        {48, 12, 4, 2, 3}, {216, 6, 2, 2, 3}, {216, 15, 1, 2, 3}, {216, 15, 1, 1, 3}, {120, 24, 1, 2, 3}, {48, 3, 32, 2, 3}, {216, 3, 2, 2, 3},
+        {48, 3, 16, 2, 3, 0}, {48, 3, 16, 2, 3, 1}, {48, 3, 16, 2, 2, 0}, {48, 3, 16, 2, 2, 1}, {216, 3, 4, 2, 2, 0}, {216, 3, 4, 2, 2, 1},
+        {48, 3, 16, 1, 0, 0}, {48, 3, 16, 1, 0, 1},
     };
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     // reference: plain device-to-device copy
@@ -117,7 +135,7 @@ int main(int argc, char** argv) {
         if (rep) { printf("cudaMemcpy D2D: %.3f ms  %.0f GB/s (read+write)\n", ms, 2.0 * bytes / ms / 1e6); fflush(stdout); }
     }
     for (const Shape& sh : shapes) {
-        Args a; a.rows = rows; a.cols = cols; a.n = n; a.R = sh.R; a.NC = sh.NC; a.FC = sh.FC; a.nin = sh.nin; a.nout = sh.nout;
+        Args a; a.rows = rows; a.cols = cols; a.n = n; a.R = sh.R; a.NC = sh.NC; a.FC = sh.FC; a.nin = sh.nin; a.nout = sh.nout; a.order = sh.order;
         a.ntr = (rows + sh.R - 1) / sh.R; a.ntc = (cols + sh.NC - 1) / sh.NC; a.ncf = (n + sh.FC - 1) / sh.FC;
         const size_t slot = ((size_t)sh.R * sh.NC * sh.FC * 4 + 127) / 128 * 128;
         int NS = (int)((220 * 1024) / (3 * slot)); if (NS > 12) NS = 12; if (NS < 2) { printf("shape too big\n"); continue; }
@@ -134,7 +152,7 @@ int main(int argc, char** argv) {
             if (ms < best) best = ms;
         }
         const double moved = (double)(sh.nin + sh.nout) * bytes;
-        printf("box {%3d rows, %2d cols, %2d frames} = %6.1f KB/slot, %2d stages, %d in / %d out: %.3f ms  %.0f GB/s  (row run %d B)\n", sh.R, sh.NC, sh.FC,
+        printf("order %d box {%3d rows, %2d cols, %2d frames} = %6.1f KB/slot, %2d stages, %d in / %d out: %.3f ms  %.0f GB/s  (row run %d B)\n", sh.order, sh.R, sh.NC, sh.FC,
                slot / 1024.0, NS, sh.nin, sh.nout, best, moved / best / 1e6, sh.R * 4);
         fflush(stdout);
     }
