@@ -122,7 +122,7 @@ __device__ void eig_control(const EigArgs& a, DevState* st, int K, double mu, do
     if (tid == 0) {
         // truncation-error bound of the int8 Gram (gram_i8.cu; summed over the ranks by the all-reduce, 0 for the fp64 Gram):
         // beyond 0.3 (1/mu)^2 a singular value a little above the threshold could be lost, so the solve continues on gram.cu
-        const double ge = a.G[(size_t)a.npad * a.npad + 8] / (thresh * thresh);
+        const double ge = sqrt(fmax(a.G[(size_t)a.npad * a.npad + 8], 0.0)) / (thresh * thresh);
         st->gram_err = ge;
         if (ge > 0.3) st->force_dmma = 1;
         int svp = 0;
@@ -168,7 +168,7 @@ __device__ void eig_control(const EigArgs& a, DevState* st, int K, double mu, do
 // =====================================================================================================================
 constexpr int EIG_PMAX = 16;
 
-struct EigFastLayout { int PM, RB, RG, NJ, JW, RBP; size_t doubles; };
+struct EigFastLayout { int PM, RB, RG, NJ, JW, RBP, gsm; size_t doubles, scratch; };
 __host__ __device__ inline EigFastLayout eig_fast_layout(int n, int C) {
     EigFastLayout L;
     L.PM = (n <= 448) ? 16 : 8;
@@ -177,10 +177,15 @@ __host__ __device__ inline EigFastLayout eig_fast_layout(int n, int C) {
     L.NJ = EIG_WARPS / L.RG; if (L.NJ < 1) L.NJ = 1;
     L.JW = (n + L.NJ - 1) / L.NJ;
     L.RBP = L.RG * 32;
-    size_t scratch = (size_t)L.NJ * L.PM * L.RBP;
-    const size_t s2 = (size_t)EIG_THREADS;                 // [nparts][PM][PM] = one double per thread
+    // this CTA's rows of G in shared memory ([RB][n]) when they fit beside X and Y: the products then need no partial sums
+    const size_t fixed = (size_t)2 * n * L.PM + (size_t)5 * L.PM * L.PM + (size_t)6 * L.PM + 16 + 8 + 64;
+    const size_t with_g = fixed + (size_t)4 * EIG_THREADS + (size_t)L.RB * n;
+    L.gsm = (with_g * sizeof(double) <= (size_t)220 * 1024) ? 1 : 0;
+    size_t scratch = L.gsm ? (size_t)4 * EIG_THREADS : (size_t)L.NJ * L.PM * L.RBP;
+    const size_t s2 = (size_t)4 * EIG_THREADS;             // small reductions: four doubles per thread
     if (scratch < s2) scratch = s2;
-    L.doubles = (size_t)2 * n * L.PM + scratch + (size_t)5 * L.PM * L.PM + (size_t)6 * L.PM + 16 + 8 + 64;
+    L.scratch = scratch;
+    L.doubles = fixed + scratch + (L.gsm ? (size_t)L.RB * n : 0);
     return L;
 }
 
@@ -224,24 +229,54 @@ __device__ void eig_fast_matvec(const EigArgs& a, const EigFastLayout& L, int p,
     cluster.sync();                                   // Ys complete in every CTA
 }
 
+// The same product with this CTA's rows of G in shared memory (Gs[rl][j]): one thread per (row, vector) output, the row of G
+// is a broadcast across the p threads of a row and X[j][0..p) is read conflict-free.
+__device__ void eig_fast_matvec_smem(const EigArgs& a, const EigFastLayout& L, int p, const double* Gs, const double* Xs, double* Ys,
+                                     cg::cluster_group& cluster) {
+    const int n = a.n, C = a.C, c = blockIdx.x, tid = threadIdx.x, PM = L.PM;
+    const int row0 = c * L.RB, nrows = max(0, min(n, row0 + L.RB) - row0);
+    cluster.sync();                                   // every CTA has finished reading the previous Ys
+    for (int item = tid; item < nrows * p; item += EIG_THREADS) {
+        const int rl = item / p, k = item - rl * p;
+        const double* gr = Gs + (size_t)rl * n;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int j = 0;
+        for (; j + 3 < n; j += 4) {
+            s0 = fma(gr[j], Xs[(size_t)j * PM + k], s0); s1 = fma(gr[j + 1], Xs[(size_t)(j + 1) * PM + k], s1);
+            s2 = fma(gr[j + 2], Xs[(size_t)(j + 2) * PM + k], s2); s3 = fma(gr[j + 3], Xs[(size_t)(j + 3) * PM + k], s3);
+        }
+        for (; j < n; ++j) s0 = fma(gr[j], Xs[(size_t)j * PM + k], s0);
+        const double y = (s0 + s1) + (s2 + s3);
+        for (int q = 0; q < C; ++q) cluster.map_shared_rank(Ys, q)[(size_t)(row0 + rl) * PM + k] = y;
+    }
+    cluster.sync();                                   // Ys complete in every CTA
+}
+
 // out[a][b] = sum_i A[i][a] B[i][b]  (p x p, computed redundantly by every CTA); scratch: one double per thread
 __device__ void eig_fast_gram(int n, int PM, int p, const double* A, const double* B, double* out, double* scratch, bool symmetrise) {
-    const int tid = threadIdx.x, pairs = PM * PM, nparts = EIG_THREADS / pairs, part = tid / pairs, pr = tid - part * pairs;
-    const int ia = pr / PM, ib = pr - ia * PM;
-    double acc = 0.0;
-    if (ia < p && ib < p) for (int i = part; i < n; i += nparts) acc = fma(A[(size_t)i * PM + ia], B[(size_t)i * PM + ib], acc);
-    scratch[tid] = acc;
+    const int tid = threadIdx.x, pairs = p * p, nparts = EIG_THREADS / pairs, part = tid / pairs, pr = tid - part * pairs;
+    const int ia = pr / p, ib = pr - ia * p;
+    if (part < nparts) {
+        double acc = 0.0, acc2 = 0.0;
+        int i = part;
+        for (; i + nparts < n; i += 2 * nparts) {
+            acc = fma(A[(size_t)i * PM + ia], B[(size_t)i * PM + ib], acc);
+            acc2 = fma(A[(size_t)(i + nparts) * PM + ia], B[(size_t)(i + nparts) * PM + ib], acc2);
+        }
+        if (i < n) acc = fma(A[(size_t)i * PM + ia], B[(size_t)i * PM + ib], acc);
+        scratch[tid] = acc + acc2;
+    }
     __syncthreads();
     double t = 0.0;
     if (tid < pairs) for (int q = 0; q < nparts; ++q) t += scratch[(size_t)q * pairs + tid];
     __syncthreads();
-    if (tid < pairs) out[tid] = t;
+    if (tid < pairs) out[ia * PM + ib] = t;
     __syncthreads();
     if (symmetrise) {
         double v = 0.0;
-        if (tid < pairs) { const int r = tid / PM, cc = tid - r * PM; v = 0.5 * (out[r * PM + cc] + out[cc * PM + r]); }
+        if (tid < pairs) v = 0.5 * (out[ia * PM + ib] + out[ib * PM + ia]);
         __syncthreads();
-        if (tid < pairs) out[tid] = v;
+        if (tid < pairs) out[ia * PM + ib] = v;
         __syncthreads();
     }
 }
@@ -253,7 +288,7 @@ __device__ void eig_fast_jacobi(int PM, int p, double* H, double* W, double* th,
     for (int idx = lane; idx < PM * PM; idx += 32) W[idx] = ((idx / PM) == (idx % PM)) ? 1.0 : 0.0;
     __syncwarp();
     const int pp = p + (p & 1), half = pp / 2;
-    for (int sweep = 0; sweep < 24 && pp >= 2; ++sweep) {
+    for (int sweep = 0; sweep < 12 && pp >= 2; ++sweep) {
         int rotated = 0;
         for (int round = 0; round < pp - 1; ++round) {
             if (lane < half) {
@@ -262,10 +297,22 @@ __device__ void eig_fast_jacobi(int PM, int p, double* H, double* W, double* th,
                 double cth = 1.0, sth = 0.0;
                 if (ia < p && ib < p) {
                     const double apq = H[ia * PM + ib], app = H[ia * PM + ia], aqq = H[ib * PM + ib];
-                    if (fabs(apq) > 0.25 * DBL_EPSILON * sqrt(fabs(app * aqq)) && fabs(apq) > DBL_MIN) {
-                        const double theta = (aqq - app) / (2.0 * apq);
-                        const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-                        cth = 1.0 / sqrt(fma(t, t, 1.0)); sth = t * cth;
+                    // rotate while the off-diagonal entry matters against the LARGER of the two diagonal entries (absolute accuracy
+                    // eps * max is all the ALM needs: the threshold (1/mu)^2 is > 1e-12 of the leading value).  A test relative to
+                    // sqrt(app aqq) never settles for a (leading, cluster) pair: the rounding of the leading entry alone leaves
+                    // eps * app behind, far above eps * sqrt(app aqq).
+                    const double amax = fmax(fabs(app), fabs(aqq));
+                    if (fabs(apq) > DBL_EPSILON * amax && fabs(apq) > DBL_MIN) {
+                        // rotation angle phi with tan(2 phi) = 2 apq / (aqq - app), |phi| <= pi/4:
+                        //   cos(2 phi) = |d| / h, h = hypot(d, 2 apq);  c = sqrt((1 + cos 2phi) / 2);  s = sgn(d) apq / (h c)
+                        // two reciprocal square roots instead of two square roots and three divisions
+                        const double dd = aqq - app, bb = 2.0 * apq;
+                        const double hinv = rsqrt(fma(dd, dd, bb * bb));
+                        const double c2 = 0.5 * fma(fabs(dd), hinv, 1.0);          // cos^2 phi in [1/2, 1]
+                        const double cinv = rsqrt(c2);
+                        cth = c2 * cinv;
+                        sth = copysign(apq * hinv * cinv, dd * apq);
+                        if (dd == 0.0) sth = copysign(fabs(sth), apq);
                         rotated = 1;
                     }
                 }
@@ -311,21 +358,26 @@ __device__ void eig_fast_jacobi(int PM, int p, double* H, double* W, double* th,
     __syncwarp();
 }
 
-// rows of M (n x p, row stride PM) <- row * W   (one thread per row)
+// rows of M (n x p, row stride PM) <- row * W, in place: p lanes of one warp own a row (32 / p rows per warp pass), every lane
+// reads the whole old row before the warp-level barrier and writes its element after it.
 __device__ void eig_fast_rotate(int n, int PM, int p, double* M, const double* W) {
-    for (int i = threadIdx.x; i < n; i += EIG_THREADS) {
-        double x[EIG_PMAX], y[EIG_PMAX];
-#pragma unroll
-        for (int k = 0; k < EIG_PMAX; ++k) { x[k] = (k < p) ? M[(size_t)i * PM + k] : 0.0; y[k] = 0.0; }
-#pragma unroll
-        for (int aa = 0; aa < EIG_PMAX; ++aa)
-            if (aa < p) {
-#pragma unroll
-                for (int k = 0; k < EIG_PMAX; ++k) if (k < p) y[k] = fma(x[aa], W[aa * PM + k], y[k]);
-            }
-#pragma unroll
-        for (int k = 0; k < EIG_PMAX; ++k) if (k < p) M[(size_t)i * PM + k] = y[k];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int RP = 32 / p, rs = lane / p, k = lane - rs * p;
+    for (int base = warp * RP; base < n; base += EIG_WARPS * RP) {
+        const int i = base + rs;
+        const bool act = rs < RP && i < n;
+        double y0 = 0.0, y1 = 0.0;
+        if (act) {
+            const double* x = M + (size_t)i * PM;
+            int aa = 0;
+            for (; aa + 1 < p; aa += 2) { y0 = fma(x[aa], W[aa * PM + k], y0); y1 = fma(x[aa + 1], W[(aa + 1) * PM + k], y1); }
+            if (aa < p) y0 = fma(x[aa], W[aa * PM + k], y0);
+        }
+        __syncwarp();
+        if (act) M[(size_t)i * PM + k] = y0 + y1;
+        __syncwarp();
     }
+    __syncthreads();
 }
 
 // returns 1: CTA 0 has written lam[0..K) and Z[0..p), *p_out = p (all CTAs return 1); 0: nothing written -> full path
@@ -338,8 +390,7 @@ __device__ int eig_fast_path(const EigArgs& a, DevState* st, int K, double mu, d
     if (L.doubles * sizeof(double) > a.smem_total) return 0;
     const double tau = 1.0 / (mu * mu);
 
-    size_t scratch_d = (size_t)L.NJ * PM * L.RBP;
-    if (scratch_d < (size_t)EIG_THREADS) scratch_d = EIG_THREADS;
+    const size_t scratch_d = L.scratch;
     double* Xs = esm;                                   // [n][PM]
     double* Ys = Xs + (size_t)n * PM;                   // [n][PM]
     double* Pp = Ys + (size_t)n * PM;                   // [NJ][PM][RBP] partial products / scratch of the small reductions
@@ -354,6 +405,14 @@ __device__ int eig_fast_path(const EigArgs& a, DevState* st, int K, double mu, d
     double* gbp = cs + 4 * PM;                          // [16] per-CTA partials of gb^2
     double* flag = gbp + 16;                            // [8]
     double* red = flag + 8;                             // [64]
+    double* Gs = red + 64;                              // [RB][n] this CTA's rows of G (only when L.gsm)
+    if (L.gsm) {
+        const int row0 = c * L.RB, nrows = max(0, min(n, row0 + L.RB) - row0);
+        for (int idx = tid; idx < nrows * n; idx += EIG_THREADS) {
+            const int rl = idx / n, j = idx - rl * n;
+            Gs[idx] = __ldg(a.G + (size_t)(row0 + rl) * a.npad + j);
+        }
+    }
 
     for (int idx = tid; idx < n * PM; idx += EIG_THREADS) {
         const int i = idx / PM, k = idx - i * PM;
@@ -361,17 +420,24 @@ __device__ int eig_fast_path(const EigArgs& a, DevState* st, int K, double mu, d
     }
     __syncthreads();
 
+    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tc = clock64();
+#define EF_TICK(k) { __syncthreads(); const long long t_ = clock64(); tph[k] += t_ - tc; tc = t_; }
+    EF_TICK(0)                                                  // load of X (and of the rows of G)
     const int max_steps = 8;
     int converged = 0, steps = 0;
     for (int step = 0; step < max_steps; ++step) {
         steps = step + 1;
-        eig_fast_matvec(a, L, p, Xs, Ys, Pp, cluster);
+        if (L.gsm) eig_fast_matvec_smem(a, L, p, Gs, Xs, Ys, cluster);
+        else eig_fast_matvec(a, L, p, Xs, Ys, Pp, cluster);
+        EF_TICK(1)
         eig_fast_gram(n, PM, p, Xs, Ys, Hs, Pp, true);          // H = X^T G X
         eig_fast_gram(n, PM, p, Ys, Ys, Bs, Pp, true);          // B = Y^T Y
+        EF_TICK(2)
         if (warp == 0) eig_fast_jacobi(PM, p, Hs, Ws, th, Ts, cs);
-        __syncthreads();
+        EF_TICK(3)
         eig_fast_rotate(n, PM, p, Xs, Ws);                      // Ritz vectors X W, and G (X W) = Y W
         eig_fast_rotate(n, PM, p, Ys, Ws);
+        EF_TICK(4)
         // B' = W^T B W (Gram of the rotated Y):  Ts = B W, then Bs = W^T Ts
         if (tid < PM * PM) {
             const int r = tid / PM, cc = tid - r * PM;
@@ -412,6 +478,7 @@ __device__ int eig_fast_path(const EigArgs& a, DevState* st, int K, double mu, d
             flag[0] = (double)ok;
         }
         __syncthreads();
+        EF_TICK(5)
         if (flag[0] != 0.0) { converged = 1; break; }
         if (step == max_steps - 1) break;
         // X <- orth(Y) by Cholesky QR: B' = R^T R, X = Y R^{-1}
@@ -422,10 +489,10 @@ __device__ int eig_fast_path(const EigArgs& a, DevState* st, int K, double mu, d
             for (int j = 0; j < p; ++j) {
                 const double d2 = Rs[j * PM + j];
                 if (!(d2 > 0.0)) { bad = 1; break; }                                // uniform over the warp
-                const double d = sqrt(d2), inv = 1.0 / d;
+                const double inv = rsqrt(d2);
                 __syncwarp();
                 if (lane > j && lane < p) Rs[j * PM + lane] *= inv;
-                if (lane == j) Rs[j * PM + j] = d;
+                if (lane == j) Rs[j * PM + j] = inv;                                // the diagonal holds 1 / R_jj
                 __syncwarp();
                 const int m2 = p - 1 - j;                                           // trailing block, upper triangle incl. diagonal
                 for (int item = lane; item < m2 * m2; item += 32) {
@@ -447,12 +514,12 @@ __device__ int eig_fast_path(const EigArgs& a, DevState* st, int K, double mu, d
                     double v = Ys[(size_t)i * PM + k];
 #pragma unroll
                     for (int aa = 0; aa < EIG_PMAX; ++aa) if (aa < k) v = fma(-x[aa], Rs[aa * PM + k], v);
-                    x[k] = v / Rs[k * PM + k];
+                    x[k] = v * Rs[k * PM + k];
                     Xs[(size_t)i * PM + k] = x[k];
                 }
             }
         }
-        __syncthreads();
+        EF_TICK(6)
     }
     if (!converged) return 0;
 
@@ -460,18 +527,29 @@ __device__ int eig_fast_path(const EigArgs& a, DevState* st, int K, double mu, d
     // defect of X.  s >= 0 is the known downward bias of the int8 Gram on everything outside the leading pairs (half of the bound
     // in the error slot, see gram_i8.cu): the deflated matrix is re-centred before its norm is taken, and
     //     lambda_{p+1}(G) <= lambda_max(G - X theta X^T) <= gb - s.
-    const double sshift = 0.5 * a.G[(size_t)a.npad * a.npad + 8];
+    const double sshift = 0.5 * sqrt(fmax(a.G[(size_t)a.npad * a.npad + 8], 0.0));
     {
         const int row0 = c * L.RB, nrows = max(0, min(n, row0 + L.RB) - row0);
         const int rg = warp % L.RG, jc = warp / L.RG, rl = rg * 32 + lane, i = row0 + rl;
         double acc = 0.0;
-        if (jc < L.NJ && rl < nrows) {
+        if (L.gsm) {
+            // Y is no longer needed: keep X transposed there ([k][n]) so that threads with consecutive j read consecutive words
+            double* Xt = Ys;
+            for (int idx = tid; idx < n * p; idx += EIG_THREADS) { const int k = idx / n, j = idx - k * n; Xt[idx] = Xs[(size_t)j * PM + k]; }
+            __syncthreads();
+            for (int item = tid; item < nrows * n; item += EIG_THREADS) {
+                const int r2 = item / n, j = item - r2 * n, i2 = row0 + r2;
+                double g = Gs[item] + ((i2 == j) ? sshift : 0.0);
+                for (int k = 0; k < p; ++k) if (th[k] > 0.0) g = fma(-(th[k] + sshift) * Xt[(size_t)k * n + i2], Xt[(size_t)k * n + j], g);
+                acc = fma(g, g, acc);
+            }
+        } else if (jc < L.NJ && rl < nrows) {
             double xt[EIG_PMAX];
 #pragma unroll
             for (int k = 0; k < EIG_PMAX; ++k) xt[k] = (k < p && th[k] > 0.0) ? (th[k] + sshift) * Xs[(size_t)i * PM + k] : 0.0;
             const int j1 = min(n, (jc + 1) * L.JW);
             for (int j = jc * L.JW; j < j1; ++j) {
-                double g = __ldg(a.G + (size_t)j * a.npad + i) + ((i == j) ? sshift : 0.0);
+                double g = (L.gsm ? Gs[(size_t)rl * n + j] : __ldg(a.G + (size_t)j * a.npad + i)) + ((i == j) ? sshift : 0.0);
                 const double* xr = Xs + (size_t)j * PM;
 #pragma unroll
                 for (int k = 0; k < EIG_PMAX; ++k) if (k < p) g = fma(-xt[k], xr[k], g);
@@ -499,7 +577,9 @@ __device__ int eig_fast_path(const EigArgs& a, DevState* st, int K, double mu, d
         flag[2] = (double)ok;
         if (c == 0) { st->eig_info = steps | (ok ? 0x100 : 0); st->eig_gb = gb / tau; }
     }
-    __syncthreads();
+    EF_TICK(7)
+    if (c == 0 && tid == 0) for (int k = 0; k < 8; ++k) st->eig_clk[8 + k] = tph[k];
+#undef EF_TICK
     if (flag[2] == 0.0) return 0;
     if (c == 0) {
         for (int k = tid; k < K; k += EIG_THREADS) a.lam[k] = (k < p) ? th[k] : 0.0;     // everything else is certified below the threshold

@@ -92,7 +92,10 @@ __global__ void control_post_kernel(DevState* st, const double* part_zz, const u
         }
         if (lane == 0) {
             comm_tail[0] = zz; comm_tail[1] = nz; comm_tail[2] = (double)mx;
-            comm_tail[3] = 0.0;
+            // a clipped digit pass while S was not being stored leaves this rank with neither valid planes nor a current S: the
+            // flag travels with the other scalars (summed over the ranks), so every rank stops with done == 5 in the same
+            // iteration and the drivers repeat the solve with S stored every time (solver.cu bsub_run, dist.ShardedLSD)
+            comm_tail[3] = (track && !missing && wm >= 1.0e38f && st->s_stale_next) ? 1.0 : 0.0;
             // scale and validity of the slices are per rank (every rank turns its own partial Gram into doubles), so this
             // stays out of the all-reduced tail
             st->wm_local = (track && !missing) ? (double)wm : -1.0;
@@ -119,9 +122,7 @@ __global__ void control_post_kernel(DevState* st, const double* part_zz, const u
                     if (wm >= 1.0e38) st->wq_scale_next = st->wq_scale_next * 16.0;
                 }
                 if (st->force_dmma) st->gram_mode = 0;            // the int8 Gram has become too coarse for the shrinking threshold (eig.cu)
-                // a clipped digit pass leaves neither valid planes nor (if the store was skipped) a current S: the host restarts the
-                // solve with S stored in every iteration (solver.cu, bsub_run)
-                if (st->wq_saturated && st->s_stale) st->done = 5;
+
             }
         }
         if (phase & 2) {
@@ -136,7 +137,8 @@ __global__ void control_post_kernel(DevState* st, const double* part_zz, const u
                 IterLog& l = log[it - 1];
                 l.iter = it; l.svp = st->svp; l.sv = st->sv_used; l.pad = 0; l.err = err; l.mu = st->mu_iter; l.nnz = st->nnzS;
             }
-            if (err < st->tol) { st->done = 1; st->converged = 1; }
+            if (comm_tail[3] > 0.0) { st->done = 5; }               // unrecoverable digit saturation somewhere: restart (see phase 1)
+            else if (err < st->tol) { st->done = 1; st->converged = 1; }
             else if (it >= st->max_iter) { st->done = 2; }
         }
     }

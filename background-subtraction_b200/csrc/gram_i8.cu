@@ -477,7 +477,12 @@ __global__ void gram_i8_finish_kernel(const unsigned long long* __restrict__ Gin
     const double scale = (st != nullptr) ? st->wq_scale * st->wq_scale * 0x1p-38 : scale_override;
     // bound of what the dropped digit classes may have taken from an eigenvalue of this rank's partial Gram (0 when the fp64
     // Gram did the work); it travels with the Gram through the all-reduce, so every rank sees the same total (eig.cu)
-    if (err_slot != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && !(st != nullptr && st->done)) *err_slot = runs ? 2.0 * err_units * scale : 0.0;
+    // (stored squared: the dominant, coherent part of the error is a sum over pixels of zero-mean terms, so the bounds of
+    // the ranks' disjoint pixel sets combine like a root sum of squares)
+    if (err_slot != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && !(st != nullptr && st->done)) {
+        const double e = runs ? 2.0 * err_units * scale : 0.0;
+        *err_slot = e * e;
+    }
     if (!runs) return;
     const size_t ldg = (size_t)nblk * 128;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < npad * npad; idx += gridDim.x * blockDim.x) {

@@ -57,10 +57,11 @@ class TorchComm:
 class CudaStepSolver:
     """Thin object view of the bsub_step_* C entry points for one shard."""
 
-    def __init__(self, rows, cols_local, n, m_global, delta=10, max_iter=500, tile_rows=0, cluster_frames=0, store_S_lazily=False):
+    def __init__(self, rows, cols_local, n, m_global, delta=10, max_iter=500, tile_rows=0, cluster_frames=0, store_S_lazily=True):
         # store_S_lazily: let the single-pass shrink kernel skip the store of S in iterations that cannot be the last (it is
-        # rebuilt at the end).  The restart that covers a clipped digit pass is local to a rank, so ShardedLSD only honours
-        # this for world_size == 1; sharded runs store S in every iteration.
+        # rebuilt from D, Y and the digit planes at the end).  A clipped digit pass in such an iteration stops EVERY rank with
+        # done == 5 in the same iteration (the flag is part of the all-reduced scalars); ShardedLSD then repeats the solve
+        # with S stored every time.
         self.m = rows * cols_local
         cfg = api.make_config(self.m, n, C.PROX_FLAT_LINF, rows, cols_local, delta=delta, m_global=m_global,
                               d_global=min(m_global, n), max_iter=max_iter, tile_rows=tile_rows,
@@ -201,7 +202,7 @@ class ShardedLSD:
             if self.fence is not None:
                 fences.append(self.fence(it))
             self.iters_enqueued += 1
-        if getattr(s, "lazy_S", False) and comm.world == 1 and s.needs_restart():
+        if getattr(s, "lazy_S", False) and s.needs_restart():
             s.store_S_always()
             return self.solve(hooks)
         return self

@@ -237,8 +237,7 @@ def main():
         Dh[f0:f0 + stepf] = ((shard_u8[f0:f0 + stepf].astype(np.float64) - lo) * scale - mean_n).astype(np.float32)
     t_gen = time.perf_counter() - t_gen
 
-    solver = bdist.CudaStepSolver(rows, cols_local, frames, m, tile_rows=args.tile_rows, cluster_frames=args.cluster_frames,
-                                  store_S_lazily=(world == 1))
+    solver = bdist.CudaStepSolver(rows, cols_local, frames, m, tile_rows=args.tile_rows, cluster_frames=args.cluster_frames)
     solver.load(Dh)
     torch.cuda.synchronize()
     driver = bdist.ShardedLSD(solver, comm, fence=bdist.cuda_fence)
@@ -340,8 +339,8 @@ def main():
     # (shrink_flat, rebuild_S x2 when S is stored lazily), shrink_tma, control_post x2; per step: rowsum, Gram(D) (quantize_D + gram_i8 +
     # finish, or gram_dmma + reduce), eig, init_Y (not with the int8 path), (rebuild_S x2), lowrank, absmax/maxS, mask_stats, mask_write
     per_iter = 2 + (2 if use_i8 else 0) + 1 + (1 if info.get("use_proj") else 0) + (2 if info["use_stream"] else 1) + \
-        ((1 + (2 if world == 1 else 0)) if two_kernel else 0) + 2
-    gpu_launches = int(args.steps * (driver.iters_enqueued * per_iter + (10 if use_i8 else 9) + (2 if two_kernel and world == 1 else 0)))
+        (3 if two_kernel else 0) + 2
+    gpu_launches = int(args.steps * (driver.iters_enqueued * per_iter + (10 if use_i8 else 9) + (2 if two_kernel else 0)))
 
     # ---- end to end through the public host-buffer API (single GPU only) ----
     # Every clip: H2D of D from pinned memory, bsub_run, D2H of L, S and the mask -- all inside the timed region.  PCIe moves
@@ -525,8 +524,8 @@ def main():
     if two_kernel:
         # bytes per matrix element that the kernels are designed to move: projection reads the 4 digit bytes;
         # the single-pass kernel reads D, Y and writes Y and the 4 digit bytes of the next W, plus S when the iteration may be
-        # the last one (world == 1: lazily, ~4 of 19 iterations; sharded runs store it every time)
-        flat_b = 16.0 + (4.0 if world > 1 else 4.0 * 4 / max(iters, 1))
+        # the last one (the residual of the previous iteration within 4x of the tolerance: 2 of 19 iterations here)
+        flat_b = 16.0 + 4.0 * 2 / max(iters - 1, 1)
         kern = {
             "shrink_flat_kernel": {"ms": shrink_ms, "launches": n_shrink, "alg_bytes": flat_b * elems_local, "bound": "hbm"},
             "project_planes_kernel": {"ms": proj_ms, "launches": n_proj, "alg_bytes": 4.0 * elems_local, "bound": "hbm"},

@@ -20,4 +20,8 @@ for rep in range(2):
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print("rep", rep, "ms", round(dt * 1e3, 2), "iters", st.iter, "conv", st.converged, "counters", dec.counters(), flush=True)
 print("svp", [l['svp'] for l in dec.log()], "sv", [l['sv'] for l in dec.log()])
+import ctypes
+out = (ctypes.c_int64 * 16)()
+C.check(dec.lib.bsub_debug_eig_cycles(dec.h, out))
+print("eig fast-path cycles of the last call [load, matvec, grams, jacobi, rotate, resid, chol+solve, certificate]:", [int(v) for v in list(out)[8:16]])
 print(dec.debug_info())
