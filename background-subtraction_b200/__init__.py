@@ -2,7 +2,7 @@
 decomposition of yakovdan/Background-Subtraction (the LSD / group-sparse RPCA hot path), behind the reference's own
 Python call surface.  All numerics run in libbsub_b200.so (hand-written CUDA) through the C ABI of
 include/bsub_b200.h; there is no CPU fallback."""
-from .api import (BLOCK_SIZE, Decomposition, LSD, apply_background_shrinkage_operator, block_shrinkage_operator,
+from .api import (BLOCK_SIZE, Decomposition, center_window_decomposition, LSD, apply_background_shrinkage_operator, block_shrinkage_operator,
                   center_window_csc, detect_center_windows, detect_flat_tiling, detect_window_graph,
                   eig_topk, foreground_mask, getGraphSPAMS_all_groups, get_proximal_flat_groups_nonoverlap,
                   get_proximal_graph_group_centers, gram,
@@ -10,6 +10,9 @@ from .api import (BLOCK_SIZE, Decomposition, LSD, apply_background_shrinkage_ope
                   inexact_alm_lsd_batch, inexact_alm_lsd_with_background, inexact_alm_rpca,
                   labels_from_blocks, lsd_decomposition, make_config, normalizeImage, prox, prox_by_frame, prox_flat,
                   resize_with_cv2, svd_k_largest, window_csc, with_background_decomposition)
-from . import _cabi, api, build  # noqa: F401
+from .flow import (LSD_improved, apply_morph_ops, build_improved_LSD_graphs, calc_mask_percent, computeSCube, connected_components,
+                   filter_sparse_map, gkern, improved_LSD_weight_mask, merge_masks, motion_saliency_blocks,
+                   resize_with_cv2_by_first_axis, run_motion_saliency_check)
+from . import _cabi, api, build, flow  # noqa: F401
 
 __all__ = [n for n in dir() if not n.startswith("_")]

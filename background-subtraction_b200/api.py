@@ -578,6 +578,26 @@ def with_background_decomposition(D0, graphs, background_masks, delta=10, img_sh
     return dec
 
 
+def center_window_decomposition(D0, weight_mask, delta=10, img_shape=None, **tuning):
+    """inexact_alm_lsd_with_background straight from the [h, w, t] weight map of build_improved_LSD_graphs
+    (/root/reference/lsd_improvement.py:406-436): a positive entry is the weight of the 3x3 window centred on that pixel of that
+    frame, a negative one marks a background pixel -- the per-frame SPAMS graphs are never built."""
+    m, n = _shape_of(D0)
+    wm = np.asarray(weight_mask)
+    h, w = (int(v) for v in (img_shape if img_shape is not None else wm.shape[:2]))
+    if wm.shape != (h, w, n) or h * w != m:
+        raise Exception("weight_mask must be [h, w, t] with h*w = %d pixels and t = %d frames" % (m, n))
+    flat = np.ascontiguousarray(wm.transpose(2, 1, 0)).reshape(n, m)          # [t][p], p = j*rows + i
+    eta = np.where(flat > 0, flat, 0).astype(np.float32)
+    bg = np.ascontiguousarray((flat < 0).astype(np.uint8))
+    cfg = make_config(m, n, C.PROX_GRAPH_CENTER_BG, h, w, delta=delta, **tuning)
+    dec = Decomposition(cfg)
+    C.check(dec.lib.bsub_set_center_windows(dec.h, eta.ctypes.data_as(C.c_float_p), bg.ctypes.data_as(C.c_uint8_p)))
+    dec.load(D0)
+    dec.run()
+    return dec
+
+
 def inexact_alm_lsd_with_background(D0, graphs, background_masks, delta=10, img_shape=None, verbose=False, **tuning):
     """Drop-in for /root/reference/lsd_improvement.py:215-304 -> (L, S, iter_out, converged): one centre-window graph
     per frame (prox_by_frame) plus the l2 shrink of every frame's background pixels at 100 lambda / mu."""
@@ -672,14 +692,9 @@ def normalizeImage(image):
 
 
 def resize_with_cv2(images, ratio):
-    """/root/reference/utils.py:129-136 (host, OpenCV)."""
-    import cv2
-    size = [int(np.ceil(images.shape[i] * ratio)) for i in [0, 1]]
-    out = np.empty(size + [images.shape[2]])
-    interp = cv2.INTER_AREA if ratio < 1 else cv2.INTER_CUBIC
-    for t in range(images.shape[2]):
-        out[:, :, t] = cv2.resize(images[:, :, t], size[::-1], interpolation=interp)
-    return out
+    """/root/reference/utils.py:129-136 on the device (cv2.INTER_AREA / INTER_CUBIC restated in csrc/post.cu)."""
+    from . import flow
+    return flow.resize_with_cv2(images, ratio)
 
 
 def LSD(ImData0, frame_start, frame_end, downsample_ratio, use_flat=False):

@@ -122,7 +122,7 @@ __device__ void eig_control(const EigArgs& a, DevState* st, int K, double mu, do
     if (tid == 0) {
         // truncation-error bound of the int8 Gram (gram_i8.cu; summed over the ranks by the all-reduce, 0 for the fp64 Gram):
         // beyond 0.3 (1/mu)^2 a singular value a little above the threshold could be lost, so the solve continues on gram.cu
-        const double ge = sqrt(fmax(a.G[(size_t)a.npad * a.npad + 8], 0.0)) / (thresh * thresh);
+        const double ge = a.G[(size_t)a.npad * a.npad + 8] / (thresh * thresh);
         st->gram_err = ge;
         if (ge > 0.3) st->force_dmma = 1;
         int svp = 0;
@@ -171,12 +171,16 @@ constexpr int EIG_PMAX = 16;
 struct EigFastLayout { int PM, RB, RG, NJ, JW, RBP, gsm; size_t doubles, scratch; };
 __host__ __device__ inline EigFastLayout eig_fast_layout(int n, int C) {
     EigFastLayout L;
-    L.PM = (n <= 448) ? 16 : 8;
+    L.PM = 16;
     L.RB = (n + C - 1) / C;
     L.RG = (L.RB + 31) / 32;
-    L.NJ = EIG_WARPS / L.RG; if (L.NJ < 1) L.NJ = 1;
-    L.JW = (n + L.NJ - 1) / L.NJ;
     L.RBP = L.RG * 32;
+    L.NJ = EIG_WARPS / L.RG; if (L.NJ < 1) L.NJ = 1;
+    {   // long clips: the partial-sum scratch [NJ][PM][RBP] must fit beside X and Y (fewer, longer column chunks)
+        const size_t fixed0 = (size_t)2 * n * L.PM + (size_t)5 * L.PM * L.PM + (size_t)6 * L.PM + 16 + 8 + 64;
+        while (L.NJ > 1 && (fixed0 + (size_t)L.NJ * L.PM * L.RBP) * sizeof(double) > (size_t)222 * 1024) --L.NJ;
+    }
+    L.JW = (n + L.NJ - 1) / L.NJ;
     // this CTA's rows of G in shared memory ([RB][n]) when they fit beside X and Y: the products then need no partial sums
     const size_t fixed = (size_t)2 * n * L.PM + (size_t)5 * L.PM * L.PM + (size_t)6 * L.PM + 16 + 8 + 64;
     const size_t with_g = fixed + (size_t)4 * EIG_THREADS + (size_t)L.RB * n;
@@ -527,7 +531,7 @@ __device__ int eig_fast_path(const EigArgs& a, DevState* st, int K, double mu, d
     // defect of X.  s >= 0 is the known downward bias of the int8 Gram on everything outside the leading pairs (half of the bound
     // in the error slot, see gram_i8.cu): the deflated matrix is re-centred before its norm is taken, and
     //     lambda_{p+1}(G) <= lambda_max(G - X theta X^T) <= gb - s.
-    const double sshift = 0.5 * sqrt(fmax(a.G[(size_t)a.npad * a.npad + 8], 0.0));
+    const double sshift = 0.5 * a.G[(size_t)a.npad * a.npad + 8];
     {
         const int row0 = c * L.RB, nrows = max(0, min(n, row0 + L.RB) - row0);
         const int rg = warp % L.RG, jc = warp / L.RG, rl = rg * 32 + lane, i = row0 + rl;

@@ -477,12 +477,7 @@ __global__ void gram_i8_finish_kernel(const unsigned long long* __restrict__ Gin
     const double scale = (st != nullptr) ? st->wq_scale * st->wq_scale * 0x1p-38 : scale_override;
     // bound of what the dropped digit classes may have taken from an eigenvalue of this rank's partial Gram (0 when the fp64
     // Gram did the work); it travels with the Gram through the all-reduce, so every rank sees the same total (eig.cu)
-    // (stored squared: the dominant, coherent part of the error is a sum over pixels of zero-mean terms, so the bounds of
-    // the ranks' disjoint pixel sets combine like a root sum of squares)
-    if (err_slot != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && !(st != nullptr && st->done)) {
-        const double e = runs ? 2.0 * err_units * scale : 0.0;
-        *err_slot = e * e;
-    }
+    if (err_slot != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && !(st != nullptr && st->done)) *err_slot = runs ? 2.0 * err_units * scale : 0.0;
     if (!runs) return;
     const size_t ldg = (size_t)nblk * 128;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < npad * npad; idx += gridDim.x * blockDim.x) {
@@ -500,7 +495,7 @@ __global__ void gram_i8_finish_kernel(const unsigned long long* __restrict__ Gin
 // -------------------------------------------------------------------------------------------------------------
 GramI8Plan make_gram_i8_plan(int n, long long ldq, int num_sms) {
     GramI8Plan p;
-    p.n = n; p.ldq = ldq; p.m_real = 0;
+    p.n = n; p.ldq = ldq; p.m_real = 0; p.m_global = 0;
     p.nblk = (n + 127) / 128;
     p.nkb = (int)(ldq / GI_KB);          // ldq = pixels per frame in the slice matrix, a multiple of 64
     p.smem_bytes = (size_t)GI_STAGES * GI_STAGE_BYTES + 256 + 1024;
@@ -580,7 +575,10 @@ int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const CUtensorMa
     // solve to the fp64 Gram (gram.cu) once that bound stops being small against the threshold (1/mu)^2 (eig.cu, force_dmma).
     // m_real = 0 (operator test) keeps the raw integer sums.  (The int64 accumulators hold the kept classes / 256^3: 2^-24.)
     const double E_d = 5461.5 + 128.0 + 65536.0 * 5461.5 + 131072.0 * 0.25, E_o = 6.2e8;
-    const double err_units = (p.m_real > 0) ? sqrt((double)p.m_real) * ((double)p.n + 3.0 * sqrt((double)p.n)) * E_o * 0x1p-24 : 0.0;
+    // Pixel-sharded runs: the noise is a sum over ALL pixels of zero-mean terms, so its norm grows like sqrt(m_global); every rank
+    // takes its share m / m_global of that global bound, and the all-reduce of the slot adds the shares up again.
+    const double mg = (double)std::max(p.m_global, p.m_real);
+    const double err_units = (p.m_real > 0) ? ((double)p.m_real / sqrt(mg)) * ((double)p.n + 3.0 * sqrt((double)p.n)) * E_o * 0x1p-24 : 0.0;
     const double diag_bias = (p.m_real > 0) ? (double)p.m_real * E_d * 0x1p-24 - err_units : 0.0;
     const size_t gbytes = sizeof(unsigned long long) * (size_t)p.nblk * 128 * p.nblk * 128;
     BSUB_CUDA_CHECK(cudaMemsetAsync(Gint, 0, gbytes, stream));

@@ -25,7 +25,8 @@ int launch_gram(const GramPlan& p, const GramMaps& maps, bool combo, const int2*
 
 // ---------------------------------------------------------------- gram_i8.cu (tcgen05 int8 Gram from the W slices)
 struct GramI8Plan { int n, nblk, nkb, grid; long long ldq; size_t smem_bytes;
-                    long long m_real; };   // pixels that hold real data (0: no correction of the dropped digit classes)
+                    long long m_real;       // pixels that hold real data (0: no correction of the dropped digit classes)
+                    long long m_global; };  // pixels of the whole matrix (pixel-sharded runs), 0 = m_real
 GramI8Plan make_gram_i8_plan(int n, long long ldq, int num_sms);
 void fill_gram_i8_tables(const GramI8Plan& p, std::vector<int4>& cta_info, std::vector<int>& blk_n);
 int make_gram_i8_map(const GramI8Plan& p, const signed char* Wq, CUtensorMap* map, int box_frames);

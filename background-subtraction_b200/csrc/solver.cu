@@ -233,6 +233,7 @@ int bsub_create(const bsub_config* cfg, bsub_solver** out) {
             const long long ldq = shrink_stream_ldq(s->ssp);
             s->gip = make_gram_i8_plan(s->n, ldq, s->num_sms);
             s->gip.m_real = (getenv("BSUB_NO_GRAM_BIAS") == nullptr) ? s->m : 0;
+            s->gip.m_global = s->cfg.m_global;
             std::vector<int4> info; std::vector<int> blkn;
             fill_gram_i8_tables(s->gip, info, blkn);
             s->gi_ncta = (int)info.size();

@@ -191,6 +191,46 @@ int bsub_eig_topk(const double* G_host, int32_t n, int32_t k, double* lam_host, 
 /* the tcgen05 int8 Gram on its own: slices int8[4][n][ldq] (host), G int64[n][n] = sum_p sum_{i+j>=3} 256^(i+j-3) d_i(f,p) d_j(g,p) */
 int bsub_gram_i8_test(const int8_t* slices_host, int32_t n, int64_t ldq, int64_t* G_host);
 
+/* ---- stages on either side of the decomposition; device pointers, csrc/post.cu ---- */
+/* resize_with_cv2 / resize_with_cv2_by_first_axis (utils.py:119-136): cv2.resize of n images, interp 0 = INTER_AREA (shrinking),
+ * 1 = INTER_CUBIC.  Element (f, y, x) of src lives at f*src_stride_f + y*src_stride_y + x*src_stride_x (elements); same for dst.
+ * Synchronises the stream before it returns. */
+int bsub_resize_dev(const float* src, int64_t src_stride_f, int64_t src_stride_y, int64_t src_stride_x, int32_t src_h, int32_t src_w, int32_t n,
+                    float* dst, int64_t dst_stride_f, int64_t dst_stride_y, int64_t dst_stride_x, int32_t dst_h, int32_t dst_w, int32_t interp,
+                    void* stream);
+/* cv2.connectedComponentsWithStats(frame, 8, CV_32S) for every frame (utils.py:411-416, motion_saliency_check.py:25-28):
+ * mask uint8[n][ld_mask] (non-zero = foreground, pixel p = j*rows + i), labels int32[n][ld]: 0 = background, 1..num_labels[f]
+ * numbered by the smallest pixel index of each component; num_labels int32[n] (device); scratch 2*n*ld int32. */
+int bsub_cc_label_dev(const uint8_t* mask, int64_t ld_mask, int32_t rows, int32_t cols, int32_t n, int32_t* labels, int64_t ld, int32_t* num_labels,
+                      int32_t* scratch, void* stream);
+/* per-component area, box {min row, max row, min col, max col, key} and (optional) sum of weight[f, j, i] over the component
+ * (compute_groups_per_frame, motion_saliency_check.py:44-47); key = index of the first 2x2 block (raster order) that meets the
+ * component: sorting a frame's components by it reproduces OpenCV's label numbering.  offsets int32[n] = exclusive prefix sum of
+ * num_labels (device), total = their sum; area int32[total], box int32[total][5], wsum double[total] (device). */
+int bsub_cc_stats_dev(const int32_t* labels, int64_t ld, int32_t rows, int32_t cols, int32_t n, const int32_t* offsets, int32_t total,
+                      const float* weight, int64_t w_stride_f, int64_t w_stride_j, int64_t w_stride_i, int32_t* area, int32_t* box, double* wsum,
+                      void* stream);
+/* label image -> uint8 map through a per-component table (uint8[total], device): out[f][p] = table[offsets[f] + label - 1], 0 stays 0.
+ * Turns the components kept by run_motion_saliency_check (motion_saliency_check.py:66-120) into the block map of bsub_set_blocks. */
+int bsub_cc_remap_dev(const int32_t* labels, int64_t ld, int64_t m, int32_t n, const int32_t* offsets, const uint8_t* table, uint8_t* out, int64_t ld_out,
+                      void* stream);
+/* filter_sparse_map(sparse_array, size_thresh) (utils.py:404-420): keep the pixels of 8-connected components with area > size_thresh.
+ * mask, out uint8[n][ld]; scratch 3*n*rows*cols int32. */
+int bsub_filter_sparse_map_dev(const uint8_t* mask, int64_t ld_mask, int32_t rows, int32_t cols, int32_t n, int32_t size_thresh, uint8_t* out,
+                               int64_t ld_out, int32_t* scratch, void* stream);
+/* computeSCube (computeSCube.py:22-50,82-92): cube[t][h][w] = |xt[w][h][t]| * |yt[h][w][t]| and its sum (double, device);
+ * scratch >= 2048 doubles.  The normalisation by the sum is applied by the first smoothing pass (divide_by_dev). */
+int bsub_scube_product_dev(const float* xt, const float* yt, float* cube, int32_t T, int32_t H, int32_t W, double* sum_out, double* scratch,
+                           void* stream);
+/* one axis of scipy.ndimage.convolve(..., mode='reflect') with a separable kernel (computeSCube.py:90):
+ * dst[o, i, r] = (1/divide_by) * sum_k w[k] * src[o, reflect(i + k - shift), r], array viewed as [outer][len][inner]. */
+int bsub_conv1d_reflect_dev(const float* src, float* dst, int64_t outer, int32_t len, int64_t inner, const float* weights_dev, int32_t taps,
+                            int32_t shift, const double* divide_by_dev, void* stream);
+/* binary dilation (erode = 0) / erosion (erode = 1) of every frame by skimage.morphology.disk(radius) (apply_morph_ops,
+ * lsd_improvement.py:323-335); src, dst uint8[n][ld]; scratch n*rows*cols + 2*radius + 1 bytes. */
+int bsub_morph_disk_dev(const uint8_t* src, int64_t ld_src, uint8_t* dst, int64_t ld_dst, int32_t rows, int32_t cols, int32_t n, int32_t radius,
+                        int32_t erode, uint8_t* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
