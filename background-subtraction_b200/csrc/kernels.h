@@ -116,7 +116,8 @@ int launch_shrink_stream(const ShrinkStreamPlan& p, const ShrinkTmaMaps& maps, S
 
 // ---------------------------------------------------------------- shrink_flat.cu (single-pass streamed shrink, rank <= 8, T from project.cu)
 struct ShrinkFlatPlan { int n, rows, cols, FC, NS, nchunkf, ntile_r, grid; long long ld, ntiles; size_t smem_bytes; };
-struct ShrinkFlatMaps { CUtensorMap D, S, Y, Q, VC; };
+struct ShrinkFlatMaps { CUtensorMap D, S, Y, Q, VC;
+                        CUtensorMap Qs; };   // digit planes, 8 frames x 9 units per box, 128-byte swizzle (register-transposed stores)
 bool make_shrink_flat_plan(int n, int rows, int cols, long long ld, int num_sms, const ShrinkStreamPlan& sp, ShrinkFlatPlan* out);
 int make_shrink_flat_maps(const ShrinkFlatPlan& p, const float* D, float* S, float* Y, signed char* Wq, long long ldq, const float* VC, int vstride,
                           ShrinkFlatMaps* m);

@@ -32,6 +32,10 @@ WORKLOADS = {
     "synthetic_small": (240, 320, 48, 5, 3),
     # the reference's own clip (BASELINE.json config 1): data/WaterSurface.mat, kept as tests/golden/watersurface_u8.npz
     "watersurface": (128, 160, 48, None, None),
+    # BASELINE.json configs 2 and 5 (scripts/bench_flows.py): the precomputed_main flow on the committed input/ fixture, and 64
+    # independent 320x240x200 clips spread over the GPUs
+    "highway_flow": (120, 160, 289, None, None),
+    "batch64_qvga_200": (240, 320, 200, 100, 3),
 }
 
 
@@ -215,6 +219,18 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.workload in ("highway_flow", "batch64_qvga_200"):
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_flows
+        if args.workload == "highway_flow":
+            out = bench_flows.highway_flow(args, rank, world, ClockSampler)
+        else:
+            out = bench_flows.batch_clips(args, rank, world, local_rank, ClockSampler)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     comm = bdist.TorchComm()
     rows, cols, frames, seed, nrect = WORKLOADS[args.workload]
     m = rows * cols

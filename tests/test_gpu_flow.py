@@ -120,3 +120,15 @@ def test_LSD_improved_two_pass(B, F, watersurface_u8):
     assert (S_mask == mask_ref).mean() >= 0.999
     with pytest.raises(Exception, match="alg ver"):
         B.LSD_improved(cube.copy(order='F'), 0, 15, 1, alg_ver=3)
+
+
+def test_motion_saliency_golden_highway(B, highway_fixture):
+    """Device run_motion_saliency_check on the inputs of the reference run that produced the committed labels / lambdas."""
+    from test_oracle_flow import highway_saliency_inputs
+    xc, mask1, sal = highway_saliency_inputs(highway_fixture)
+    labels, ptr, lam = B.motion_saliency_blocks(xc.shape, mask1, sal)
+    assert np.array_equal(ptr, highway_fixture["lam_ptr"])
+    assert np.array_equal(labels.cpu().numpy(), highway_fixture["labels"])
+    assert np.allclose(lam[:-1], highway_fixture["lam"], rtol=2e-6, atol=0)        # float32 saliency cube on the device
+    gb, wb = B.run_motion_saliency_check(xc, mask1, sal)
+    assert [len(g) for g in gb] == np.diff(ptr).tolist() and gb[0][0].dtype == bool if len(gb[0]) else True

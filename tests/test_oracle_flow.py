@@ -130,3 +130,28 @@ def test_merge_masks_against_reference():
     ref = R.load()["lsd_improvement"]
     a, b = random_masks(1, 10, 12, 3)[..., 0], random_masks(2, 10, 12, 3)[..., 0]
     assert np.array_equal(ref.merge_masks((a, a | b), (1, 1.5)), F.merge_masks((a, a | b), (1, 1.5)))
+
+
+def highway_saliency_inputs(fx):
+    """Inputs of the run_motion_saliency_check call that produced the fixture's labels (tests/golden/make_golden.py)."""
+    frames = fx["frames"]
+    h, w, t = frames.shape
+    x = np.asfortranarray(frames.astype(np.float64))
+    x -= np.min(x)
+    x *= 1.0 / np.max(x)
+    sal = np.abs(x - np.median(x, axis=2, keepdims=True))
+    sal /= sal.sum()
+    mask1 = np.unpackbits(fx["lsd_mask"])[:h * w * t].reshape((h * w, t), order='F').reshape((h, w, t), order='F').astype(bool)
+    return x - np.mean(x), mask1, sal
+
+
+def test_motion_saliency_golden_highway(highway_fixture):
+    """The labels / lambdas committed with the fixture came from the reference's own run_motion_saliency_check."""
+    xc, mask1, sal = highway_saliency_inputs(highway_fixture)
+    gb, wb = F.run_motion_saliency_check(xc, mask1, sal)
+    labels, ptr, lam = highway_fixture["labels"], highway_fixture["lam_ptr"], highway_fixture["lam"]
+    assert [len(g) for g in gb] == np.diff(ptr).tolist()
+    for f in range(len(gb)):
+        for b, g in enumerate(gb[f]):
+            assert np.array_equal(g, labels[f] == b + 1)
+            assert abs(wb[f][b] - lam[ptr[f] + b]) <= 1e-12 * lam[ptr[f] + b]
