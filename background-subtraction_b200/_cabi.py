@@ -102,6 +102,8 @@ SIGNATURES = {
                                                   ctypes.c_int64, vp, vp]),
     "bsub_scube_product_dev": (ctypes.c_int, [vp, vp, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, vp, vp]),
     "bsub_conv1d_reflect_dev": (ctypes.c_int, [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, vp, ctypes.c_int32, ctypes.c_int32, vp, vp]),
+    "bsub_rpca_rank1_batch_dev": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.c_double,
+                                                 ctypes.c_double, ctypes.c_double, ctypes.c_int32, vp, vp, vp, vp, vp, vp]),
     "bsub_morph_disk_dev": (ctypes.c_int, [vp, ctypes.c_int64, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                            ctypes.c_int32, vp, vp]),
 }

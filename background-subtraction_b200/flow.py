@@ -419,3 +419,65 @@ def LSD_improved(ImData0, frame_start=0, frame_end=47, downsample_ratio=1, delta
     L, S, iterations, converged = A._finish(dec, D, False)
     S_mask = dec.mask(2).reshape(shape, order='F')
     return (S, S_mask, L.reshape(shape, order='F'), ImData1, ImMean, shape, iterations, converged, graph_iter, graph_converged)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# stage 2: saliency RPCA over the X-T and Y-T slices (computeRPCADecomposition.py)
+# --------------------------------------------------------------------------------------------------------------
+def inexact_alm_rpca_batch(slices, delta=1.0, max_rank=1, tol=1e-7, tol_l1=0.0, max_iter=500, rho=1.2, return_info=False):
+    """inexact_alm_rpca (/root/reference/lsd_improvement.py:123-196) on every slices[i, :, :] at once, the rank of L capped at
+    max_rank = 1: one thread-block cluster per slice, state resident in shared memory (csrc/rpca_batch.cu).  -> (L, S) like the
+    input ([slices, rows, cols]); with return_info also the per-slice iteration counts (negative: not converged), errors, ranks."""
+    if max_rank != 1:
+        raise Exception("inexact_alm_rpca_batch: the batched kernel caps the rank at 1 (use inexact_alm_rpca for a free rank)")
+    torch = _torch()
+    on_dev = A._is_torch(slices)
+    M = slices.to(torch.float32).contiguous() if on_dev else torch.from_numpy(np.ascontiguousarray(slices, dtype=np.float32)).to("cuda")
+    if M.dim() != 3:
+        raise Exception("inexact_alm_rpca_batch: slices must be [batch, rows, cols]")
+    batch, rows, cols = (int(v) for v in M.shape)
+    L, S = torch.empty_like(M), torch.empty_like(M)
+    iters = torch.empty(batch, dtype=torch.int32, device="cuda")
+    rank = torch.empty(batch, dtype=torch.int32, device="cuda")
+    err = torch.empty(batch, dtype=torch.float32, device="cuda")
+    C.check(C.load().bsub_rpca_rank1_batch_dev(_vp(M), batch, rows, cols, float(delta), float(rho), float(tol), float(tol_l1), int(max_iter),
+                                               _vp(L), _vp(S), _vp(iters), _vp(err), _vp(rank), A._stream_ptr()))
+    torch.cuda.current_stream().synchronize()
+    if not on_dev:
+        L, S = L.double().cpu().numpy(), S.double().cpu().numpy()
+    if return_info:
+        return L, S, {"iters": iters.cpu().numpy(), "err": err.cpu().numpy(), "rank": rank.cpu().numpy()}
+    return L, S
+
+
+def compute_RPCA(image_array, grayscale=True, max_error=None, max_iter=200000):
+    """Drop-in for /root/reference/computeRPCADecomposition.py:12-48 (grayscale branch) -> (L_array, S_array): a max_rank = 1
+    robust PCA of every image_array[i, :, :].  The reference hands each slice to RobustPCA(max_rank=1, tol=max_error) -- a package
+    that is not vendored, pinned or installable (parity unpinned there); here every slice goes through the reference's own
+    inexact_alm_rpca iteration with the rank capped at 1, stopped by the same residual test sum|M - L - S| <= max_error (or the
+    iteration's own 1e-7 relative tolerance, whichever comes first; 500 iterations at most, like inexact_alm_rpca)."""
+    if not grayscale:
+        raise Exception("compute_RPCA: only the grayscale work mode (the reference's default) is implemented in this build")
+    if max_error is None:
+        max_error = image_array.shape[1] * image_array.shape[2] * 0.0001
+    return inexact_alm_rpca_batch(image_array, delta=1.0, tol_l1=float(max_error), max_iter=min(int(max_iter), 500))
+
+
+def executeSaliencyRPCA(ImData, downsample_ratio, grayscale_workmode=True, grayscale_input=True):
+    """Drop-in for /root/reference/computeRPCADecomposition.py:52-95 -> (xt_lowrank, xt_sparse, yt_lowrank, yt_sparse): the video
+    [t, h, w] cut into X-T planes ([w, h, t]) and Y-T planes ([h, w, t]), each resized by 1/downsample_ratio over its first two
+    axes (resize_with_cv2) and decomposed slice by slice."""
+    if not (grayscale_workmode and grayscale_input):
+        raise Exception("executeSaliencyRPCA: only the grayscale mode is implemented in this build")
+    torch = _torch()
+    v = ImData.to(torch.float32) if A._is_torch(ImData) else torch.from_numpy(np.ascontiguousarray(ImData, dtype=np.float32)).to("cuda")
+    xt = v.permute(2, 1, 0).contiguous()
+    yt = v.permute(1, 2, 0).contiguous()
+    if downsample_ratio != 1:
+        xt = resize_with_cv2(xt, 1 / downsample_ratio)
+        yt = resize_with_cv2(yt, 1 / downsample_ratio)
+    xt_l, xt_s = compute_RPCA(xt, True, xt.shape[1] * xt.shape[2] * 0.0001)
+    yt_l, yt_s = compute_RPCA(yt, True, yt.shape[1] * yt.shape[2] * 0.0001)
+    if A._is_torch(ImData):
+        return xt_l, xt_s, yt_l, yt_s
+    return tuple(x.double().cpu().numpy() for x in (xt_l, xt_s, yt_l, yt_s))

@@ -230,6 +230,14 @@ int bsub_conv1d_reflect_dev(const float* src, float* dst, int64_t outer, int32_t
  * lsd_improvement.py:323-335); src, dst uint8[n][ld]; scratch n*rows*cols + 2*radius + 1 bytes. */
 int bsub_morph_disk_dev(const uint8_t* src, int64_t ld_src, uint8_t* dst, int64_t ld_dst, int32_t rows, int32_t cols, int32_t n, int32_t radius,
                         int32_t erode, uint8_t* scratch, void* stream);
+/* compute_RPCA (computeRPCADecomposition.py:12-48), grayscale branch: one rank-capped (max_rank = 1) robust PCA per slice D[b]
+ * (float32 [batch][rows][cols], device), all slices in one launch.  Engine: the reference's own inexact_alm_rpca iteration
+ * (lsd_improvement.py:123-196: lambda = 1/(sqrt(max(rows, cols)) delta), Y0 = D/max(||D||_2, ||D||_inf/lambda), mu0 = 1.25/||D||_2,
+ * mu *= rho) with the rank of L capped at 1; stops when ||Z||_F/||D||_F < tol or (tol_l1 > 0) sum|Z| <= tol_l1 or after max_iter.
+ * iters[b] > 0: iterations used; < 0: -max_iter, tolerance not met.  err[b] = last ||Z||_F/||D||_F, rank[b] in {0, 1}.
+ * cols <= 640 and 4 * ceil(rows/8) * cols floats must fit the shared memory of one CTA (csrc/rpca_batch.cu). */
+int bsub_rpca_rank1_batch_dev(const float* D, int32_t batch, int32_t rows, int32_t cols, double delta, double rho, double tol,
+                              double tol_l1, int32_t max_iter, float* L, float* S, int32_t* iters, float* err, int32_t* rank, void* stream);
 
 #ifdef __cplusplus
 }

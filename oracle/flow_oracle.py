@@ -312,3 +312,61 @@ def LSD_improved_from_weight_mask(D, shape, wm):
     bg = [(wm[:, :, i] < 0).flatten(order='F') for i in range(t)]
     L, S, it, conv = O.inexact_alm_lsd_with_background(D, graphs, bg)
     return L, S, it, conv, O.foreground_mask(D, L, S, 2).reshape(shape, order='F')
+
+
+# ---------------------------------------------------------------- stage-2 saliency RPCA (computeRPCADecomposition.py:12-95)
+def inexact_alm_rpca_capped(D0, delta=1.0, max_rank=None, tol_out=1e-7, tol_l1=0.0, max_iter=500, rho=1.2):
+    """inexact_alm_rpca (lsd_improvement.py:123-196, use_sv_prediction=False) with an optional cap on the rank of L and an optional
+    second stopping test sum|Z| <= tol_l1 (the test RobustPCA(tol=...) applies in compute_RPCA).  max_rank=None, tol_l1=0 is the
+    reference function itself (pinned in tests/test_oracle_flow.py).  Returns (L, S, iterations, converged)."""
+    D = np.asarray(D0, dtype=np.float64)
+    m, n = D.shape
+    lam = (np.sqrt(max(m, n)) * delta) ** (-1)
+    norm_two = np.linalg.norm(D, ord=2)
+    norm_inf = np.linalg.norm(D, ord=np.inf) / lam
+    Y = D / max(norm_two, norm_inf)
+    mu = 1.25 / norm_two
+    L = np.zeros_like(D)
+    S = np.zeros_like(D)
+    for it in range(1, max_iter + 1):
+        u, s, vh = np.linalg.svd(D - S + Y / mu, full_matrices=False)
+        svp = int(np.sum(s - 1 / mu > 0))
+        if max_rank is not None:
+            svp = min(svp, max_rank)
+        L = (u[:, :svp] * (s[:svp] - 1 / mu)) @ vh[:svp, :]
+        G = D - L + Y / mu
+        S = np.maximum(G - lam / mu, 0) + np.minimum(G + lam / mu, 0)
+        Z = D - L - S
+        Y = Y + mu * Z
+        mu = min(mu * rho, mu * 1e7)
+        err = np.linalg.norm(Z, 'fro') / np.linalg.norm(D, 'fro')
+        if err < tol_out or (tol_l1 > 0 and np.sum(np.abs(Z)) <= tol_l1):
+            return L, S, it, True
+    return L, S, max_iter, False
+
+
+def compute_RPCA(image_array, max_error, max_iter=500):
+    """compute_RPCA (computeRPCADecomposition.py:12-48), grayscale branch, with the engine this repo substitutes for the
+    un-installable RobustPCA package (PARITY UNPINNED at that boundary): rank-1-capped inexact_alm_rpca per slice, stopped by
+    sum|M - L - S| <= max_error."""
+    L = np.zeros(image_array.shape)
+    S = np.zeros(image_array.shape)
+    its = []
+    for i in range(image_array.shape[0]):
+        L[i], S[i], it, conv = inexact_alm_rpca_capped(image_array[i], 1.0, 1, 1e-7, max_error, max_iter)
+        its.append(it if conv else -it)
+    return L, S, np.array(its)
+
+
+def executeSaliencyRPCA(video_thw, downsample_ratio):
+    """executeSaliencyRPCA (computeRPCADecomposition.py:52-95), grayscale."""
+    xt = video_thw.transpose([2, 1, 0])
+    yt = video_thw.transpose([1, 2, 0])
+    if downsample_ratio != 1:
+        xt = resize_with_cv2(xt, 1 / downsample_ratio)
+        yt = resize_with_cv2(yt, 1 / downsample_ratio)
+    xt = xt.astype(np.float64)
+    yt = yt.astype(np.float64)
+    xl, xs, _ = compute_RPCA(xt, xt.shape[1] * xt.shape[2] * 0.0001)
+    yl, ys, _ = compute_RPCA(yt, yt.shape[1] * yt.shape[2] * 0.0001)
+    return xl, xs, yl, ys

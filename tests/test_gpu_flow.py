@@ -132,3 +132,39 @@ def test_motion_saliency_golden_highway(B, highway_fixture):
     assert np.allclose(lam[:-1], highway_fixture["lam"], rtol=2e-6, atol=0)        # float32 saliency cube on the device
     gb, wb = B.run_motion_saliency_check(xc, mask1, sal)
     assert [len(g) for g in gb] == np.diff(ptr).tolist() and gb[0][0].dtype == bool if len(gb[0]) else True
+
+
+@pytest.mark.parametrize("h,w,t", [(48, 64, 40), (60, 45, 33), (240, 320, 200)])
+def test_saliency_rpca_batch(B, F, h, w, t):
+    """compute_RPCA / executeSaliencyRPCA (computeRPCADecomposition.py:12-95): every X-T and Y-T slice through the rank-1-capped
+    inexact_alm_rpca, one cluster per slice, against the float64 oracle with an exact SVD."""
+    from test_oracle_flow import saliency_slices
+    from background_subtraction_b200 import flow
+    video = saliency_slices(7, h, w, t)                                      # [t, h, w], 0..255
+    xt = np.ascontiguousarray(video.transpose(2, 1, 0))                      # [w, h, t]
+    nsl = min(xt.shape[0], 12)
+    tol_l1 = xt.shape[1] * xt.shape[2] * 1e-4
+    L, S, info = flow.inexact_alm_rpca_batch(xt, delta=1.0, tol_l1=tol_l1, return_info=True)
+    assert L.shape == xt.shape and np.all(info["iters"] > 0) and np.all(info["rank"] == 1)
+    sel = np.linspace(0, xt.shape[0] - 1, nsl).astype(int)
+    Lr, Sr, its = F.compute_RPCA(xt[sel], tol_l1)
+    print("[saliency batch] iters gpu", info["iters"][sel].tolist(), "oracle", its.tolist())
+    assert np.all(np.abs(info["iters"][sel] - its) <= 1)
+    for k, i in enumerate(sel):
+        same_iters = info["iters"][i] == its[k]
+        assert rel_fro(L[i], Lr[k]) <= 1e-4
+        if same_iters:
+            assert rel_fro(S[i], Sr[k]) <= 1e-4
+        assert np.sum(np.abs(xt[i] - L[i] - S[i])) <= 2 * tol_l1            # float32 L + S against the float64 input
+    # the drop-in pair and the chain into computeSCube
+    Lc, Sc = B.compute_RPCA(xt[sel], True, tol_l1)
+    assert np.array_equal(Lc, L[sel]) and np.array_equal(Sc, S[sel])
+    if h * w * t <= 60 * 45 * 40:
+        xl, xs, yl, ys = B.executeSaliencyRPCA(video, 1)
+        rxl, rxs, ryl, rys = F.executeSaliencyRPCA(video, 1)
+        assert xs.shape == (w, h, t) and ys.shape == (h, w, t)
+        cube = B.computeSCube(xs, ys)
+        ref = F.compute_scube_separable(rxs, rys)
+        assert np.abs(cube - ref).max() <= 2e-3 * np.abs(ref).max()
+    with pytest.raises(Exception, match="rank"):
+        flow.inexact_alm_rpca_batch(xt[:2], max_rank=2)

@@ -155,3 +155,26 @@ def test_motion_saliency_golden_highway(highway_fixture):
         for b, g in enumerate(gb[f]):
             assert np.array_equal(g, labels[f] == b + 1)
             assert abs(wb[f][b] - lam[ptr[f] + b]) <= 1e-12 * lam[ptr[f] + b]
+
+
+def saliency_slices(seed=3, h=48, w=64, t=40):
+    """[t, h, w] float64 video (0..255, like import_video_as_frames) from the seeded synthetic generator."""
+    from background_subtraction_b200 import synth
+    video, _ = synth.make_clip(h, w, t, seed=seed, n_rect=2)
+    return video.reshape(t, w, h).transpose(0, 2, 1).astype(np.float64)
+
+
+def test_rank_capped_rpca_restatement():
+    """The batch engine's oracle: without the cap it IS inexact_alm_rpca (oracle port, and the reference when present)."""
+    from oracle import alm_oracle as O
+    xt = saliency_slices().transpose(2, 1, 0)
+    D = np.asfortranarray(xt[5] - xt[5].mean())
+    L, S, it, conv = F.inexact_alm_rpca_capped(D, 1.0)
+    Lo, So, ito, convo = O.inexact_alm_rpca(D, 1.0)
+    assert (it, conv) == (ito, convo) and np.array_equal(L, Lo) and np.array_equal(S, So)
+    if R.available():
+        with R.quiet():
+            Lr, Sr, itr, convr = R.load()["lsd_improvement"].inexact_alm_rpca(D, 1.0)
+        assert (it, conv) == (itr, convr) and np.allclose(L, Lr, atol=1e-12) and np.allclose(S, Sr, atol=1e-12)
+    L1, S1, it1, conv1 = F.inexact_alm_rpca_capped(xt[5], 1.0, max_rank=1, tol_l1=xt.shape[1] * xt.shape[2] * 1e-4)
+    assert conv1 and np.linalg.matrix_rank(L1) == 1 and np.sum(np.abs(xt[5] - L1 - S1)) <= xt.shape[1] * xt.shape[2] * 1e-4
