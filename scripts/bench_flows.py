@@ -48,6 +48,7 @@ def highway_flow(args, rank, world, sampler_cls):
     groups = B.get_proximal_flat_groups_nonoverlap((h, w), (3, 3))
     Dh = torch.from_numpy(np.ascontiguousarray(D.T, dtype=np.float32)).pin_memory().numpy()     # [t][m] float32, pinned
     sal_dev = torch.from_numpy(np.ascontiguousarray(sal, dtype=np.float32)).cuda()
+    video_thw = torch.from_numpy(np.ascontiguousarray(frames.transpose(2, 0, 1), dtype=np.float32)).cuda()   # raw 0..255, [t, h, w]
     stream = torch.cuda.current_stream()
     stages = {}
 
@@ -72,6 +73,12 @@ def highway_flow(args, rank, world, sampler_cls):
             return torch.from_numpy(d1.mask(2).T.copy()).cuda()            # [t][m] bool -> device
         mask1 = tm("stage1_lsd_flat", s1)
         mask1_hwt = mask1.view(t, w, h).permute(2, 1, 0)
+        # stage 2: saliency RPCA of every X-T / Y-T slice + computeSCube (timed; the parity fields below use the stand-in cube the
+        # golden labels were generated with, the cube of this stage is scored separately as F*_rpca_saliency)
+        def s2():
+            xl, xs, yl, ys = B.executeSaliencyRPCA(video_thw, 1)
+            return B.computeSCube(xs, ys, return_device=True).permute(1, 2, 0).contiguous()      # [h, w, t] like precomputed_main.py:42
+        cube2 = tm("stage2_saliency_rpca_scube", s2)
         # stage 3a: groups and lambdas from the mask and the saliency cube
         labels, ptr, lam = tm("motion_saliency", lambda: B.motion_saliency_blocks((h, w, t), mask1_hwt, sal_dev))
         # stage 3b: group-sparse RPCA, masks, size filter
@@ -88,7 +95,7 @@ def highway_flow(args, rank, world, sampler_cls):
         dec, st, mk = tm("group_sparse", s3)
         filt = tm("filter_sparse_map", lambda: [B.filter_sparse_map(v) for v in mk])
         torch.cuda.synchronize()
-        return d1, labels, ptr, lam, dec, st, mk, filt
+        return d1, labels, ptr, lam, dec, st, mk, filt, mask1_hwt, cube2
 
     for _ in range(max(args.warmup, 1)):
         flow(False)
@@ -98,7 +105,7 @@ def highway_flow(args, rank, world, sampler_cls):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        d1, labels, ptr, lam, dec, st, mk, filt = flow(True)
+        d1, labels, ptr, lam, dec, st, mk, filt, mask1_hwt, cube2 = flow(True)
     e1.record(stream)
     torch.cuda.synchronize()
     clocks = sampler.stop()
@@ -120,9 +127,22 @@ def highway_flow(args, rank, world, sampler_cls):
         parity["F%d_gpu" % k] = SC.mean_fscore(g, gt)
         parity["F%d_reference" % k] = SC.mean_fscore(golden[k], gt)
         parity["F%d_filtered_gpu" % k] = SC.mean_fscore(filt[i].cpu().numpy(), gt)
+    # the same flow once more (untimed) with the saliency cube of stage 2 instead of the stand-in
+    try:
+        lab2, ptr2, lam2 = B.motion_saliency_blocks((h, w, t), mask1_hwt, cube2)
+        dec2 = B.Decomposition(B.make_config(m, t, C.PROX_BLOCK_L2, h, w, delta=10, mu_scale=1.25, break_on_rank0=True, use_sv_prediction=True))
+        dec2.set_blocks(lab2.cpu().numpy(), ptr2, lam2)
+        dec2.load(Dh)
+        dec2.run()
+        st2 = dec2.status()
+        parity["rpca_saliency"] = {"blocks": int(ptr2[-1]), "iters": int(st2.iter), "converged": bool(st2.converged),
+                                   "F2": SC.mean_fscore(dec2.mask(2).reshape((h, w, t), order='F'), gt),
+                                   "F3": SC.mean_fscore(dec2.mask(3).reshape((h, w, t), order='F'), gt)}
+    except Exception as ex:                                                 # e.g. no group survives the weight filter
+        parity["rpca_saliency"] = {"error": str(ex)}
     stage_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in stages.items()}
     cfg = {"workload": "highway_flow", "rows": h, "cols": w, "frames": t,
-           "flow": "flat LSD -> mask -> run_motion_saliency_check -> group-sparse RPCA -> masks k=2,3 -> filter_sparse_map",
+           "flow": "flat LSD -> mask -> saliency RPCA batch + computeSCube -> run_motion_saliency_check -> group-sparse RPCA -> masks k=2,3 -> filter_sparse_map",
            "fixture": "half-resolution input/ frames 1-289 (tests/golden/highway_half_u8.npz); stage-2 saliency = |x - median| stand-in",
            "timing": "CUDA events on the launching stream around the whole flow (host glue included); pinned float32 D in, masks out"}
     return _line(args, world, t / (ms * 1e-3), ms, cfg,
