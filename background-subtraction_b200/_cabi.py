@@ -92,6 +92,7 @@ SIGNATURES = {
     "bsub_gram_dev": (ctypes.c_int, [vp, vp, vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, c_double_p, vp]),
     "bsub_eig_topk": (ctypes.c_int, [c_double_p, ctypes.c_int32, ctypes.c_int32, c_double_p, c_double_p]),
     "bsub_gram_i8_test": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int64, vp]),
+    "bsub_gram_i8_bench": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, vp]),
     "bsub_resize_dev": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                        vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp]),
     "bsub_cc_label_dev": (ctypes.c_int, [vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, ctypes.c_int64, vp, vp, vp]),

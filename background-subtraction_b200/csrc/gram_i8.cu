@@ -77,6 +77,27 @@ __device__ __forceinline__ void gi_mma(uint32_t tmem_c, uint64_t da, uint64_t db
 __device__ __forceinline__ void gi_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// The MMA warp runs its loop with ALL 32 lanes on warp-uniform values and lets one elected lane issue (the `_w` forms below).
+// With a single-thread `if (lane == 0)` region the compiler cannot prove the descriptors uniform and wraps every
+// tcgen05.mma in ELECT + 4 R2UR.BROADCAST + a BRA.U.ANY waterfall: ~92 cycles of issue per MMA against 64 cycles of execution
+// (measured with clock64 in round 2: the issuing thread, not the tensor pipe or the operand feed, set the 1.5 ms of this kernel).
+__device__ __forceinline__ void gi_mma_w(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void gi_commit_w(uint64_t* bar) {
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+// whole-warp wait: every lane polls (all see the phase flip), then the warp reconverges
+__device__ __forceinline__ void gi_mbar_wait_w(uint64_t* bar, uint32_t parity) {
+    gi_mbar_wait(bar, parity);
+    __syncwarp();
+}
 __device__ __forceinline__ void gi_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -95,7 +116,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     uint64_t* tmem_empty = tmem_full + 1;                                        // accumulators drained
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tmem_empty + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;     // provably warp-uniform
     const int4 info = a.cta_info[blockIdx.x];
     const int bi = info.x, bj = info.y, kb0 = info.z, kstride = info.w;
     const bool diag = (bi == bj);
@@ -118,7 +139,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_base_s;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_s, 0);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -141,8 +162,8 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp, one elected lane issues: see gi_mma_w) =====================
+        {
             const uint32_t idesc = gi_instr_desc(Nj);
             const uint32_t lboB = (diag || Nj == 128) ? 2048u : (uint32_t)(Nj * 16);
             const uint64_t descA0 = gi_smem_desc(0u, 2048u), descB0 = gi_smem_desc(0u, lboB);
@@ -151,14 +172,13 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                 const int s = kb % GI_STAGES;
                 const int u = kb / GI_STAGES;
                 if (since_flush == 0 && nflush > 0) {
-                    gi_mbar_wait(tmem_empty, (uint32_t)((nflush - 1) & 1));          // epilogue has drained TMEM
+                    gi_mbar_wait_w(tmem_empty, (uint32_t)((nflush - 1) & 1));        // epilogue has drained TMEM
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                gi_mbar_wait(&full[s], (uint32_t)(u & 1));
+                gi_mbar_wait_w(&full[s], (uint32_t)(u & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sbase = smem_u32(stages + (size_t)s * GI_STAGE_BYTES);
-                // descriptors = per-kernel constant part + (address >> 4): one 64-bit add per operand keeps the single issuing
-                // thread ahead of the tensor pipe (a 128x128x32 MMA lasts ~68 cycles)
+                // descriptors = per-kernel constant part + (address >> 4): one 64-bit add per operand
                 const uint64_t sa = descA0 + (uint64_t)((sbase >> 4) & 0x3FFF);
                 const uint64_t sb = descB0 + (uint64_t)(((sbase + (diag ? 0u : (uint32_t)(4 * GI_TILE_BYTES))) >> 4) & 0x3FFF);
 #pragma unroll
@@ -173,13 +193,13 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                             const uint64_t db = sb + (uint64_t)((j * GI_TILE_BYTES) >> 4) + (uint64_t)ks * (uint64_t)((2 * lboB) >> 4);
                             // first pair of a class right after a flush overwrites the accumulator
                             const bool first = (since_flush == 0 && ks == 0 && j == 3);   // (i, 3) is the first pair of class i
-                            gi_mma(tmem_base + (uint32_t)(cls * 128), da, db, idesc, first ? 0u : 1u);
+                            gi_mma_w(tmem_base + (uint32_t)(cls * 128), da, db, idesc, first ? 0u : 1u);
                         }
                 }
-                gi_commit(&empty[s]);                                            // smem stage reusable when these MMAs finish
+                gi_commit_w(&empty[s]);                                          // smem stage reusable when these MMAs finish
                 ++since_flush;
                 if (since_flush == GI_FLUSH_KB || kb == nkb - 1) {
-                    gi_commit(tmem_full);                                        // accumulators complete -> epilogue
+                    gi_commit_w(tmem_full);                                      // accumulators complete -> epilogue
                     since_flush = 0; ++nflush;
                 }
             }
@@ -247,8 +267,9 @@ __device__ __forceinline__ void gi_tma_load_3d_mc(void* smem_dst, const CUtensor
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask) : "memory");
 }
-__device__ __forceinline__ void gi_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+__device__ __forceinline__ void gi_commit_mc_w(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
                  ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
@@ -265,7 +286,7 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
     uint64_t* tmem_empty = tmem_full + 1;
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tmem_empty + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;     // provably warp-uniform
     const int rank = (int)cluster.block_rank();
     const int cid = blockIdx.x / 3;
     const bool tX = cid < a.nX;
@@ -299,7 +320,7 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster.sync();                                        // barriers of all three CTAs exist before anything is signalled
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_base_s;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_s, 0);
 
     if (warp == 0) {
         // ===================== TMA producer: arms my full barrier, loads the slot I own =====================
@@ -321,8 +342,8 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp, one elected lane issues: see gi_mma_w) =====================
+        {
             const uint32_t idesc = gi_instr_desc(Nj);
             const uint32_t offA = useA ? 0u : (uint32_t)(4 * GI_TILE_BYTES);             // (2,2) takes both operands from slot B
             const uint32_t offB = diag ? offA : (uint32_t)(4 * GI_TILE_BYTES);
@@ -332,10 +353,10 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
                 const int s = kb % GI_STAGES;
                 const int u = kb / GI_STAGES;
                 if (since_flush == 0 && nflush > 0) {
-                    gi_mbar_wait(tmem_empty, (uint32_t)((nflush - 1) & 1));
+                    gi_mbar_wait_w(tmem_empty, (uint32_t)((nflush - 1) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                gi_mbar_wait(&full[s], (uint32_t)(u & 1));
+                gi_mbar_wait_w(&full[s], (uint32_t)(u & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sbase = smem_u32(stages + (size_t)s * GI_STAGE_BYTES);
                 // (in a cluster launch the shared-window address carries CTA-rank bits above the 14-bit descriptor field: mask)
@@ -351,14 +372,14 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
                             const uint64_t da = sa + (uint64_t)((i * GI_TILE_BYTES + ks * 4096) >> 4);
                             const uint64_t db = sb + (uint64_t)((j * GI_TILE_BYTES + ks * 4096) >> 4);
                             const bool first = (since_flush == 0 && ks == 0 && j == 3);
-                            gi_mma(tmem_base + (uint32_t)(cls * 128), da, db, idesc, first ? 0u : 1u);
+                            gi_mma_w(tmem_base + (uint32_t)(cls * 128), da, db, idesc, first ? 0u : 1u);
                         }
                 }
-                gi_commit_mc(&empty[s], sup_mask);                                 // hand the operand slots back to their loaders
-                gi_commit(&mine[s]);
+                gi_commit_mc_w(&empty[s], sup_mask);                               // hand the operand slots back to their loaders
+                gi_commit_w(&mine[s]);
                 ++since_flush;
                 if (since_flush == GI_FLUSH_KB || kb == nkb - 1) {
-                    gi_commit(tmem_full);
+                    gi_commit_w(tmem_full);
                     since_flush = 0; ++nflush;
                 }
             }

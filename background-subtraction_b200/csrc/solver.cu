@@ -1042,6 +1042,44 @@ int bsub_gram_i8_test(const int8_t* slices_host, int32_t n, int64_t ldq, int64_t
     return 0;
 }
 
+int bsub_gram_i8_bench(int32_t n, int64_t ldq, int32_t reps, float* ms_out) {
+    // profiling hook: average time of `reps` launches of the int8 Gram on device-resident digit planes of arbitrary content
+    if (!ms_out || n <= 0 || ldq <= 0 || (ldq % 64) != 0 || reps <= 0) { set_error("bsub_gram_i8_bench: bad argument"); return -1; }
+    int dev = 0, sms = 148;
+    CK(cudaGetDevice(&dev));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    GramI8Plan gp = make_gram_i8_plan(n, ldq, sms);
+    std::vector<int4> info; std::vector<int> blkn;
+    fill_gram_i8_tables(gp, info, blkn);
+    DevScope mem;
+    signed char* q = nullptr; int4* info_d = nullptr; int* blkn_d = nullptr; unsigned long long* Gint = nullptr; double* G = nullptr;
+    const size_t qbytes = (size_t)4 * n * ldq, gn = (size_t)gp.nblk * 128;
+    const int npad = ((n + 31) / 32) * 32;
+    RET_IF(mem.alloc(&q, qbytes));
+    RET_IF(mem.alloc(&info_d, sizeof(int4) * info.size()));
+    RET_IF(mem.alloc(&blkn_d, sizeof(int) * blkn.size()));
+    RET_IF(mem.alloc(&Gint, sizeof(unsigned long long) * gn * gn));
+    RET_IF(mem.alloc(&G, sizeof(double) * ((size_t)npad * npad + 16)));
+    CK(cudaMemset(q, 0x35, qbytes));
+    CK(cudaMemcpy(info_d, info.data(), sizeof(int4) * info.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(blkn_d, blkn.data(), sizeof(int) * blkn.size(), cudaMemcpyHostToDevice));
+    CUtensorMap map, map_last;
+    RET_IF(make_gram_i8_map(gp, q, &map, 128));
+    RET_IF(make_gram_i8_map(gp, q, &map_last, gram_i8_last_block_n(gp)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int r = 0; r < 2; ++r) RET_IF(launch_gram_i8(gp, map, map_last, info_d, (int)info.size(), blkn_d, Gint, G, npad, nullptr, 1.0, 1, 0));
+    CK(cudaEventRecord(e0, 0));
+    for (int r = 0; r < reps; ++r) RET_IF(launch_gram_i8(gp, map, map_last, info_d, (int)info.size(), blkn_d, Gint, G, npad, nullptr, 1.0, 1, 0));
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_out = ms / (float)reps;
+    return 0;
+}
+
 int bsub_eig_topk(const double* G_host, int32_t n, int32_t k, double* lam_host, double* vec_host) {
     if (!G_host || n <= 0 || k <= 0 || k > n || !lam_host) { set_error("bsub_eig_topk: bad argument"); return -1; }
     const int npad = ((n + 31) / 32) * 32;

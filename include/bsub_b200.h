@@ -190,6 +190,8 @@ int bsub_gram_dev(const float* D, const float* S, const float* Y, int64_t ld, in
 int bsub_eig_topk(const double* G_host, int32_t n, int32_t k, double* lam_host, double* vec_host);
 /* the tcgen05 int8 Gram on its own: slices int8[4][n][ldq] (host), G int64[n][n] = sum_p sum_{i+j>=3} 256^(i+j-3) d_i(f,p) d_j(g,p) */
 int bsub_gram_i8_test(const int8_t* slices_host, int32_t n, int64_t ldq, int64_t* G_host);
+/* profiling hook: mean milliseconds of `reps` launches of that Gram on device-resident planes [4][ldq/16][n][16] */
+int bsub_gram_i8_bench(int32_t n, int64_t ldq, int32_t reps, float* ms_out);
 
 /* ---- stages on either side of the decomposition; device pointers, csrc/post.cu ---- */
 /* resize_with_cv2 / resize_with_cv2_by_first_axis (utils.py:119-136): cv2.resize of n images, interp 0 = INTER_AREA (shrinking),
