@@ -179,7 +179,10 @@ int launch_block_l2_apply(const float* U, float* V, const unsigned char* labels,
                           double mu_override, double non_block_lambda, cudaStream_t s, int keep_other = 0);
 int launch_prox_l1(const float* U, float* V, long long ld, long long m, int n, float lam, cudaStream_t s);
 struct GraphProxPlan { int rows, cols, n; long long ld; size_t xi_floats; int max_sweeps; float tol; };
-int launch_prox_graph3(const float* U, float* V, float* xi, float* tot, const float* eta, long long ld, int rows,
+// workspace: xi = duals of whole frames (capped: the kernel walks the frames in chunks that fit), tot = per-pixel dual sums of
+// the frames held (ld floats each); BSUB_GRAPH_GLOBAL selects the HBM-resident sweep kernel (all frames at once)
+void prox_graph3_workspace(int rows, int cols, int n, long long ld, int center, long long* xi_floats, long long* tot_floats);
+int launch_prox_graph3(const float* U, float* V, float* xi, long long xi_floats, float* tot, const float* eta, long long ld, int rows,
                        int cols, int n, float lam, int max_sweeps, float tol, int* sweeps_out, const DevState* st,
                        cudaStream_t s, int center = 0, long long eta_stride = 0);
 

@@ -64,7 +64,7 @@ struct bsub_solver {
     // generic flat groups
     int* gptr = nullptr; int* gidx = nullptr; int ngroups = 0; bool groups_set = false;
     // overlapping graph
-    float* eta_dev = nullptr; float* xi = nullptr; float* tot = nullptr; int* sweeps_dev = nullptr; bool graph_set = false;
+    float* eta_dev = nullptr; float* xi = nullptr; long long xi_floats = 0; float* tot = nullptr; int* sweeps_dev = nullptr; bool graph_set = false;
     // l2 blocks
     unsigned char* labels_dev = nullptr; double* lam_table = nullptr; double* bsums = nullptr; int nlab = 0; bool blocks_set = false;
     unsigned char* mask_stage = nullptr;      // bsub_mask_host staging
@@ -331,8 +331,13 @@ int bsub_set_graph_windows(bsub_solver* s, const double* eta, int64_t n_eta) {
         if (!s->eta_dev) CK(cudaMalloc((void**)&s->eta_dev, sizeof(float) * nw));
         CK(cudaMemcpy(s->eta_dev, ef.data(), sizeof(float) * nw, cudaMemcpyHostToDevice));
     }
-    if (!s->xi) CK(cudaMalloc((void**)&s->xi, sizeof(float) * (size_t)s->n * nw * 9));
-    if (!s->tot) CK(cudaMalloc((void**)&s->tot, sizeof(float) * (size_t)s->n * s->ld));
+    // duals of the overlapping windows: whole frames up to a cap (the prox kernel walks the frames in chunks that fit)
+    if (!s->xi) {
+        long long tot_floats = 0;
+        prox_graph3_workspace(rows, cols, s->n, s->ld, 0, &s->xi_floats, &tot_floats);
+        CK(cudaMalloc((void**)&s->xi, sizeof(float) * (size_t)s->xi_floats));
+        CK(cudaMalloc((void**)&s->tot, sizeof(float) * (size_t)tot_floats));
+    }
     if (!s->sweeps_dev) CK(cudaMalloc((void**)&s->sweeps_dev, sizeof(int) * 4));
     s->graph_set = true;
     return 0;
@@ -352,8 +357,13 @@ int bsub_set_center_windows(bsub_solver* s, const float* eta, const uint8_t* bac
     CK(cudaMemcpy(s->eta_dev, eta, sizeof(float) * nm, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s->labels_dev, lab.data(), nm, cudaMemcpyHostToDevice));
     s->nlab = 1;
-    if (!s->xi) CK(cudaMalloc((void**)&s->xi, sizeof(float) * nm * 9));          // one candidate window per pixel and frame
-    if (!s->tot) CK(cudaMalloc((void**)&s->tot, sizeof(float) * (size_t)s->n * s->ld));
+    // one candidate window per pixel and frame
+    if (!s->xi) {
+        long long tot_floats = 0;
+        prox_graph3_workspace(s->cfg.rows, s->cfg.cols, s->n, s->ld, 1, &s->xi_floats, &tot_floats);
+        CK(cudaMalloc((void**)&s->xi, sizeof(float) * (size_t)s->xi_floats));
+        CK(cudaMalloc((void**)&s->tot, sizeof(float) * (size_t)tot_floats));
+    }
     if (!s->sweeps_dev) CK(cudaMalloc((void**)&s->sweeps_dev, sizeof(int) * 4));
     s->graph_set = true;
     return 0;
@@ -614,11 +624,11 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
         if (s->cfg.prox == BSUB_PROX_FLAT_LINF) {
             RET_IF(launch_prox_groups_csr(s->U, s->S, s->ld, s->m, s->n, s->gptr, s->gidx, s->ngroups, 0.f, s->st, st));
         } else if (s->cfg.prox == BSUB_PROX_GRAPH_LINF) {
-            RET_IF(launch_prox_graph3(s->U, s->S, s->xi, s->tot, s->eta_dev, s->ld, s->cfg.rows, s->cfg.cols, s->n, 0.f,
+            RET_IF(launch_prox_graph3(s->U, s->S, s->xi, s->xi_floats, s->tot, s->eta_dev, s->ld, s->cfg.rows, s->cfg.cols, s->n, 0.f,
                                       s->cfg.graph_max_sweeps, (float)s->cfg.graph_tol, s->sweeps_dev, s->st, st));
         } else if (s->cfg.prox == BSUB_PROX_GRAPH_CENTER_BG) {
             // S = prox_by_frame(G_S) then the background pixels of every frame are overwritten by their l2 shrink of G_S
-            RET_IF(launch_prox_graph3(s->U, s->S, s->xi, s->tot, s->eta_dev, s->ld, s->cfg.rows, s->cfg.cols, s->n, 0.f,
+            RET_IF(launch_prox_graph3(s->U, s->S, s->xi, s->xi_floats, s->tot, s->eta_dev, s->ld, s->cfg.rows, s->cfg.cols, s->n, 0.f,
                                       s->cfg.graph_max_sweeps, (float)s->cfg.graph_tol, s->sweeps_dev, s->st, st, 1, s->m));
             RET_IF(launch_block_l2_sums(s->U, s->labels_dev, s->ld, s->m, s->n, 1, s->bsums, s->st, st));
             RET_IF(launch_block_l2_apply(s->U, s->S, s->labels_dev, s->ld, s->m, s->n, 1, s->bsums, nullptr, s->st, 0.0, 0.0, st, 1));
@@ -911,8 +921,10 @@ int bsub_prox_graph3_dev(const float* U, float* V, int64_t ld, int32_t rows, int
     const long long nwi = rows - std::min(3, rows) + 1, nwj = cols - std::min(3, cols) + 1, nw = nwi * nwj;
     DevScope mem;
     float *xi = nullptr, *tot = nullptr, *eta = nullptr; int* sw = nullptr;
-    RET_IF(mem.alloc(&xi, sizeof(float) * (size_t)n * nw * 9));
-    RET_IF(mem.alloc(&tot, sizeof(float) * (size_t)n * ld));
+    long long xi_floats = 0, tot_floats = 0;
+    prox_graph3_workspace(rows, cols, n, ld, 0, &xi_floats, &tot_floats);
+    RET_IF(mem.alloc(&xi, sizeof(float) * (size_t)xi_floats));
+    RET_IF(mem.alloc(&tot, sizeof(float) * (size_t)tot_floats));
     RET_IF(mem.alloc(&sw, sizeof(int) * 4));
     if (eta_host) {
         std::vector<float> ef((size_t)nw);
@@ -920,7 +932,7 @@ int bsub_prox_graph3_dev(const float* U, float* V, int64_t ld, int32_t rows, int
         RET_IF(mem.alloc(&eta, sizeof(float) * nw));
         CK(cudaMemcpy(eta, ef.data(), sizeof(float) * nw, cudaMemcpyHostToDevice));
     }
-    RET_IF(launch_prox_graph3(U, V, xi, tot, eta, ld, rows, cols, n, (float)lambda1, max_sweeps > 0 ? max_sweeps : 4000, (float)tol, sw,
+    RET_IF(launch_prox_graph3(U, V, xi, xi_floats, tot, eta, ld, rows, cols, n, (float)lambda1, max_sweeps > 0 ? max_sweeps : 4000, (float)tol, sw,
                               nullptr, st));
     int sw_h = 0;
     CK(cudaMemcpyAsync(&sw_h, sw, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -936,12 +948,14 @@ int bsub_prox_center3_dev(const float* U, float* V, int64_t ld, int32_t rows, in
     const long long m = (long long)rows * cols;
     DevScope mem;
     float *xi = nullptr, *tot = nullptr, *eta = nullptr; int* sw = nullptr;
-    RET_IF(mem.alloc(&xi, sizeof(float) * (size_t)n * m * 9));          // one candidate window per pixel and frame
-    RET_IF(mem.alloc(&tot, sizeof(float) * (size_t)n * ld));
+    long long xi_floats = 0, tot_floats = 0;                                      // one candidate window per pixel and frame
+    prox_graph3_workspace(rows, cols, n, ld, 1, &xi_floats, &tot_floats);
+    RET_IF(mem.alloc(&xi, sizeof(float) * (size_t)xi_floats));
+    RET_IF(mem.alloc(&tot, sizeof(float) * (size_t)tot_floats));
     RET_IF(mem.alloc(&eta, sizeof(float) * (size_t)n * m));
     RET_IF(mem.alloc(&sw, sizeof(int) * 4));
     CK(cudaMemcpy(eta, eta_host, sizeof(float) * (size_t)n * m, cudaMemcpyHostToDevice));
-    RET_IF(launch_prox_graph3(U, V, xi, tot, eta, ld, rows, cols, n, (float)lambda1, max_sweeps > 0 ? max_sweeps : 4000, (float)tol, sw,
+    RET_IF(launch_prox_graph3(U, V, xi, xi_floats, tot, eta, ld, rows, cols, n, (float)lambda1, max_sweeps > 0 ? max_sweeps : 4000, (float)tol, sw,
                               nullptr, st, 1, m));
     int sw_h = 0;
     CK(cudaMemcpyAsync(&sw_h, sw, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -36,6 +36,10 @@ WORKLOADS = {
     # independent 320x240x200 clips spread over the GPUs
     "highway_flow": (120, 160, 289, None, None),
     "batch64_qvga_200": (240, 320, 200, 100, 3),
+    # the reference's default LSD() mode (overlapping 3x3 windows, spams.proximalGraph) on its own clip and at the headline size
+    "watersurface_graph": (128, 160, 48, None, None),
+    "synthetic_qvga_200_graph": (240, 320, 200, 100, 3),
+    "synthetic_1080p_300_graph": (1080, 1920, 300, 0, 6),
 }
 
 
@@ -161,7 +165,7 @@ def cpu_sample(video_u8, rows, cols, frames, div):
 def load_video(workload):
     """uint8 clip [frames][m], frame-major with the reference's pixel order p = j*rows + i."""
     rows, cols, frames, seed, nrect = WORKLOADS[workload]
-    if workload == "watersurface":
+    if workload.startswith("watersurface"):
         cube = np.load(os.path.join(ROOT, "tests", "golden", "watersurface_u8.npz"))["ImData"]       # [rows, cols, frames]
         return np.ascontiguousarray(cube.transpose(2, 1, 0)).reshape(frames, rows * cols)
     from background_subtraction_b200 import synth
@@ -219,11 +223,14 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if args.workload in ("highway_flow", "batch64_qvga_200"):
+    if args.workload in ("highway_flow", "batch64_qvga_200") or args.workload.endswith("_graph"):
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         import bench_flows
         if args.workload == "highway_flow":
             out = bench_flows.highway_flow(args, rank, world, ClockSampler)
+        elif args.workload.endswith("_graph"):
+            rows, cols, frames, seed, nrect = WORKLOADS[args.workload]
+            out = bench_flows.graph_lsd(args, rank, world, ClockSampler, rows, cols, frames, load_video(args.workload), args.workload)
         else:
             out = bench_flows.batch_clips(args, rank, world, local_rank, ClockSampler)
         if out is not None:

@@ -197,3 +197,26 @@ def test_gram_i8_exact(B, n, ldq):
             if i + j >= 3:
                 ref += (s64[i] @ s64[j].T) << (8 * (i + j - 3))
     assert np.array_equal(G, ref), (np.abs(G - ref).max(), np.argwhere(G != ref)[:5])
+
+
+@pytest.mark.parametrize("shape,xi_mb", [((70, 95, 5), None), ((70, 95, 5), "1"), ((33, 64, 3), None), ((131, 45, 2), None)])
+def test_prox_graph_tiled_multi_tile(B, shape, xi_mb, monkeypatch):
+    """The tile-local dual BCD (prox_graph3_tile_kernel): images of several 32-pixel tiles in both directions, so that windows
+    straddle tile borders in every one of the three shifted tilings; with BSUB_GRAPH_XI_MB=1 the frames are walked in chunks
+    whose duals fit a 1 MB buffer (2 chunks here).  Checked against the oracle's sequential sweeps at 1e-12."""
+    from oracle import alm_oracle as O
+    h, w, t = shape
+    if xi_mb is not None:
+        monkeypatch.setenv("BSUB_GRAPH_XI_MB", xi_mb)
+    rng = np.random.default_rng(h * w)
+    U = (rng.standard_normal((h * w, t)) * 0.05)
+    U[rng.random((h * w, t)) < 0.02] += 0.4                     # a few strong pixels, like foreground
+    U = np.asfortranarray(U.astype(np.float32).astype(np.float64))
+    graph = B.getGraphSPAMS_all_groups((h, w), (3, 3))
+    gc = O.graph_from_spams_dict(graph)
+    for lam in (0.003, 0.08):
+        ref = O.prox_graph(U, lam, gc, tol=1e-12)
+        out, sw = B.prox(U, lam, graph, return_sweeps=True, tol=1e-6)
+        err = np.abs(out - ref).max()
+        assert err <= 2e-5 * max(np.abs(U).max(), lam), (lam, err, sw)
+        assert 1 <= sw < 20000
