@@ -18,6 +18,7 @@
 //   warps 4-7  epilogue: tcgen05.ld of the four class accumulators, recombination into int64, atomicAdd to global
 #include <cooperative_groups.h>
 #include <stdio.h>
+#include <math.h>
 #include <algorithm>
 #include <vector>
 #include "common.cuh"
@@ -246,17 +247,23 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 
 // ---------------------------------------------------------------------------------------------------------------
 // Three frame blocks (256 < n <= 384, the 300-frame clips): clusters of 3 CTAs share operand tiles through TMA multicast.
-// gram_i8_kernel above is bound by L2 -> SM bytes: every 128-frame block is fetched by each of the block pairs that use
-// it (912 frame rows per 64-pixel step for n = 300).  Here a cluster owns a block ROW of the output triangle:
-//   type X  rank 0: (0,0)   rank 1: (0,1)   rank 2: (0,2)     block 0 -> slot A of all three (one multicast load)
-//   type Y  rank 0: (1,1)   rank 1: (1,2)   rank 2: (2,2)     block 1 -> slot A of ranks 0,1; block 2 -> slot B of ranks 1,2
-// => 300 + 172 = 472 rows per step.  Stage hand-back: the MMA thread commits (tcgen05.commit ... multicast::cluster) to
-// the `empty` barrier of every CTA that supplied one of its operands, and to its own `mine` barrier, which paces the
-// re-arming of its `full` barrier.  X and Y clusters cost the same per step and take alternating pixel blocks.
+// gram_i8_kernel above is bound by L2 -> SM bytes: every 128-frame block is fetched by each of the block pairs that use it.
+// Here the frames are cut into three blocks of nb = ceil(n / 3) frames (100 for n = 300: MMA N = 112 instead of 128; a box still
+// carries 128 frames, the rows / columns beyond a block's own frames are never read by the epilogue) and the six tiles of the
+// block triangle are dealt to two kinds of cluster:
+//   type X (off-diagonal)  rank 0: (0,1)   rank 1: (0,2)   rank 2: (1,2)      10 digit pairs per k-step
+//        block 0 -> slot A of ranks 0,1 (one multicast load by rank 0); block 2 -> slot B of ranks 1,2 (rank 1);
+//        block 1 -> slot A of rank 2 (rank 2) and slot B of rank 0 (rank 0: a block can only be multicast to ONE slot offset)
+//   type Y (diagonal)      rank r: (r,r), both operands from its own slot A     7 digit pairs per k-step
+//        P_ji = P_ij^T on a diagonal tile, so classes 0 and 2 accumulate only H = sum_{i<j} P_ij and the epilogue adds H to
+//        (r,c) AND (c,r); class 1 holds the symmetric pair P_22 and keeps all three of its products, class 3 is P_33 alone.
+// X clusters cost 20 MMAs per 64-pixel stage, Y clusters 14: the pixel stages are split nX : nY ~ 20 : 14 between them.
+// Stage hand-back: the MMA warp commits (tcgen05.commit ... multicast::cluster) to the `empty` barrier of every CTA that supplied
+// one of its operands, and to its own `mine` barrier, which paces the re-arming of its `full` barrier.
 struct GramI8C3Args {
     int n, nkb;                           // frames; 64-pixel stages in the slice matrix
     int nX, nY;                           // clusters of each type (cluster id < nX: type X)
-    int n2;                               // MMA N of frame block 2 (multiple of 16)
+    int nb, N;                            // frames per block, MMA N (nb rounded up to 16)
     unsigned long long* Gint;
     const DevState* st;
     int require_mode;
@@ -280,7 +287,7 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
     extern __shared__ __align__(1024) unsigned char gi_smem[];
     unsigned char* stages = gi_smem;                                             // [GI_STAGES][A: 4 planes | B: 4 planes][128][64]
     uint64_t* full = reinterpret_cast<uint64_t*>(gi_smem + (size_t)GI_STAGES * GI_STAGE_BYTES);   // [GI_STAGES]
-    uint64_t* empty = full + GI_STAGES;                                          // [GI_STAGES] consumers of the slot I load are done
+    uint64_t* empty = full + GI_STAGES;                                          // [GI_STAGES] consumers of the slots I load are done
     uint64_t* mine = empty + GI_STAGES;                                          // [GI_STAGES] my own MMAs on the stage are done
     uint64_t* tmem_full = mine + GI_STAGES;
     uint64_t* tmem_empty = tmem_full + 1;
@@ -293,21 +300,20 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
     const int kb0 = tX ? cid : cid - a.nX, kstride = tX ? a.nX : a.nY;
     const int nkb = (a.nkb > kb0) ? (a.nkb - kb0 + kstride - 1) / kstride : 0;
     // role table (see the header comment)
-    const int bi = tX ? 0 : (rank == 2 ? 2 : 1);
-    const int bj = tX ? rank : (rank == 0 ? 1 : 2);
-    const bool useA = tX || rank < 2, useB = tX ? (rank > 0) : (rank > 0);
-    const bool diag = (bi == bj);
-    const int Nj = (bj == 2) ? a.n2 : 128;
-    // what I load: slot (0 = A, 1 = B), frame block, destination CTAs
-    int ld_slot = -1, ld_blk = 0; uint16_t ld_mask = 0;
-    if (tX) { if (rank == 0) { ld_slot = 0; ld_blk = 0; ld_mask = 0x7; } else { ld_slot = 1; ld_blk = rank; ld_mask = (uint16_t)(1u << rank); } }
-    else { if (rank == 0) { ld_slot = 0; ld_blk = 1; ld_mask = 0x3; } else if (rank == 1) { ld_slot = 1; ld_blk = 2; ld_mask = 0x6; } }
-    // who supplies my operands
-    const uint16_t sup_mask = tX ? (uint16_t)(0x1 | (rank > 0 ? (1u << rank) : 0u)) : (uint16_t)(rank == 0 ? 0x1 : (rank == 1 ? 0x3 : 0x2));
-    const int n_consumers = __popc((unsigned)ld_mask);
+    const int bi = tX ? (rank == 2 ? 1 : 0) : rank;
+    const int bj = tX ? (rank == 0 ? 1 : 2) : rank;
+    const bool diag = !tX;
+    // what I load: up to two (slot, frame block, destination CTAs)
+    int ld0_slot, ld0_blk, ld1_slot = -1, ld1_blk = 0; uint16_t ld0_mask, ld1_mask = 0;
+    uint16_t sup_mask; int n_consumers;
+    if (tX) {
+        if (rank == 0)      { ld0_slot = 0; ld0_blk = 0; ld0_mask = 0x3; ld1_slot = 1; ld1_blk = 1; ld1_mask = 0x1; sup_mask = 0x1; n_consumers = 2; }
+        else if (rank == 1) { ld0_slot = 1; ld0_blk = 2; ld0_mask = 0x6; sup_mask = 0x3; n_consumers = 2; }
+        else                { ld0_slot = 0; ld0_blk = 1; ld0_mask = 0x4; sup_mask = 0x6; n_consumers = 1; }
+    } else { ld0_slot = 0; ld0_blk = rank; ld0_mask = (uint16_t)(1u << rank); sup_mask = ld0_mask; n_consumers = 1; }
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < GI_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], n_consumers > 0 ? n_consumers : 1); mbar_init(&mine[s], 1); }
+        for (int s = 0; s < GI_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], n_consumers); mbar_init(&mine[s], 1); }
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, 128);
         mbar_fence_init();
@@ -323,30 +329,30 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_base_s, 0);
 
     if (warp == 0) {
-        // ===================== TMA producer: arms my full barrier, loads the slot I own =====================
+        // ===================== TMA producer: arms my full barrier, loads the slots I own =====================
         if (lane == 0) {
-            const uint32_t tx = (uint32_t)((useA ? 4 : 0) + (useB ? 4 : 0)) * GI_TILE_BYTES;
+            const uint32_t tx = (uint32_t)(tX ? 8 : 4) * GI_TILE_BYTES;
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % GI_STAGES;
                 const int u = kb / GI_STAGES;
                 if (u > 0) gi_mbar_wait(&mine[s], (uint32_t)((u - 1) & 1));           // my MMAs of the previous round are done
                 mbar_expect_tx(&full[s], tx);
-                if (ld_slot >= 0) {
-                    if (u > 0) gi_mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));      // and so are those of everyone I feed
-                    unsigned char* base = stages + (size_t)s * GI_STAGE_BYTES + (size_t)ld_slot * 4 * GI_TILE_BYTES;
-                    const int k16 = (kb0 + kb * kstride) * (GI_KB / 16);
+                if (u > 0) gi_mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));          // and so are those of everyone I feed
+                unsigned char* base = stages + (size_t)s * GI_STAGE_BYTES;
+                const int k16 = (kb0 + kb * kstride) * (GI_KB / 16);
+                for (int sl = 0; sl < 4; ++sl)
+                    gi_tma_load_3d_mc(base + (size_t)(ld0_slot * 4 + sl) * GI_TILE_BYTES, &mapQ, &full[s], ld0_blk * 2 * a.nb, k16, sl, ld0_mask);
+                if (ld1_slot >= 0)
                     for (int sl = 0; sl < 4; ++sl)
-                        gi_tma_load_3d_mc(base + (size_t)sl * GI_TILE_BYTES, &mapQ, &full[s], ld_blk * 256, k16, sl, ld_mask);
-                }
+                        gi_tma_load_3d_mc(base + (size_t)(ld1_slot * 4 + sl) * GI_TILE_BYTES, &mapQ, &full[s], ld1_blk * 2 * a.nb, k16, sl, ld1_mask);
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp, one elected lane issues: see gi_mma_w) =====================
         {
-            const uint32_t idesc = gi_instr_desc(Nj);
-            const uint32_t offA = useA ? 0u : (uint32_t)(4 * GI_TILE_BYTES);             // (2,2) takes both operands from slot B
-            const uint32_t offB = diag ? offA : (uint32_t)(4 * GI_TILE_BYTES);
+            const uint32_t idesc = gi_instr_desc(a.N);
+            const uint32_t offB = diag ? 0u : (uint32_t)(4 * GI_TILE_BYTES);
             const uint64_t desc0 = gi_smem_desc(0u, 2048u);      // constant part of the operand descriptors (see gram_i8_kernel)
             int since_flush = 0, nflush = 0;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -360,20 +366,38 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t sbase = smem_u32(stages + (size_t)s * GI_STAGE_BYTES);
                 // (in a cluster launch the shared-window address carries CTA-rank bits above the 14-bit descriptor field: mask)
-                const uint64_t sa = desc0 + (uint64_t)(((sbase + offA) >> 4) & 0x3FFF), sb = desc0 + (uint64_t)(((sbase + offB) >> 4) & 0x3FFF);
+                const uint64_t sa = desc0 + (uint64_t)((sbase >> 4) & 0x3FFF), sb = desc0 + (uint64_t)(((sbase + offB) >> 4) & 0x3FFF);
+                if (!diag) {
 #pragma unroll
-                for (int ks = 0; ks < GI_KB / 32; ++ks) {
+                    for (int ks = 0; ks < GI_KB / 32; ++ks) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int cls = i + j - 3;
-                            if (cls < 0) continue;
-                            const uint64_t da = sa + (uint64_t)((i * GI_TILE_BYTES + ks * 4096) >> 4);
-                            const uint64_t db = sb + (uint64_t)((j * GI_TILE_BYTES + ks * 4096) >> 4);
-                            const bool first = (since_flush == 0 && ks == 0 && j == 3);
-                            gi_mma_w(tmem_base + (uint32_t)(cls * 128), da, db, idesc, first ? 0u : 1u);
-                        }
+                            for (int j = 0; j < 4; ++j) {
+                                const int cls = i + j - 3;
+                                if (cls < 0) continue;
+                                const uint64_t da = sa + (uint64_t)((i * GI_TILE_BYTES + ks * 4096) >> 4);
+                                const uint64_t db = sb + (uint64_t)((j * GI_TILE_BYTES + ks * 4096) >> 4);
+                                const bool first = (since_flush == 0 && ks == 0 && j == 3);
+                                gi_mma_w(tmem_base + (uint32_t)(cls * 128), da, db, idesc, first ? 0u : 1u);
+                            }
+                    }
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < GI_KB / 32; ++ks) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int cls = i + j - 3;
+                                if (cls < 0) continue;
+                                if (cls != 1 && i > j) continue;       // classes 0 and 2: the i < j half; the epilogue adds the transpose
+                                const uint64_t da = sa + (uint64_t)((i * GI_TILE_BYTES + ks * 4096) >> 4);
+                                const uint64_t db = sb + (uint64_t)((j * GI_TILE_BYTES + ks * 4096) >> 4);
+                                const bool first = (since_flush == 0 && ks == 0 && j == 3);
+                                gi_mma_w(tmem_base + (uint32_t)(cls * 128), da, db, idesc, first ? 0u : 1u);
+                            }
+                    }
                 }
                 gi_commit_mc_w(&empty[s], sup_mask);                               // hand the operand slots back to their loaders
                 gi_commit_w(&mine[s]);
@@ -386,15 +410,17 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ===================== epilogue (as in gram_i8_kernel) =====================
+        // ===================== epilogue =====================
         const int ew = warp - 4;
         const int nflush_total = (nkb + GI_FLUSH_KB - 1) / GI_FLUSH_KB;
-        const int row = bi * 128 + ew * 32 + lane;
+        const int lrow = ew * 32 + lane;
+        const int row = bi * a.nb + lrow;
+        const bool row_ok = lrow < a.nb && row < a.n;
         const size_t ldg = (size_t)3 * 128;
         for (int fl = 0; fl < nflush_total; ++fl) {
             gi_mbar_wait(tmem_full, (uint32_t)(fl & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int c0 = 0; c0 < Nj; c0 += 16) {
+            for (int c0 = 0; c0 < a.N; c0 += 16) {
                 uint32_t v3[16], v4[16], v5[16], v6[16];
                 const uint32_t ta = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0;
                 gi_tmem_ld16(ta + 0 * 128, v3);
@@ -402,14 +428,16 @@ gram_i8_c3_kernel(const __grid_constant__ CUtensorMap mapQ, GramI8C3Args a) {
                 gi_tmem_ld16(ta + 2 * 128, v5);
                 gi_tmem_ld16(ta + 3 * 128, v6);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < a.n) {
+                if (row_ok) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
-                        const int col = bj * 128 + c0 + e;
-                        if (col < a.n) {
-                            const long long val = (long long)(int)v3[e] + ((long long)(int)v4[e] << 8) + ((long long)(int)v5[e] << 16) +
-                                                  ((long long)(int)v6[e] << 24);
+                        const int lcol = c0 + e, col = bj * a.nb + lcol;
+                        if (lcol < a.nb && col < a.n) {
+                            const long long half = (long long)(int)v3[e] + ((long long)(int)v5[e] << 16);
+                            const long long whole = ((long long)(int)v4[e] << 8) + ((long long)(int)v6[e] << 24);
+                            const long long val = half + whole;
                             if (val != 0) atomicAdd(a.Gint + (size_t)row * ldg + col, (unsigned long long)val);
+                            if (diag && half != 0) atomicAdd(a.Gint + (size_t)col * ldg + row, (unsigned long long)half);
                         }
                     }
                 }
@@ -491,7 +519,7 @@ int launch_quantize_D(const float* D, long long ld, int n, long long ldq, signed
 }
 
 // G[i][j] (double, [npad][npad], symmetric) = Gint * scale   with  scale = S^2 * 2^-38
-__global__ void gram_i8_finish_kernel(const unsigned long long* __restrict__ Gint, int nblk, int n, int npad, double* __restrict__ G,
+__global__ void gram_i8_finish_kernel(const unsigned long long* __restrict__ Gint, int nblk, int blk, int n, int npad, double* __restrict__ G,
                                       const DevState* st, double scale_override, int require_mode, double diag_bias, double err_units,
                                       double* err_slot) {
     const bool runs = !(st != nullptr && (st->done || st->gram_mode != require_mode));
@@ -505,7 +533,7 @@ __global__ void gram_i8_finish_kernel(const unsigned long long* __restrict__ Gin
         const int i = idx / npad, j = idx - i * npad;
         double v = 0.0;
         if (i < n && j < n) {
-            const int r = (i / 128 <= j / 128) ? i : j, c = (i / 128 <= j / 128) ? j : i;     // upper block triangle holds the data
+            const int r = (i / blk <= j / blk) ? i : j, c = (i / blk <= j / blk) ? j : i;     // upper block triangle holds the data (blk frames per block)
             // diag_bias: expected value of the digit products the kernel drops (classes i + j <= 2), see launch_gram_i8
             v = ((double)(long long)Gint[(size_t)r * ldg + c] + ((i == j) ? diag_bias : 0.0)) * scale;
         }
@@ -573,6 +601,10 @@ int make_gram_i8_map(const GramI8Plan& p, const signed char* Wq, CUtensorMap* ma
     return make_tensor_map_u64(map, Wq, 3, dims, strides, box);
 }
 
+static int g_last_block_frames = 128;
+// frames per block of the upper block triangle the most recent launch left in Gint (test hook: bsub_gram_i8_test reads Gint itself)
+int gram_i8_last_block_frames() { return g_last_block_frames; }
+
 int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const CUtensorMap& map_last, const int4* cta_info_dev, int ncta, const int* blk_n_dev,
                    unsigned long long* Gint, double* G, int npad, const DevState* st, double scale_override, int require_mode,
                    cudaStream_t stream) {
@@ -624,11 +656,15 @@ int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const CUtensorMa
         }
         if (c3_clusters >= 2) {
             GramI8C3Args c;
-            c.n = p.n; c.nkb = p.nkb; c.nX = (c3_clusters + 1) / 2; c.nY = c3_clusters / 2; c.n2 = gram_i8_last_block_n(p);
+            c.n = p.n; c.nkb = p.nkb;
+            c.nb = (p.n + 2) / 3; c.N = ((c.nb + 15) / 16) * 16;
+            // pixel stages in proportion to the MMAs per stage: 20 on the off-diagonal clusters, 14 on the diagonal ones
+            c.nX = std::min(c3_clusters - 1, std::max(1, (int)lround(c3_clusters * 20.0 / 34.0))); c.nY = c3_clusters - c.nX;
             c.Gint = Gint; c.st = st; c.require_mode = require_mode;
+            g_last_block_frames = c.nb;
             cfg.gridDim = dim3(3 * c3_clusters);
             BSUB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_c3_kernel, map, c));
-            gram_i8_finish_kernel<<<64, 256, 0, stream>>>(Gint, p.nblk, p.n, npad, G, st, scale_override, require_mode, diag_bias, err_units,
+            gram_i8_finish_kernel<<<64, 256, 0, stream>>>(Gint, p.nblk, c.nb, p.n, npad, G, st, scale_override, require_mode, diag_bias, err_units,
                                                           (st != nullptr) ? G + (size_t)npad * npad + 8 : nullptr);
             BSUB_CUDA_CHECK(cudaGetLastError());
             return 0;
@@ -638,7 +674,8 @@ int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const CUtensorMa
     a.n = p.n; a.nblk = p.nblk; a.nkb = p.nkb; a.cta_info = cta_info_dev; a.blk_n = blk_n_dev; a.Gint = Gint; a.st = st; a.require_mode = require_mode;
     gram_i8_kernel<<<ncta, GI_THREADS, p.smem_bytes, stream>>>(map, map_last, a);
     BSUB_CUDA_CHECK(cudaGetLastError());
-    gram_i8_finish_kernel<<<64, 256, 0, stream>>>(Gint, p.nblk, p.n, npad, G, st, scale_override, require_mode, diag_bias, err_units,
+    g_last_block_frames = 128;
+    gram_i8_finish_kernel<<<64, 256, 0, stream>>>(Gint, p.nblk, 128, p.n, npad, G, st, scale_override, require_mode, diag_bias, err_units,
                                                           (st != nullptr) ? G + (size_t)npad * npad + 8 : nullptr);
     BSUB_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -31,6 +31,7 @@ GramI8Plan make_gram_i8_plan(int n, long long ldq, int num_sms);
 void fill_gram_i8_tables(const GramI8Plan& p, std::vector<int4>& cta_info, std::vector<int>& blk_n);
 int make_gram_i8_map(const GramI8Plan& p, const signed char* Wq, CUtensorMap* map, int box_frames);
 int gram_i8_last_block_n(const GramI8Plan& p);
+int gram_i8_last_block_frames();
 int launch_quantize_D(const float* D, long long ld, int n, long long ldq, signed char* Wq, const double* dmax, DevState* st,
                       cudaStream_t stream);
 int launch_gram_i8(const GramI8Plan& p, const CUtensorMap& map, const CUtensorMap& map_last, const int4* cta_info_dev, int ncta, const int* blk_n_dev,

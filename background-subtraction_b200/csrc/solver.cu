@@ -1050,7 +1050,8 @@ int bsub_gram_i8_test(const int8_t* slices_host, int32_t n, int64_t ldq, int64_t
     CK(cudaMemcpy(tmp.data(), Gint, sizeof(long long) * gn * gn, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) {
-            const int r = (i / 128 <= j / 128) ? i : j, c = (i / 128 <= j / 128) ? j : i;
+            const int blk = gram_i8_last_block_frames();
+            const int r = (i / blk <= j / blk) ? i : j, c = (i / blk <= j / blk) ? j : i;
             G_host[(size_t)i * n + j] = tmp[(size_t)r * gn + c];
         }
     return 0;
