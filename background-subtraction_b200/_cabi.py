@@ -64,6 +64,9 @@ SIGNATURES = {
     "bsub_step_project": (ctypes.c_int, [vp, vp]),
     "bsub_step_shrink": (ctypes.c_int, [vp, vp]),
     "bsub_step_finish_iter": (ctypes.c_int, [vp, vp]),
+    "bsub_step_shrink_a": (ctypes.c_int, [vp, vp]),
+    "bsub_step_shrink_b": (ctypes.c_int, [vp, vp]),
+    "bsub_block_sums_buffer": (ctypes.c_int, [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64)]),
     "bsub_poll": (ctypes.c_int, [vp, ctypes.POINTER(Status)]),
     "bsub_sync_status": (ctypes.c_int, [vp, ctypes.POINTER(Status), vp]),
     "bsub_finalize": (ctypes.c_int, [vp, vp]),

@@ -573,9 +573,23 @@ int bsub_step_project(bsub_solver* s, void* stream) {
     return 0;
 }
 
-int bsub_step_shrink(bsub_solver* s, void* stream) {
+// part: 0 = the whole pass; 1 / 2 = the two halves of the l2-block mode around the all-reduce of the per-(frame, group) sums of
+// squares (pixel-sharded drivers: a block -- and the frame-wide complement group -- spans the shards).  For every other mode part 1
+// is the whole pass and part 2 does nothing.
+static int step_shrink_impl(bsub_solver* s, void* stream, int part) {
     if (!s || !s->initialised) { set_error("bsub_step_shrink: solver not initialised"); return -1; }
     cudaStream_t st = use_stream(s, stream);
+    const bool split = (s->shrink_mode == SHRINK_SPILL && s->cfg.prox == BSUB_PROX_BLOCK_L2);
+    if (part == 2 && !split) return 0;
+    if (part == 2) {
+        RET_IF(launch_block_l2_apply(s->U, s->S, s->labels_dev, s->ld, s->m, s->n, s->nlab, s->bsums, s->lam_table, s->st, 0.0, 0.0, st));
+        const int np2 = s->num_sms * 8;
+        RET_IF(launch_dual_update(s->D, s->S, s->S, s->Y, s->T, s->eb.VC, s->eb.vstride, s->st, s->L, s->ld, s->n, s->part_zz,
+                                  s->part_nnz, s->part_max, np2, st));
+        RET_IF(launch_control_post(s->st, s->part_zz, s->part_nnz, s->part_max, np2, s->comm_sum + (size_t)s->npad * s->npad, s->log,
+                                   s->mirror_dev, 1 | 4, nullptr, 0, st));
+        return 0;
+    }
     ShrinkBuffers b;
     b.D = s->D; b.S = s->S; b.Y = s->Y; b.T = s->T; b.U = s->U; b.tpart = s->tpart; b.Vr = s->eb.Vr; b.VC = s->eb.VC;
     b.vstride = s->eb.vstride; b.part_zz = s->part_zz; b.part_nnz = s->part_nnz; b.part_max = s->part_max;
@@ -634,6 +648,7 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
             RET_IF(launch_block_l2_apply(s->U, s->S, s->labels_dev, s->ld, s->m, s->n, 1, s->bsums, nullptr, s->st, 0.0, 0.0, st, 1));
         } else {   // BSUB_PROX_BLOCK_L2
             RET_IF(launch_block_l2_sums(s->U, s->labels_dev, s->ld, s->m, s->n, s->nlab, s->bsums, s->st, st));
+            if (part == 1) return 0;                       // the driver all-reduces bsums, then calls part 2
             RET_IF(launch_block_l2_apply(s->U, s->S, s->labels_dev, s->ld, s->m, s->n, s->nlab, s->bsums, s->lam_table, s->st, 0.0,
                                          0.0, st));
         }
@@ -644,6 +659,18 @@ int bsub_step_shrink(bsub_solver* s, void* stream) {
     RET_IF(launch_control_post(s->st, s->part_zz, s->part_nnz, s->part_max, nparts, s->comm_sum + (size_t)s->npad * s->npad, s->log,
                                s->mirror_dev, 1 | 4, (s->use_i8 && s->use_stream) ? s->part_wmax : nullptr,
                                s->use_i8 ? s->ssp.grid + (flat ? s->sfp.grid : 0) : 0, st));
+    return 0;
+}
+
+int bsub_step_shrink(bsub_solver* s, void* stream) { return step_shrink_impl(s, stream, 0); }
+int bsub_step_shrink_a(bsub_solver* s, void* stream) { return step_shrink_impl(s, stream, 1); }
+int bsub_step_shrink_b(bsub_solver* s, void* stream) { return step_shrink_impl(s, stream, 2); }
+
+int bsub_block_sums_buffer(bsub_solver* s, double** sums, int64_t* count) {
+    if (!s) { set_error("bsub_block_sums_buffer: null solver"); return -1; }
+    const bool have = s->cfg.prox == BSUB_PROX_BLOCK_L2 && s->bsums != nullptr;
+    if (sums) *sums = have ? s->bsums : nullptr;
+    if (count) *count = have ? (int64_t)s->n * s->nlab : 0;
     return 0;
 }
 

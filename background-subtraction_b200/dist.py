@@ -2,7 +2,7 @@
 
 The path shards by image columns (pixel index p = j*rows + i, so a block of whole columns is a contiguous pixel
 range of every frame): rank r owns the column triples [t0, t1) so that no 3x3 tile straddles two ranks
-(SURVEY.md section 8e).  Per ALM iteration there is ONE exchange: an all-reduce(SUM) of a single buffer that holds the
+(SURVEY.md section 8e).  Per ALM iteration there is ONE exchange (two in the l2-block mode, see ShardedLSD): an all-reduce(SUM) of a single buffer that holds the
 frames x frames fp64 Gram partial of iteration k+1 followed by the 4 scalars of iteration k (sum Z^2, ||S||_0, ...).  The
 shrink pass of iteration k advances mu itself (local data only), the Gram of k+1 is enqueued right behind it, and the
 residual / stop test of iteration k is evaluated after the joint message has arrived; an iteration that turns out to be
@@ -57,20 +57,37 @@ class TorchComm:
 class CudaStepSolver:
     """Thin object view of the bsub_step_* C entry points for one shard."""
 
-    def __init__(self, rows, cols_local, n, m_global, delta=10, max_iter=500, tile_rows=0, cluster_frames=0, store_S_lazily=True):
+    def __init__(self, rows, cols_local, n, m_global, delta=10, max_iter=500, tile_rows=0, cluster_frames=0, store_S_lazily=True,
+                 blocks=None, use_sv_prediction=True):
+        """blocks = (labels uint8 [n][rows * cols_local] of THIS shard's pixels, lam_ptr int32 [n + 1], lam float64) selects the
+        group-sparse solver (inexact_alm_group_sparse_RPCA, /root/reference/group_sparse_RPCA.py:45-126: l2 blocks per frame,
+        mu0 = 1.25 / ||D||_2, stop on rank 0); lam_ptr / lam are the same on every rank.  Default: flat 3x3 l_inf groups (LSD)."""
         # store_S_lazily: let the single-pass shrink kernel skip the store of S in iterations that cannot be the last (it is
         # rebuilt from D, Y and the digit planes at the end).  A clipped digit pass in such an iteration stops EVERY rank with
         # done == 5 in the same iteration (the flag is part of the all-reduced scalars); ShardedLSD then repeats the solve
         # with S stored every time.
         self.m = rows * cols_local
-        cfg = api.make_config(self.m, n, C.PROX_FLAT_LINF, rows, cols_local, delta=delta, m_global=m_global,
-                              d_global=min(m_global, n), max_iter=max_iter, tile_rows=tile_rows,
-                              cluster_frames=cluster_frames, flags=0 if store_S_lazily else C.FLAG_ALWAYS_STORE_S)
-        self.lazy_S = bool(store_S_lazily)
-        self.dec = api.Decomposition(cfg)
-        self.dec.set_flat_groups(api.get_proximal_flat_groups_nonoverlap((rows, cols_local), api.BLOCK_SIZE))
+        if blocks is None:
+            cfg = api.make_config(self.m, n, C.PROX_FLAT_LINF, rows, cols_local, delta=delta, m_global=m_global,
+                                  d_global=min(m_global, n), max_iter=max_iter, tile_rows=tile_rows,
+                                  cluster_frames=cluster_frames, flags=0 if store_S_lazily else C.FLAG_ALWAYS_STORE_S)
+            self.lazy_S = bool(store_S_lazily)
+            self.dec = api.Decomposition(cfg)
+            self.dec.set_flat_groups(api.get_proximal_flat_groups_nonoverlap((rows, cols_local), api.BLOCK_SIZE))
+        else:
+            cfg = api.make_config(self.m, n, C.PROX_BLOCK_L2, rows, cols_local, delta=delta, mu_scale=1.25, break_on_rank0=True,
+                                  use_sv_prediction=use_sv_prediction, m_global=m_global, d_global=min(m_global, n), max_iter=max_iter)
+            self.lazy_S = False
+            self.dec = api.Decomposition(cfg)
+            self.dec.set_blocks(*blocks)
         self.lib, self.h = self.dec.lib, self.dec.h
         self.n = n
+        self.block_sums = None
+        if blocks is not None:
+            bp, bc = ctypes.c_void_p(), ctypes.c_int64(0)
+            C.check(self.lib.bsub_block_sums_buffer(self.h, ctypes.byref(bp), ctypes.byref(bc)))
+            import torch as _torch
+            self.block_sums = api._wrap_device(bp.value, (bc.value,), _torch.float64)
         sp, mp = ctypes.c_void_p(), ctypes.c_void_p()
         sc, mc = ctypes.c_int64(0), ctypes.c_int64(0)
         C.check(self.lib.bsub_comm_buffers(self.h, ctypes.byref(sp), ctypes.byref(sc), ctypes.byref(mp), ctypes.byref(mc)))
@@ -102,6 +119,16 @@ class CudaStepSolver:
 
     def shrink(self):
         C.check(self.lib.bsub_step_shrink(self.h, self._s()))
+
+    def shrink_a(self):
+        C.check(self.lib.bsub_step_shrink_a(self.h, self._s()))
+
+    def shrink_b(self):
+        C.check(self.lib.bsub_step_shrink_b(self.h, self._s()))
+
+    def block_sums_view(self):
+        """l2-block mode: per-(frame, group) sums of squares of this shard, to be all-reduced between shrink_a and shrink_b."""
+        return self.block_sums
 
     def finish_iter(self):
         C.check(self.lib.bsub_step_finish_iter(self.h, self._s()))
@@ -162,7 +189,8 @@ class CudaStepSolver:
 
 
 class ShardedLSD:
-    """inexact_alm_lsd (flat 3x3 groups) over `comm.world` shards.  hooks: optional callbacks
+    """inexact_alm_lsd (flat 3x3 groups) or inexact_alm_group_sparse_RPCA (l2 blocks, one more all-reduce per iteration: the
+    per-(frame, group) sums of squares) over `comm.world` shards -- the step solver decides which.  hooks: optional callbacks
     hooks[name](phase) with phase in {'begin', 'end'} around 'gram', 'solve', 'shrink' for timing."""
 
     def __init__(self, solver, comm, run_ahead=3, max_iter=500, fence=None):
@@ -198,7 +226,13 @@ class ShardedLSD:
             hk('solve', 'begin'); s.solve(); hk('solve', 'end')
             if hooks is not None and hasattr(s, 'project'):      # timed runs: the projection as a phase of its own
                 hk('project', 'begin'); s.project(); hk('project', 'end')
-            hk('shrink', 'begin'); s.shrink(); hk('shrink', 'end')
+            hk('shrink', 'begin')
+            bs = s.block_sums_view() if hasattr(s, 'block_sums_view') else None
+            if bs is None:
+                s.shrink()
+            else:                               # l2 blocks: the groups span the shards (group_sparse_RPCA.py:29-40)
+                s.shrink_a(); comm.all_reduce_sum(bs); s.shrink_b()
+            hk('shrink', 'end')
             if self.fence is not None:
                 fences.append(self.fence(it))
             self.iters_enqueued += 1

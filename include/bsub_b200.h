@@ -136,6 +136,13 @@ int bsub_step_solve(bsub_solver* s, void* stream);         /* eigensolve + rank 
 int bsub_step_project(bsub_solver* s, void* stream);       /* optional: T = Vr^T W from the digit planes (else part of _shrink) */
 int bsub_step_shrink(bsub_solver* s, void* stream);        /* fused pass B; leaves sum Z^2 etc. in the sum_buf tail  */
 int bsub_step_finish_iter(bsub_solver* s, void* stream);   /* err, mu update, stop flags                            */
+/* l2-block mode (group_sparse_RPCA.py:13-42) on pixel shards: a block -- and the frame-wide complement group, :37-40 -- spans the
+ * shards, so its shrink factor needs the sum of squares over ALL of them.  _shrink_a leaves the local sums in the buffer
+ * bsub_block_sums_buffer returns (double [n][labels], device memory), the driver all-reduces it (SUM), _shrink_b applies the
+ * factors and finishes the pass.  For the other prox modes _shrink_a is the whole pass, _shrink_b does nothing and the buffer is NULL. */
+int bsub_step_shrink_a(bsub_solver* s, void* stream);
+int bsub_step_shrink_b(bsub_solver* s, void* stream);
+int bsub_block_sums_buffer(bsub_solver* s, double** sums, int64_t* count);
 int bsub_poll(bsub_solver* s, bsub_status* st);            /* non-blocking: host mirror written by the device       */
 int bsub_sync_status(bsub_solver* s, bsub_status* st, void* stream);   /* blocking                                 */
 

@@ -8,7 +8,10 @@ from oracle import alm_oracle as O
 
 
 class NumpyStepSolver:
-    def __init__(self, D_local, rows, cols_local, n, m_global, delta=10, mu_scale=12.5, rho=1.6, tol=1e-7, max_iter=500):
+    def __init__(self, D_local, rows, cols_local, n, m_global, delta=10, mu_scale=12.5, rho=1.6, tol=1e-7, max_iter=500,
+                 labels=None, lambdas_by_frame=None):
+        """labels (int [n][m_local], 0 = complement) + lambdas_by_frame select the group-sparse solver
+        (/root/reference/group_sparse_RPCA.py:45-126: l2 blocks, mu0 = 1.25/||D||_2, break on rank 0)."""
         self.D = np.asfortranarray(D_local, dtype=np.float64)          # m_local x n
         self.rows, self.cols, self.n = rows, cols_local, n
         self.groups = O.flat_groups_nonoverlap((rows, cols_local), (3, 3))
@@ -19,6 +22,15 @@ class NumpyStepSolver:
         self.max_buf = torch.zeros(8, dtype=torch.float64)
         self.ngram = n * n
         self.log = []
+        self.labels, self.lams = labels, lambdas_by_frame
+        self.bsums = None
+        if labels is not None:
+            self.mu_scale = 1.25
+            self.nlab = 1 + max(len(l) for l in lambdas_by_frame)
+            self.bsums = torch.zeros(n * self.nlab, dtype=torch.float64)
+            self.nbl = 100.0 * self.lam
+
+    def block_sums_view(self): return self.bsums
 
     # -- views used by the driver's all-reduces
     def gram_view(self): return self.sum_buf[:self.ngram]
@@ -55,6 +67,9 @@ class NumpyStepSolver:
         s = np.sqrt(np.maximum(w[::-1][:self.sv], 0)); v = v[:, ::-1][:, :self.sv]
         self.iter += 1
         self.svp, self.sv = O.rank_logic(s, self.sv, self.mu, self.d)
+        if self.labels is not None and self.svp == 0:              # group_sparse_RPCA.py:91-93: stop before L / S are touched
+            self.done_flag = 3
+            return
         self.P = (v[:, :self.svp] * (1 - 1 / (self.mu * s[:self.svp]))) @ v[:, :self.svp].T
 
     def shrink(self):
@@ -67,6 +82,32 @@ class NumpyStepSolver:
         self.sum_buf[self.ngram:self.ngram + 4] = torch.tensor([float((Z * Z).sum()), float(np.count_nonzero(self.S)), 0.0, 0.0],
                                                               dtype=torch.float64)
         self.mu *= self.rho                      # like the device solver: mu advances with the shrink pass (local data only)
+
+    def shrink_a(self):
+        if self.done_flag: return
+        self.L = self.W @ self.P
+        self.G_S = self.D - self.L + self.Y / self.mu
+        sums = np.zeros((self.n, self.nlab))
+        for f in range(self.n):
+            np.add.at(sums[f], self.labels[f], self.G_S[:, f] ** 2)
+        self.bsums[:] = torch.from_numpy(sums.ravel())
+
+    def shrink_b(self):
+        if self.done_flag: return
+        sums = self.bsums.numpy().reshape(self.n, self.nlab)
+        S = np.zeros_like(self.G_S)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            for f in range(self.n):
+                eps = np.array([self.nbl] + list(self.lams[f]) + [0.0] * (self.nlab - 1 - len(self.lams[f]))) / self.mu
+                nrm = np.sqrt(sums[f])
+                fac = np.where(nrm > 0, np.maximum(1 - eps / nrm, 0), 0.0)
+                S[:, f] = fac[self.labels[f]] * self.G_S[:, f]
+        self.S = S
+        Z = self.D - self.L - self.S
+        self.Y = self.Y + self.mu * Z
+        self.sum_buf[self.ngram:self.ngram + 4] = torch.tensor([float((Z * Z).sum()), float(np.count_nonzero(self.S)), 0.0, 0.0],
+                                                              dtype=torch.float64)
+        self.mu *= self.rho
 
     def finish_iter(self):
         """Stop test of the iteration whose scalars arrived with the last all-reduce (the Gram of the NEXT iteration has

@@ -224,3 +224,37 @@ def test_generic_groups_first_multiplier(B, watersurface_u8):
     print("[generic Y1] relF(Y) %.3e  (dropping Y0 would give %.3e)" % (rel_fro(Y, Y1), rel_fro(Y1 - Y0, Y1)))
     assert rel_fro(Y, Y1) <= 1e-5
     assert rel_fro(dec.download('S'), Sr) <= 1e-5
+
+
+def test_group_sparse_through_sharded_driver(B, highway_fixture, summary):
+    """The l2-block mode through dist.ShardedLSD (world size 1: same kernels, the split shrink pass and the block-sum buffer that
+    the multi-GPU driver all-reduces): identical to the reference run on the highway fixture."""
+    import torch
+    from background_subtraction_b200 import dist as bdist
+    from oracle import alm_oracle as O
+    gold = summary["highway_half_group_sparse"]
+    frames = highway_fixture["frames"]
+    h, w, t = frames.shape
+    D, _x, _mean = O.normalize_and_center(frames)
+    labels, ptr, lam = highway_fixture["labels"], highway_fixture["lam_ptr"], highway_fixture["lam"]
+    s = bdist.CudaStepSolver(h, w, t, h * w, blocks=(labels, ptr, np.append(lam, 0.0)))
+    s.load(np.ascontiguousarray(D.T, dtype=np.float32))
+
+    class Solo:
+        world, rank = 1, 0
+
+        def all_reduce_sum(self, t_):
+            pass
+
+        def all_reduce_max(self, t_):
+            pass
+    assert s.block_sums_view() is not None and s.block_sums_view().numel() == t * (int(np.diff(ptr).max()) + 1)
+    drv = bdist.ShardedLSD(s, Solo())
+    drv.solve()
+    drv.finish(2.0, want_mask=False)
+    torch.cuda.synchronize()
+    st, log = s.status(), s.dec.log()
+    assert st.iter == gold["iters"] and bool(st.converged) == gold["converged"]
+    assert [l['svp'] for l in log] == gold["svp"]
+    L = s.dec.download('L')
+    assert abs(np.linalg.norm(L) - gold["normL"]) <= 1e-5 * gold["normL"]
