@@ -401,6 +401,7 @@ struct GraphTileArgs {
     const float* U; float* V; float* xi; float* tot; const float* eta;
     long long ld; int rows, cols, n; float lam; int max_outer; float tol;
     int* sweeps_out; unsigned int* change_bits;   // [3]: largest dual change of outer iteration k lives in slot k % 3
+    unsigned int* item_ctr;                       // [3]: work counter of phase k lives in slot k % 3 (dynamic tile scheduling)
     const DevState* st;
     int center; long long eta_stride;
     int nwi, nwj, chunk;
@@ -434,9 +435,10 @@ __global__ void __launch_bounds__(GT_THREADS) prox_graph3_tile_kernel(GraphTileA
     const long long nw = (long long)nwi * nwj;
     const int tid = threadIdx.x;
     const long long gsz = (long long)gridDim.x * blockDim.x, gid = (long long)blockIdx.x * blockDim.x + tid;
-    if (blockIdx.x == 0 && tid < 3) a.change_bits[tid] = 0u;
+    __shared__ long long item_s;
+    if (blockIdx.x == 0 && tid < 3) { a.change_bits[tid] = 0u; a.item_ctr[tid] = 0u; }
     grid.sync();
-    int oc = 0, most = 0;
+    int oc = 0, most = 0, pc = 0;                                // outer iterations and phases done so far (slot rotation)
     for (int f0 = 0; f0 < a.n; f0 += a.chunk) {
         const int nf = min(a.chunk, a.n - f0);
         int outer = 0;
@@ -448,7 +450,14 @@ __global__ void __launch_bounds__(GT_THREADS) prox_graph3_tile_kernel(GraphTileA
                 const int ntc = (max(cols - off, 0) + GT_T - 1) / GT_T + (off > 0 ? 1 : 0);
                 const long long per_frame = (long long)ntr * ntc, nitems = per_frame * nf;
                 const bool first = (outer == 0 && ph == 0);      // nothing has been written yet: tot = 0, xi = 0
-                for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+                // Tiles are handed out through a counter: a visit costs between 1 and GT_INNER sweeps, and with a fixed assignment
+                // half of the warp time of a small clip was spent waiting at the grid barrier for the unluckiest CTA (ncu r2y).
+                for (;;) {
+                    if (tid == 0) item_s = (long long)atomicAdd(a.item_ctr + (pc % 3), 1u);
+                    __syncthreads();
+                    const long long item = item_s;
+                    __syncthreads();
+                    if (item >= nitems) break;
                     const int fl = (int)(item / per_frame);
                     const int tt = (int)(item - (long long)fl * per_frame);
                     const int tc = tt / ntr, tr = tt - tc * ntr;
@@ -577,6 +586,8 @@ __global__ void __launch_bounds__(GT_THREADS) prox_graph3_tile_kernel(GraphTileA
                     if ((tid & 31) == 0 && mych > 0.f) atomicMax(a.change_bits + (oc % 3), __float_as_uint(mych));
                 }
                 grid.sync();
+                if (blockIdx.x == 0 && tid == 0) a.item_ctr[(pc + 2) % 3] = 0u;      // next used two phases from now
+                ++pc;
             }
             const float chg = __uint_as_float(*((volatile unsigned int*)(a.change_bits + (oc % 3))));
             if (blockIdx.x == 0 && tid == 0) a.change_bits[(oc + 2) % 3] = 0u;      // next written two outer iterations from now
@@ -610,7 +621,7 @@ void prox_graph3_workspace(int rows, int cols, int n, long long ld, int center, 
         const long long cap = cap_mb * (1LL << 20) / 4;
         frames = std::max(1LL, std::min<long long>(n, cap / std::max(1LL, nw * 9)));
     }
-    *xi_floats = frames * nw * 9;
+    *xi_floats = frames * nw * 9 + 16;            // + the three work counters of the tile kernel
     *tot_floats = frames * ld;
 }
 
@@ -644,8 +655,9 @@ int launch_prox_graph3(const float* U, float* V, float* xi, long long xi_floats,
     a.nwi = center ? rows : rows - std::min(3, rows) + 1;
     a.nwj = center ? cols : cols - std::min(3, cols) + 1;
     const long long per_frame = (long long)a.nwi * a.nwj * 9;
-    if (xi_floats < per_frame) { set_error("prox_graph3: dual buffer smaller than one frame"); return -1; }
-    a.chunk = (int)std::max(1LL, std::min<long long>(n, xi_floats / std::max(1LL, per_frame)));
+    if (xi_floats < per_frame + 16) { set_error("prox_graph3: dual buffer smaller than one frame"); return -1; }
+    a.chunk = (int)std::max(1LL, std::min<long long>(n, (xi_floats - 16) / std::max(1LL, per_frame)));
+    a.item_ctr = reinterpret_cast<unsigned int*>(xi + (xi_floats - 16));
     const long long tiles = (long long)((rows + GT_T - 1) / GT_T + 1) * ((cols + GT_T - 1) / GT_T + 1) * std::min(n, a.chunk);
     long long want = std::min<long long>(tiles, (long long)blocks_per_sm * num_sms);
     if (want < 1) want = 1;
