@@ -190,6 +190,9 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                         for (int j = 0; j < 4; ++j) {
                             const int cls = i + j - 3;
                             if (cls < 0) continue;
+                            // diagonal tile: P_ji = P_ij^T, classes 0 and 2 keep the i < j half (7 of 10 products); the epilogue
+                            // adds the transpose (as in gram_i8_c3_kernel)
+                            if (diag && cls != 1 && i > j) continue;
                             const uint64_t da = sa + (uint64_t)((i * GI_TILE_BYTES + ks * 4096) >> 4);
                             const uint64_t db = sb + (uint64_t)((j * GI_TILE_BYTES) >> 4) + (uint64_t)ks * (uint64_t)((2 * lboB) >> 4);
                             // first pair of a class right after a flush overwrites the accumulator
@@ -228,9 +231,10 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                     for (int e = 0; e < 16; ++e) {
                         const int col = bj * 128 + c0 + e;
                         if (col < a.n) {
-                            const long long val = (long long)(int)v3[e] + ((long long)(int)v4[e] << 8) + ((long long)(int)v5[e] << 16) +
-                                                  ((long long)(int)v6[e] << 24);
+                            const long long half = (long long)(int)v3[e] + ((long long)(int)v5[e] << 16);
+                            const long long val = half + ((long long)(int)v4[e] << 8) + ((long long)(int)v6[e] << 24);
                             if (val != 0) atomicAdd(a.Gint + (size_t)row * ldg + col, (unsigned long long)val);
+                            if (diag && half != 0) atomicAdd(a.Gint + (size_t)col * ldg + row, (unsigned long long)half);
                         }
                     }
                 }
@@ -562,8 +566,9 @@ void fill_gram_i8_tables(const GramI8Plan& p, std::vector<int4>& cta_info, std::
     double wsum = 0.0;
     for (int bi = 0; bi < p.nblk; ++bi)
         for (int bj = bi; bj < p.nblk; ++bj) {
-            // the kernel is bound by operand bytes per 64-pixel stage (L2 -> SM), not by the MMAs: balance on bytes
-            const double cost = 128.0 + (bi == bj ? 0.0 : (double)blk_n[bj]);
+            // half operand bytes per 64-pixel stage (one block on the diagonal, two off it), half MMAs (14 vs 20 per stage, x N / 128)
+            const double cost = 0.5 * (128.0 + (bi == bj ? 0.0 : (double)blk_n[bj])) / 256.0 +
+                                0.5 * (bi == bj ? 0.7 : 1.0) * (double)blk_n[bj] / 128.0;
             tiles.push_back({bi, bj}); w.push_back(cost); wsum += cost;
         }
     std::vector<int> cnt(tiles.size(), 1);
