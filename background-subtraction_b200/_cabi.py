@@ -79,6 +79,7 @@ SIGNATURES = {
     "bsub_debug_eig_cycles": (ctypes.c_int, [vp, c_int64_p]),
     "bsub_debug_info": (ctypes.c_int, [vp, c_int32_p]),
     "bsub_debug_counters": (ctypes.c_int, [vp, c_int64_p]),
+    "bsub_debug_graph": (ctypes.c_int, [vp, c_int64_p]),
     "bsub_get_log": (ctypes.c_int, [vp, ctypes.POINTER(IterLog), ctypes.c_int32, c_int32_p]),
     "bsub_mask_stats_local": (ctypes.c_int, [vp, ctypes.c_int, vp]),
     "bsub_mask_host": (ctypes.c_int, [vp, ctypes.c_double, vp, vp]),

@@ -402,6 +402,8 @@ struct GraphTileArgs {
     long long ld; int rows, cols, n; float lam; int max_outer; float tol;
     int* sweeps_out; unsigned int* change_bits;   // [3]: largest dual change of outer iteration k lives in slot k % 3
     unsigned int* item_ctr;                       // [3]: work counter of phase k lives in slot k % 3 (dynamic tile scheduling)
+    float count_factor;                           // a change counts towards the stop test when it exceeds count_factor x the dead band
+    int* stats;                                   // [3] running totals over the calls of a handle: outer iterations, calls, calls that hit the cap
     const DevState* st;
     int center; long long eta_stride;
     int nwi, nwj, chunk;
@@ -562,7 +564,10 @@ __global__ void __launch_bounds__(GT_THREADS) prox_graph3_tile_kernel(GraphTileA
                                                 ts[po + c * GT_PITCH + dr] += r[e] - xo[e];
                                             }
                                         }
-                                    ch = fmaxf(ch, dmax);
+                                    // ... and it takes more than count_factor dead bands to keep the iteration going: among the 6e7 windows of
+                                    // a 1080p clip a few keep trading 3-10 ulp with their neighbours for ever (theta sums nine values), which
+                                    // held every call at the outer-iteration cap
+                                    if (dmax > a.count_factor * 2.4e-7f * wscale) ch = fmaxf(ch, dmax);
                                 }
                             }
                             __syncthreads();
@@ -603,7 +608,10 @@ __global__ void __launch_bounds__(GT_THREADS) prox_graph3_tile_kernel(GraphTileA
         }
         grid.sync();                                             // tot and xi are reused by the next chunk
     }
-    if (blockIdx.x == 0 && tid == 0 && a.sweeps_out != nullptr) *a.sweeps_out = most;
+    if (blockIdx.x == 0 && tid == 0 && a.sweeps_out != nullptr) {
+        *a.sweeps_out = most;
+        if (a.stats != nullptr) { a.stats[0] += most; a.stats[1] += 1; if (most >= a.max_outer) a.stats[2] += 1; }
+    }
 }
 
 static bool graph3_use_global() {
@@ -648,9 +656,12 @@ int launch_prox_graph3(const float* U, float* V, float* xi, long long xi_floats,
     GraphTileArgs a;
     a.U = U; a.V = V; a.xi = xi; a.tot = tot; a.eta = eta; a.ld = ld; a.rows = rows; a.cols = cols; a.n = n; a.lam = lam;
     a.max_outer = max_sweeps; a.tol = tol; a.sweeps_out = sweeps_out; a.st = st;
-    // sweeps_out, when given, is an int[4] owned by the caller: [0] outer iterations used, [1..3] the rotating change flags (per
-    // solver handle, so that handles running concurrently on different streams do not share them)
+    // sweeps_out, when given, is an int[8] owned by the caller: [0] outer iterations used, [1..3] the rotating change flags (per
+    // solver handle, so that handles running concurrently on different streams do not share them), [4..6] running totals
     a.change_bits = (sweeps_out != nullptr) ? reinterpret_cast<unsigned int*>(sweeps_out + 1) : change_bits;
+    a.stats = (sweeps_out != nullptr) ? sweeps_out + 4 : nullptr;          // the caller's int[8]: [4..6] running totals
+    static const float count_factor = getenv("BSUB_GRAPH_COUNT_FACTOR") ? (float)atof(getenv("BSUB_GRAPH_COUNT_FACTOR")) : 8.f;
+    a.count_factor = count_factor;
     a.center = center; a.eta_stride = eta_stride;
     a.nwi = center ? rows : rows - std::min(3, rows) + 1;
     a.nwj = center ? cols : cols - std::min(3, cols) + 1;

@@ -338,7 +338,7 @@ int bsub_set_graph_windows(bsub_solver* s, const double* eta, int64_t n_eta) {
         CK(cudaMalloc((void**)&s->xi, sizeof(float) * (size_t)s->xi_floats));
         CK(cudaMalloc((void**)&s->tot, sizeof(float) * (size_t)tot_floats));
     }
-    if (!s->sweeps_dev) CK(cudaMalloc((void**)&s->sweeps_dev, sizeof(int) * 4));
+    if (!s->sweeps_dev) { CK(cudaMalloc((void**)&s->sweeps_dev, sizeof(int) * 8)); CK(cudaMemset(s->sweeps_dev, 0, sizeof(int) * 8)); }
     s->graph_set = true;
     return 0;
 }
@@ -364,7 +364,7 @@ int bsub_set_center_windows(bsub_solver* s, const float* eta, const uint8_t* bac
         CK(cudaMalloc((void**)&s->xi, sizeof(float) * (size_t)s->xi_floats));
         CK(cudaMalloc((void**)&s->tot, sizeof(float) * (size_t)tot_floats));
     }
-    if (!s->sweeps_dev) CK(cudaMalloc((void**)&s->sweeps_dev, sizeof(int) * 4));
+    if (!s->sweeps_dev) { CK(cudaMalloc((void**)&s->sweeps_dev, sizeof(int) * 8)); CK(cudaMemset(s->sweeps_dev, 0, sizeof(int) * 8)); }
     s->graph_set = true;
     return 0;
 }
@@ -833,6 +833,14 @@ int bsub_debug_counters(bsub_solver* s, int64_t* out8) {
     return 0;
 }
 
+int bsub_debug_graph(bsub_solver* s, int64_t* out4) {
+    if (!s || !out4) { set_error("bsub_debug_graph: null argument"); return -1; }
+    int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (s->sweeps_dev) CK(cudaMemcpy(h, s->sweeps_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    out4[0] = h[0]; out4[1] = h[4]; out4[2] = h[5]; out4[3] = h[6];
+    return 0;
+}
+
 int bsub_get_log(bsub_solver* s, bsub_iter_log* out, int32_t cap, int32_t* count) {
     if (!s || !out || !count) { set_error("bsub_get_log: null argument"); return -1; }
     DevState h;
@@ -952,7 +960,8 @@ int bsub_prox_graph3_dev(const float* U, float* V, int64_t ld, int32_t rows, int
     prox_graph3_workspace(rows, cols, n, ld, 0, &xi_floats, &tot_floats);
     RET_IF(mem.alloc(&xi, sizeof(float) * (size_t)xi_floats));
     RET_IF(mem.alloc(&tot, sizeof(float) * (size_t)tot_floats));
-    RET_IF(mem.alloc(&sw, sizeof(int) * 4));
+    RET_IF(mem.alloc(&sw, sizeof(int) * 8));
+    CK(cudaMemset(sw, 0, sizeof(int) * 8));
     if (eta_host) {
         std::vector<float> ef((size_t)nw);
         for (long long i = 0; i < nw; ++i) ef[i] = (float)eta_host[i];
@@ -980,7 +989,8 @@ int bsub_prox_center3_dev(const float* U, float* V, int64_t ld, int32_t rows, in
     RET_IF(mem.alloc(&xi, sizeof(float) * (size_t)xi_floats));
     RET_IF(mem.alloc(&tot, sizeof(float) * (size_t)tot_floats));
     RET_IF(mem.alloc(&eta, sizeof(float) * (size_t)n * m));
-    RET_IF(mem.alloc(&sw, sizeof(int) * 4));
+    RET_IF(mem.alloc(&sw, sizeof(int) * 8));
+    CK(cudaMemset(sw, 0, sizeof(int) * 8));
     CK(cudaMemcpy(eta, eta_host, sizeof(float) * (size_t)n * m, cudaMemcpyHostToDevice));
     RET_IF(launch_prox_graph3(U, V, xi, xi_floats, tot, eta, ld, rows, cols, n, (float)lambda1, max_sweeps > 0 ? max_sweeps : 4000, (float)tol, sw,
                               nullptr, st, 1, m));

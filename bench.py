@@ -40,6 +40,7 @@ WORKLOADS = {
     "watersurface_graph": (128, 160, 48, None, None),
     "synthetic_qvga_200_graph": (240, 320, 200, 100, 3),
     "synthetic_1080p_300_graph": (1080, 1920, 300, 0, 6),
+    "synthetic_1080p_30_graph": (1080, 1920, 30, 0, 6),       # the first 10th of the period of that clip (the prox cost is per frame)
 }
 
 

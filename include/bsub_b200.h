@@ -164,6 +164,8 @@ int bsub_debug_info(bsub_solver* s, int32_t* out16);   /* ..., [12] plane projec
  * [4] Gram mode of the next iteration (0 fp64 DMMA, 1 int8 tcgen05), [5] last digit pass saturated, [6] the solve has switched
  * to the fp64 Gram for accuracy, [7] 1e6 * bound of the int8 Gram's truncation error relative to (1/mu)^2 */
 int bsub_debug_counters(bsub_solver* s, int64_t* out8);
+/* overlapping-window prox of this handle: out4 = {outer iterations of the last call, their total over all calls, calls, calls that hit graph_max_sweeps} */
+int bsub_debug_graph(bsub_solver* s, int64_t* out4);
 /* foreground_mask(D, L, S, sigmas) of utils.py:139-149 on the solver's own D, L, S; mask uint8[n][m] on the host */
 int bsub_mask_stats_local(bsub_solver* s, int phase /*0: max|S|, 1: count/sum/sumsq*/, void* stream);
 int bsub_mask_host(bsub_solver* s, double sigmas, uint8_t* mask_host, void* stream);
