@@ -449,10 +449,10 @@ def _finish(dec, D0, verbose):
             print(f"Iteration: {l['iter']:3d} rank(L): {l['svp']:2d} ||S||_0: {l['nnz']:.2E} err: {l['err']:.3E}")
         print('CONVERGED' if st.converged else ('L reached rank 0' if st.done == 3 else 'NOT CONVERGED'))
     if _is_torch(D0):
-        L = dec.device_tensor('L').t()
-        S = dec.device_tensor('S').t()
-        L._bsub_owner = dec
-        S._bsub_owner = dec
+        # copies that own their storage: a view of solver memory would dangle as soon as a derived view (L[:, :k], .t(), ...)
+        # outlives the handle.  Zero-copy access stays available through Decomposition.device_tensor().
+        L = dec.device_tensor('L').clone().t()
+        S = dec.device_tensor('S').clone().t()
     else:
         L = dec.download('L')
         S = dec.download('S')

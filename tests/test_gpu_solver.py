@@ -269,3 +269,25 @@ def test_errors(B):
         B.inexact_alm_lsd(D, graphs=B.getGraphSPAMS_all_groups((6, 6), (3, 3)), groups=np.ones(36, dtype=np.int32))
     with pytest.raises(Exception):
         B.inexact_alm_lsd(D, groups=np.ones(35, dtype=np.int32))
+
+
+def test_torch_cuda_input_returns_owning_tensors(B, watersurface_u8):
+    """Drop-in call with a torch CUDA matrix: L and S come back as CUDA tensors that own their storage (they -- and views derived
+    from them -- stay valid after the solver handle is gone) and equal the NumPy path."""
+    import gc
+    import torch
+    from oracle import alm_oracle as O
+    D, _x, _mean = O.normalize_and_center(watersurface_u8[:64, :60, :24])
+    groups = B.get_proximal_flat_groups_nonoverlap((64, 60), (3, 3))
+    Ln, Sn, itn, convn = B.inexact_alm_lsd(D, groups=groups)
+    Dt = torch.from_numpy(np.ascontiguousarray(D.T, dtype=np.float32)).cuda().t()          # [m, n] view, F-order like the reference
+    Lt, St, itt, convt = B.inexact_alm_lsd(Dt, groups=groups)
+    assert Lt.is_cuda and St.is_cuda and tuple(Lt.shape) == D.shape and itt == itn and convt == convn
+    view = Lt[:, :5]
+    gc.collect()
+    torch.cuda.synchronize()
+    junk = [torch.full((1 << 22,), float("nan"), device="cuda") for _ in range(8)]          # recycle freed device memory, if any
+    torch.cuda.synchronize()
+    assert rel_fro(Lt.cpu().numpy().astype(np.float64), Ln) <= 1e-6 and rel_fro(St.cpu().numpy().astype(np.float64), Sn) <= 1e-6
+    assert torch.isfinite(view).all()
+    del junk
