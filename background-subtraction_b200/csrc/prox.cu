@@ -639,8 +639,8 @@ int launch_prox_graph3(const float* U, float* V, float* xi, long long xi_floats,
     if (xi == nullptr || tot == nullptr) { set_error("prox_graph3: missing workspace"); return -1; }
     if (graph3_use_global())
         return launch_prox_graph3_global(U, V, xi, tot, eta, ld, rows, cols, n, lam, max_sweeps, tol, sweeps_out, st, s, center, eta_stride);
+    if (sweeps_out == nullptr) { set_error("prox_graph3: the caller's int[8] status block is required"); return -1; }
     static int blocks_per_sm = 0, num_sms = 0;
-    static unsigned int* change_bits = nullptr;
     static unsigned long long attr_devs = 0;
     if (first_call_on_device(&attr_devs))
         BSUB_CUDA_CHECK(cudaFuncSetAttribute(prox_graph3_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM));
@@ -650,16 +650,15 @@ int launch_prox_graph3(const float* U, float* V, float* xi, long long xi_floats,
         BSUB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         BSUB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, prox_graph3_tile_kernel, GT_THREADS, GT_SMEM));
         if (blocks_per_sm < 1) { set_error("prox_graph3: kernel does not fit"); return -1; }
-        BSUB_CUDA_CHECK(cudaMalloc(&change_bits, 3 * sizeof(unsigned int)));
     }
     if (center && eta == nullptr) { set_error("prox_graph3: centre mode needs the per-frame eta map"); return -1; }
     GraphTileArgs a;
     a.U = U; a.V = V; a.xi = xi; a.tot = tot; a.eta = eta; a.ld = ld; a.rows = rows; a.cols = cols; a.n = n; a.lam = lam;
     a.max_outer = max_sweeps; a.tol = tol; a.sweeps_out = sweeps_out; a.st = st;
-    // sweeps_out, when given, is an int[8] owned by the caller: [0] outer iterations used, [1..3] the rotating change flags (per
+    // sweeps_out is an int[8] owned by the caller: [0] outer iterations used, [1..3] the rotating change flags (per
     // solver handle, so that handles running concurrently on different streams do not share them), [4..6] running totals
-    a.change_bits = (sweeps_out != nullptr) ? reinterpret_cast<unsigned int*>(sweeps_out + 1) : change_bits;
-    a.stats = (sweeps_out != nullptr) ? sweeps_out + 4 : nullptr;          // the caller's int[8]: [4..6] running totals
+    a.change_bits = reinterpret_cast<unsigned int*>(sweeps_out + 1);
+    a.stats = sweeps_out + 4;                                              // the caller's int[8]: [4..6] running totals
     static const float count_factor = getenv("BSUB_GRAPH_COUNT_FACTOR") ? (float)atof(getenv("BSUB_GRAPH_COUNT_FACTOR")) : 8.f;
     a.count_factor = count_factor;
     a.center = center; a.eta_stride = eta_stride;
