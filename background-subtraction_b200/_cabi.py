@@ -67,6 +67,8 @@ SIGNATURES = {
     "bsub_step_shrink_a": (ctypes.c_int, [vp, vp]),
     "bsub_step_shrink_b": (ctypes.c_int, [vp, vp]),
     "bsub_block_sums_buffer": (ctypes.c_int, [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64)]),
+    "bsub_step_prox_buffers": (ctypes.c_int, [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), c_int64_p]),
+    "bsub_step_prox_frames": (ctypes.c_int, [vp, vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp]),
     "bsub_poll": (ctypes.c_int, [vp, ctypes.POINTER(Status)]),
     "bsub_sync_status": (ctypes.c_int, [vp, ctypes.POINTER(Status), vp]),
     "bsub_finalize": (ctypes.c_int, [vp, vp]),

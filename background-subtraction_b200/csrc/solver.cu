@@ -64,7 +64,9 @@ struct bsub_solver {
     // generic flat groups
     int* gptr = nullptr; int* gidx = nullptr; int ngroups = 0; bool groups_set = false;
     // overlapping graph
-    float* eta_dev = nullptr; float* xi = nullptr; long long xi_floats = 0; float* tot = nullptr; int* sweeps_dev = nullptr; bool graph_set = false;
+    float* eta_dev = nullptr; float* xi = nullptr; long long xi_floats = 0; float* tot = nullptr;
+    float* xi2 = nullptr; float* tot2 = nullptr; int* sweeps2 = nullptr; long long xi2_floats = 0, tot2_floats = 0;   // bsub_step_prox_frames
+    int* sweeps_dev = nullptr; bool graph_set = false;
     // l2 blocks
     unsigned char* labels_dev = nullptr; double* lam_table = nullptr; double* bsums = nullptr; int nlab = 0; bool blocks_set = false;
     unsigned char* mask_stage = nullptr;      // bsub_mask_host staging
@@ -133,7 +135,7 @@ int bsub_destroy(bsub_solver* s) {
     void* ptrs[] = {s->D, s->S, s->Y, s->T, s->L, s->U, s->st, s->log, s->comm_sum, s->comm_max, s->tasks_dev, s->gram_partial,
                     s->eb.work, s->eb.lam, s->eb.Z, s->eb.Vr, s->eb.VC, s->tpart, s->part_zz, s->part_nnz, s->part_max, s->gptr,
                     s->gidx, s->eta_dev, s->xi, s->tot, s->sweeps_dev, s->labels_dev, s->lam_table, s->bsums, s->Wq, s->Gint,
-                    s->gi_info, s->gi_blkn, s->part_wmax, s->mask_stage, s->mask_scratch, s->stage64, s->Tt};
+                    s->gi_info, s->gi_blkn, s->part_wmax, s->mask_stage, s->mask_scratch, s->stage64, s->Tt, s->xi2, s->tot2, s->sweeps2};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (s->mirror) cudaFreeHost((void*)s->mirror);
     for (int i = 0; i <= kRunAhead; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -579,10 +581,13 @@ int bsub_step_project(bsub_solver* s, void* stream) {
 static int step_shrink_impl(bsub_solver* s, void* stream, int part) {
     if (!s || !s->initialised) { set_error("bsub_step_shrink: solver not initialised"); return -1; }
     cudaStream_t st = use_stream(s, stream);
-    const bool split = (s->shrink_mode == SHRINK_SPILL && s->cfg.prox == BSUB_PROX_BLOCK_L2);
+    // the overlapping-window mode splits too: between the halves the driver re-shards G_S by FRAMES (the prox of a frame needs the
+    // whole image, bsub_step_prox_frames) and brings S back
+    const bool split = s->shrink_mode == SHRINK_SPILL && (s->cfg.prox == BSUB_PROX_BLOCK_L2 || s->cfg.prox == BSUB_PROX_GRAPH_LINF);
     if (part == 2 && !split) return 0;
     if (part == 2) {
-        RET_IF(launch_block_l2_apply(s->U, s->S, s->labels_dev, s->ld, s->m, s->n, s->nlab, s->bsums, s->lam_table, s->st, 0.0, 0.0, st));
+        if (s->cfg.prox == BSUB_PROX_BLOCK_L2)
+            RET_IF(launch_block_l2_apply(s->U, s->S, s->labels_dev, s->ld, s->m, s->n, s->nlab, s->bsums, s->lam_table, s->st, 0.0, 0.0, st));
         const int np2 = s->num_sms * 8;
         RET_IF(launch_dual_update(s->D, s->S, s->S, s->Y, s->T, s->eb.VC, s->eb.vstride, s->st, s->L, s->ld, s->n, s->part_zz,
                                   s->part_nnz, s->part_max, np2, st));
@@ -638,6 +643,7 @@ static int step_shrink_impl(bsub_solver* s, void* stream, int part) {
         if (s->cfg.prox == BSUB_PROX_FLAT_LINF) {
             RET_IF(launch_prox_groups_csr(s->U, s->S, s->ld, s->m, s->n, s->gptr, s->gidx, s->ngroups, 0.f, s->st, st));
         } else if (s->cfg.prox == BSUB_PROX_GRAPH_LINF) {
+            if (part == 1) return 0;                       // the driver runs the prox on frame shards, then calls part 2
             RET_IF(launch_prox_graph3(s->U, s->S, s->xi, s->xi_floats, s->tot, s->eta_dev, s->ld, s->cfg.rows, s->cfg.cols, s->n, 0.f,
                                       s->cfg.graph_max_sweeps, (float)s->cfg.graph_tol, s->sweeps_dev, s->st, st));
         } else if (s->cfg.prox == BSUB_PROX_GRAPH_CENTER_BG) {
@@ -665,6 +671,30 @@ static int step_shrink_impl(bsub_solver* s, void* stream, int part) {
 int bsub_step_shrink(bsub_solver* s, void* stream) { return step_shrink_impl(s, stream, 0); }
 int bsub_step_shrink_a(bsub_solver* s, void* stream) { return step_shrink_impl(s, stream, 1); }
 int bsub_step_shrink_b(bsub_solver* s, void* stream) { return step_shrink_impl(s, stream, 2); }
+
+int bsub_step_prox_buffers(bsub_solver* s, float** G_S, float** S, int64_t* ld) {
+    if (!s || !s->initialised) { set_error("bsub_step_prox_buffers: solver not initialised"); return -1; }
+    if (G_S) *G_S = s->U;
+    if (S) *S = s->S;
+    if (ld) *ld = s->ld;
+    return 0;
+}
+
+int bsub_step_prox_frames(bsub_solver* s, const float* Uf, float* Vf, int64_t ldf, int32_t rows, int32_t cols, int32_t nf, void* stream) {
+    if (!s || !s->initialised) { set_error("bsub_step_prox_frames: solver not initialised"); return -1; }
+    if (s->cfg.prox != BSUB_PROX_GRAPH_LINF) { set_error("bsub_step_prox_frames: solver was not created with BSUB_PROX_GRAPH_LINF"); return -1; }
+    if (nf <= 0) return 0;
+    if (!Uf || !Vf || (long long)rows * cols > ldf) { set_error("bsub_step_prox_frames: bad argument"); return -1; }
+    cudaStream_t st = use_stream(s, stream);
+    long long xf = 0, tf = 0;
+    prox_graph3_workspace(rows, cols, nf, ldf, 0, &xf, &tf);
+    if (xf > s->xi2_floats) { if (s->xi2) cudaFree(s->xi2); s->xi2 = nullptr; CK(cudaMalloc((void**)&s->xi2, sizeof(float) * (size_t)xf)); s->xi2_floats = xf; }
+    if (tf > s->tot2_floats) { if (s->tot2) cudaFree(s->tot2); s->tot2 = nullptr; CK(cudaMalloc((void**)&s->tot2, sizeof(float) * (size_t)tf)); s->tot2_floats = tf; }
+    if (!s->sweeps2) { CK(cudaMalloc((void**)&s->sweeps2, sizeof(int) * 8)); CK(cudaMemset(s->sweeps2, 0, sizeof(int) * 8)); }
+    // lambda / mu and the stop flag come from the device state, exactly as in the unsharded pass
+    return launch_prox_graph3(Uf, Vf, s->xi2, xf, s->tot2, nullptr, ldf, rows, cols, nf, 0.f, s->cfg.graph_max_sweeps, (float)s->cfg.graph_tol,
+                              s->sweeps2, s->st, st);
+}
 
 int bsub_block_sums_buffer(bsub_solver* s, double** sums, int64_t* count) {
     if (!s) { set_error("bsub_block_sums_buffer: null solver"); return -1; }

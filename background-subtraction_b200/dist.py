@@ -35,8 +35,16 @@ def shard_columns(cols, world, rank):
     return min(3 * t0, cols), min(3 * t1, cols)
 
 
+def shard_frames(n, world, rank):
+    """Frame range [f0, f1) of `rank` for the frame-wise re-sharding of the overlapping-window prox: as even as possible."""
+    base, extra = divmod(n, world)
+    f0 = rank * base + min(rank, extra)
+    return f0, f0 + base + (1 if rank < extra else 0)
+
+
 class TorchComm:
-    """all-reduce on torch tensors over torch.distributed (NCCL on GPUs, gloo on CPU)."""
+    """all-reduce (and the all-to-all of the overlapping-window mode) on torch tensors over torch.distributed (NCCL on GPUs, gloo
+    on CPU)."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -53,21 +61,52 @@ class TorchComm:
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
 
+    def exchange(self, recv, send):
+        """all-to-all: send[q] goes to rank q, recv[q] arrives from rank q (contiguous tensors, sizes agreed by construction)."""
+        if self.world == 1:
+            recv[0].copy_(send[0])
+            return
+        if self.dist.get_backend(self.group) == "nccl":
+            self.dist.all_to_all(recv, send, group=self.group)
+            return
+        recv[self.rank].copy_(send[self.rank])          # gloo has no all-to-all: pairwise non-blocking sends / receives
+        reqs = []
+        for q in range(self.world):
+            if q != self.rank:
+                if send[q].numel():
+                    reqs.append(self.dist.isend(send[q], q, group=self.group))
+                if recv[q].numel():
+                    reqs.append(self.dist.irecv(recv[q], q, group=self.group))
+        for r_ in reqs:
+            r_.wait()
+
 
 class CudaStepSolver:
     """Thin object view of the bsub_step_* C entry points for one shard."""
 
     def __init__(self, rows, cols_local, n, m_global, delta=10, max_iter=500, tile_rows=0, cluster_frames=0, store_S_lazily=True,
-                 blocks=None, use_sv_prediction=True):
+                 blocks=None, use_sv_prediction=True, graph_cols=None):
         """blocks = (labels uint8 [n][rows * cols_local] of THIS shard's pixels, lam_ptr int32 [n + 1], lam float64) selects the
         group-sparse solver (inexact_alm_group_sparse_RPCA, /root/reference/group_sparse_RPCA.py:45-126: l2 blocks per frame,
-        mu0 = 1.25 / ||D||_2, stop on rank 0); lam_ptr / lam are the same on every rank.  Default: flat 3x3 l_inf groups (LSD)."""
+        mu0 = 1.25 / ||D||_2, stop on rank 0); lam_ptr / lam are the same on every rank.  graph_cols = number of image columns of the
+        WHOLE frame selects the reference's default LSD() mode (overlapping 3x3 windows with unit weights,
+        /root/reference/inexact_alm_lsd.py:13-57): the prox then runs on whole frames after a frame-wise re-sharding (ShardedLSD).
+        Default: flat 3x3 l_inf groups (LSD)."""
+        self.rows, self.cols_local, self.graph_cols = rows, cols_local, graph_cols
         # store_S_lazily: let the single-pass shrink kernel skip the store of S in iterations that cannot be the last (it is
         # rebuilt from D, Y and the digit planes at the end).  A clipped digit pass in such an iteration stops EVERY rank with
         # done == 5 in the same iteration (the flag is part of the all-reduced scalars); ShardedLSD then repeats the solve
         # with S stored every time.
         self.m = rows * cols_local
-        if blocks is None:
+        if graph_cols is not None:
+            if blocks is not None:
+                raise Exception("CudaStepSolver: blocks and graph_cols are mutually exclusive")
+            cfg = api.make_config(self.m, n, C.PROX_GRAPH_LINF, rows, cols_local, delta=delta, m_global=m_global,
+                                  d_global=min(m_global, n), max_iter=max_iter)
+            self.lazy_S = False
+            self.dec = api.Decomposition(cfg)
+            self.dec.set_graph_windows(None)
+        elif blocks is None:
             cfg = api.make_config(self.m, n, C.PROX_FLAT_LINF, rows, cols_local, delta=delta, m_global=m_global,
                                   d_global=min(m_global, n), max_iter=max_iter, tile_rows=tile_rows,
                                   cluster_frames=cluster_frames, flags=0 if store_S_lazily else C.FLAG_ALWAYS_STORE_S)
@@ -125,6 +164,28 @@ class CudaStepSolver:
 
     def shrink_b(self):
         C.check(self.lib.bsub_step_shrink_b(self.h, self._s()))
+
+    def graph_split(self):
+        """(rows, columns of the whole frame) when the prox has to run on whole frames (overlapping-window mode), else None."""
+        return (self.rows, self.graph_cols) if self.graph_cols is not None else None
+
+    def prox_buffers(self):
+        """G_S of this pixel shard (valid after shrink_a) and the S it expects before shrink_b: torch views [n][m_local]."""
+        import torch
+        gp, sp, ld = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64(0)
+        C.check(self.lib.bsub_step_prox_buffers(self.h, ctypes.byref(gp), ctypes.byref(sp), ctypes.byref(ld)))
+        return (api._wrap_device(gp.value, (self.n, ld.value), torch.float32)[:, :self.m],
+                api._wrap_device(sp.value, (self.n, ld.value), torch.float32)[:, :self.m])
+
+    def frames_like(self, nf, ldf):
+        import torch
+        return torch.empty((max(nf, 1), ldf), dtype=torch.float32, device="cuda")
+
+    def prox_frames(self, Uf, Vf, rows, cols, nf):
+        """Overlapping-window prox of nf whole frames (rows of Uf / Vf, row stride Uf.stride(0)) at this handle's lambda / mu."""
+        if nf > 0:
+            C.check(self.lib.bsub_step_prox_frames(self.h, ctypes.c_void_p(Uf.data_ptr()), ctypes.c_void_p(Vf.data_ptr()),
+                                                   int(Uf.stride(0)), rows, cols, nf, self._s()))
 
     def block_sums_view(self):
         """l2-block mode: per-(frame, group) sums of squares of this shard, to be all-reduced between shrink_a and shrink_b."""
@@ -190,7 +251,8 @@ class CudaStepSolver:
 
 class ShardedLSD:
     """inexact_alm_lsd (flat 3x3 groups) or inexact_alm_group_sparse_RPCA (l2 blocks, one more all-reduce per iteration: the
-    per-(frame, group) sums of squares) over `comm.world` shards -- the step solver decides which.  hooks: optional callbacks
+    per-(frame, group) sums of squares) or the overlapping-window LSD (the prox runs on whole frames after an all-to-all to a frame
+    sharding, _prox_on_frames) over `comm.world` shards -- the step solver decides which.  hooks: optional callbacks
     hooks[name](phase) with phase in {'begin', 'end'} around 'gram', 'solve', 'shrink' for timing."""
 
     def __init__(self, solver, comm, run_ahead=3, max_iter=500, fence=None):
@@ -228,7 +290,10 @@ class ShardedLSD:
                 hk('project', 'begin'); s.project(); hk('project', 'end')
             hk('shrink', 'begin')
             bs = s.block_sums_view() if hasattr(s, 'block_sums_view') else None
-            if bs is None:
+            gs = s.graph_split() if hasattr(s, 'graph_split') else None
+            if gs is not None:                  # overlapping windows: the prox of a frame needs the whole image
+                s.shrink_a(); self._prox_on_frames(gs); s.shrink_b()
+            elif bs is None:
                 s.shrink()
             else:                               # l2 blocks: the groups span the shards (group_sparse_RPCA.py:29-40)
                 s.shrink_a(); comm.all_reduce_sum(bs); s.shrink_b()
@@ -240,6 +305,40 @@ class ShardedLSD:
             s.store_S_always()
             return self.solve(hooks)
         return self
+
+    def _prox_on_frames(self, geometry):
+        """G_S is sharded by pixel columns, the overlapping-window prox couples the pixels of a frame but not the frames: all-to-all
+        to a FRAME sharding (rank r gets whole frames [f0_r, f1_r)), prox, all-to-all back into S.  Exact (no halo approximation);
+        3 x the shard per rank over NVLink per iteration, small against the prox itself."""
+        s, comm = self.s, self.comm
+        rows, cols = geometry
+        W, r = comm.world, comm.rank
+        U, S = s.prox_buffers()                                  # [n][m_local]
+        n = U.shape[0]
+        f0, f1 = shard_frames(n, W, r)
+        nf = f1 - f0
+        if W == 1:
+            s.prox_frames(U, S, rows, cols, nf)
+            return
+        cr = [shard_columns(cols, W, q) for q in range(W)]
+        fr = [shard_frames(n, W, q) for q in range(W)]
+        m_full = rows * cols
+        ldf = (m_full + 31) // 32 * 32
+        Uf, Vf = s.frames_like(nf, ldf), s.frames_like(nf, ldf)
+        # S travels too: once the solve has stopped (the host runs a few iterations ahead of the device-side flag) the prox kernel
+        # returns at its first line, and what comes back must then be the S that is already there
+        for src, dst in ((U, Uf), (S, Vf)):
+            send = [src[a:b, :].contiguous() for a, b in fr]
+            recv = [U.new_empty((nf, (c1 - c0) * rows)) for c0, c1 in cr]
+            comm.exchange(recv, send)
+            for (c0, c1), t in zip(cr, recv):
+                dst[:nf, c0 * rows:c1 * rows] = t
+        s.prox_frames(Uf, Vf, rows, cols, nf)
+        send = [Vf[:nf, c0 * rows:c1 * rows].contiguous() for c0, c1 in cr]
+        recv = [U.new_empty((b - a, U.shape[1])) for a, b in fr]
+        comm.exchange(recv, send)
+        for (a, b), t in zip(fr, recv):
+            S[a:b, :] = t
 
     def finish(self, sigmas=2.0, want_mask=True):
         s, comm = self.s, self.comm

@@ -143,6 +143,14 @@ int bsub_step_finish_iter(bsub_solver* s, void* stream);   /* err, mu update, st
 int bsub_step_shrink_a(bsub_solver* s, void* stream);
 int bsub_step_shrink_b(bsub_solver* s, void* stream);
 int bsub_block_sums_buffer(bsub_solver* s, double** sums, int64_t* count);
+/* Overlapping-window mode (inexact_alm_lsd.py:49-57) on pixel shards: the prox of a frame needs the whole image, so between the two
+ * halves of the pass the driver re-shards G_S by FRAMES (all-to-all), runs the prox of its frames and brings S back:
+ *   _shrink_a (G_S of this pixel shard into the buffer _prox_buffers returns) -> exchange -> _prox_frames (nf whole frames of
+ *   rows x cols pixels, device pointers, lambda/mu and the stop flag from this handle's device state) -> exchange (result into the S
+ *   pointer of _prox_buffers) -> _shrink_b.  All-window graphs with unit weights only. */
+int bsub_step_prox_buffers(bsub_solver* s, float** G_S, float** S, int64_t* ld);
+int bsub_step_prox_frames(bsub_solver* s, const float* U_frames, float* V_frames, int64_t ld_frames, int32_t rows, int32_t cols,
+                          int32_t n_frames, void* stream);
 int bsub_poll(bsub_solver* s, bsub_status* st);            /* non-blocking: host mirror written by the device       */
 int bsub_sync_status(bsub_solver* s, bsub_status* st, void* stream);   /* blocking                                 */
 

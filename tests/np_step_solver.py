@@ -9,7 +9,7 @@ from oracle import alm_oracle as O
 
 class NumpyStepSolver:
     def __init__(self, D_local, rows, cols_local, n, m_global, delta=10, mu_scale=12.5, rho=1.6, tol=1e-7, max_iter=500,
-                 labels=None, lambdas_by_frame=None):
+                 labels=None, lambdas_by_frame=None, graph_cols=None):
         """labels (int [n][m_local], 0 = complement) + lambdas_by_frame select the group-sparse solver
         (/root/reference/group_sparse_RPCA.py:45-126: l2 blocks, mu0 = 1.25/||D||_2, break on rank 0)."""
         self.D = np.asfortranarray(D_local, dtype=np.float64)          # m_local x n
@@ -23,6 +23,9 @@ class NumpyStepSolver:
         self.ngram = n * n
         self.log = []
         self.labels, self.lams = labels, lambdas_by_frame
+        self.graph_cols = graph_cols            # overlapping 3x3 windows of the WHOLE frame (rows x graph_cols): prox on whole frames
+        if graph_cols is not None:
+            self.gc_full = O.graph_all_groups((rows, graph_cols), (3, 3))
         self.bsums = None
         if labels is not None:
             self.mu_scale = 1.25
@@ -31,6 +34,19 @@ class NumpyStepSolver:
             self.nbl = 100.0 * self.lam
 
     def block_sums_view(self): return self.bsums
+
+    def graph_split(self): return (self.rows, self.graph_cols) if self.graph_cols is not None else None
+
+    def prox_buffers(self):
+        return torch.from_numpy(self.G_S.T), torch.from_numpy(self.S.T)          # [n][m_local] views of the F-order matrices
+
+    def frames_like(self, nf, ldf): return torch.zeros((max(nf, 1), ldf), dtype=torch.float64)
+
+    def prox_frames(self, Uf, Vf, rows, cols, nf):
+        if self.done_flag or nf == 0: return
+        m = rows * cols
+        V = O.prox_graph(np.asfortranarray(Uf[:nf, :m].numpy().T), self.lam / self.mu, self.gc_full, tol=1e-13)
+        Vf[:nf, :m] = torch.from_numpy(np.ascontiguousarray(V.T))
 
     # -- views used by the driver's all-reduces
     def gram_view(self): return self.sum_buf[:self.ngram]
@@ -86,7 +102,10 @@ class NumpyStepSolver:
     def shrink_a(self):
         if self.done_flag: return
         self.L = self.W @ self.P
-        self.G_S = self.D - self.L + self.Y / self.mu
+        self.G_S = np.asfortranarray(self.D - self.L + self.Y / self.mu)
+        if self.graph_cols is not None:
+            self.S = np.asfortranarray(self.S)
+            return
         sums = np.zeros((self.n, self.nlab))
         for f in range(self.n):
             np.add.at(sums[f], self.labels[f], self.G_S[:, f] ** 2)
@@ -94,6 +113,13 @@ class NumpyStepSolver:
 
     def shrink_b(self):
         if self.done_flag: return
+        if self.graph_cols is not None:          # S has been filled by the driver (prox on whole frames)
+            Z = self.D - self.L - self.S
+            self.Y = self.Y + self.mu * Z
+            self.sum_buf[self.ngram:self.ngram + 4] = torch.tensor([float((Z * Z).sum()), float(np.count_nonzero(self.S)), 0.0, 0.0],
+                                                                  dtype=torch.float64)
+            self.mu *= self.rho
+            return
         sums = self.bsums.numpy().reshape(self.n, self.nlab)
         S = np.zeros_like(self.G_S)
         with np.errstate(divide='ignore', invalid='ignore'):

@@ -123,3 +123,43 @@ def test_sharded_group_sparse_matches_oracle(tmp_path):
         assert int(p["iters"]) == it and bool(p["conv"]) == conv
         assert p["svp"].tolist() == [l["svp"] for l in log if l["err"] is not None]
     assert np.abs(Ls - L).max() <= 1e-9 and np.abs(Ss - S).max() <= 1e-9
+
+
+def _worker_graph(rank, world, port, rows, cols, n, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from background_subtraction_b200 import dist as bdist, synth
+    from np_step_solver import NumpyStepSolver
+    from oracle import alm_oracle as O
+    video, _ = synth.make_clip(rows, cols, n, seed=11, n_rect=2)
+    cube = np.asfortranarray(video.reshape(n, cols, rows).transpose(2, 1, 0))
+    D, _x, _mean = O.normalize_and_center(cube)
+    c0, c1 = bdist.shard_columns(cols, world, rank)
+    solver = NumpyStepSolver(D[c0 * rows:c1 * rows, :], rows, c1 - c0, n, rows * cols, graph_cols=cols)
+    driver = bdist.ShardedLSD(solver, bdist.TorchComm(), run_ahead=2)
+    driver.solve()
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), L=solver.L, S=solver.S, iters=solver.iter, conv=solver.converged,
+             svp=[l[1] for l in solver.log])
+    dist.destroy_process_group()
+
+
+def test_sharded_graph_mode_matches_oracle(tmp_path):
+    """Overlapping-window LSD on 2 ranks: G_S is re-sharded by frames (all-to-all; 7 frames -> 4 + 3), the prox runs on whole
+    frames, S comes back by columns (SURVEY 8e "Exceptions", solved exactly instead of with a halo)."""
+    rows, cols, n, world = 12, 15, 7, 2
+    port = _free_port()
+    mp.spawn(_worker_graph, args=(world, port, rows, cols, n, str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, ROOT)
+    from background_subtraction_b200 import synth
+    from oracle import alm_oracle as O
+    video, _ = synth.make_clip(rows, cols, n, seed=11, n_rect=2)
+    cube = np.asfortranarray(video.reshape(n, cols, rows).transpose(2, 1, 0))
+    D, _x, _mean = O.normalize_and_center(cube)
+    log = []
+    L, S, it, conv = O.inexact_alm_lsd(D, graphs=O.graph_all_groups((rows, cols), (3, 3)), log=log)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    Ls = np.vstack([p["L"] for p in parts]); Ss = np.vstack([p["S"] for p in parts])
+    for p in parts:
+        assert int(p["iters"]) == it and bool(p["conv"]) == conv and p["svp"].tolist() == [l["svp"] for l in log]
+    assert np.abs(Ls - L).max() <= 1e-9 and np.abs(Ss - S).max() <= 1e-9

@@ -258,3 +258,36 @@ def test_group_sparse_through_sharded_driver(B, highway_fixture, summary):
     assert [l['svp'] for l in log] == gold["svp"]
     L = s.dec.download('L')
     assert abs(np.linalg.norm(L) - gold["normL"]) <= 1e-5 * gold["normL"]
+
+
+def test_graph_mode_through_sharded_driver(B, watersurface_u8):
+    """The overlapping-window LSD through dist.ShardedLSD (world size 1: the split shrink pass, bsub_step_prox_buffers /
+    bsub_step_prox_frames -- the pieces the multi-GPU driver puts an all-to-all between): same result as bsub_run."""
+    import torch
+    from background_subtraction_b200 import dist as bdist
+    from oracle import alm_oracle as O
+    h, w, t = 64, 60, 12
+    D, _x, _mean = O.normalize_and_center(watersurface_u8[:h, :w, :t])
+    graph = B.getGraphSPAMS_all_groups((h, w), (3, 3))
+    dec = B.lsd_decomposition(D, graphs=graph)
+    st0, log0 = dec.status(), dec.log()
+    S0 = dec.download('S')
+    s = bdist.CudaStepSolver(h, w, t, h * w, graph_cols=w)
+    s.load(np.ascontiguousarray(D.T, dtype=np.float32))
+
+    class Solo:
+        world, rank = 1, 0
+
+        def all_reduce_sum(self, t_):
+            pass
+
+        def all_reduce_max(self, t_):
+            pass
+    drv = bdist.ShardedLSD(s, Solo())
+    drv.solve()
+    drv.finish(2.0, want_mask=False)
+    torch.cuda.synchronize()
+    st, log = s.status(), s.dec.log()
+    assert st.iter == st0.iter and bool(st.converged) and bool(st0.converged)
+    assert [l['svp'] for l in log] == [l['svp'] for l in log0]
+    assert rel_fro(s.dec.download('S'), S0) <= 1e-6
