@@ -1,6 +1,6 @@
 """Overlapping-window LSD sharded over GPUs (frame re-sharding around the prox, dist.ShardedLSD._prox_on_frames) against the
-single-GPU solve of the same clip.  NOT yet run on hardware: the all-to-all choreography is covered by
-tests/test_dist_gloo.py on CPU ranks and the split entry points by tests/test_gpu_parity.py on one GPU.
+single-GPU solve of the same clip (run on 2 B200s in round 2: profiles/r2x_check_sharded_2gpu.log).  The all-to-all choreography
+is also covered by tests/test_dist_gloo.py on CPU ranks and the split entry points by tests/test_gpu_parity.py on one GPU.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 scripts/check_sharded_graph.py
 """

@@ -18,3 +18,15 @@ def test_two_rank_nccl_matches_single_gpu():
            "--master-port", "29517", os.path.join(ROOT, "scripts", "check_sharded.py")]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_two_rank_nccl_graph_mode_matches_single_gpu():
+    """Overlapping-window LSD with the frame re-sharding all-to-all around the prox (dist.ShardedLSD._prox_on_frames)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", os.path.join(ROOT, "scripts", "check_sharded_graph.py")]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
