@@ -253,53 +253,87 @@ def batch_clips(args, rank, world, local_rank, sampler_cls, nclips=64, rows=240,
 # ------------------------------------------------------------------------------------------------------------------
 def graph_lsd(args, rank, world, sampler_cls, rows, cols, frames, video, label):
     """The reference's DEFAULT LSD() mode (graphs=getGraphSPAMS_all_groups: overlapping 3x3 windows at every pixel,
-    /root/reference/inexact_alm_lsd.py:203-235, :49-57) on one GPU: spill pass -> tile-local dual BCD (prox.cu) -> dual update, fp64
-    Gram.  One step = one whole decomposition (init + ALM iterations + L + mask), device-resident float32 input."""
+    /root/reference/inexact_alm_lsd.py:203-235, :49-57): spill pass -> tile-local dual BCD (prox.cu) -> dual update, fp64 Gram.  One
+    step = one whole decomposition (init + ALM iterations + L + mask), device-resident float32 input.  --gpus N > 1: pixel-column
+    shards with the prox on whole frames after an all-to-all (this leg of the bench was written after the round's GPU budget was
+    spent: the driver it calls is verified on 2 B200s by scripts/check_sharded_graph.py, the bench wrapper itself has not run)."""
     import ctypes
     import torch
     import background_subtraction_b200 as B
     from background_subtraction_b200 import _cabi as C, synth
-    if world > 1:
-        raise SystemExit("the graph workloads are single-GPU (the overlapping-window prox needs a halo exchange to shard; not built)")
     m = rows * cols
-    D = torch.from_numpy(synth.preprocess_u8(video)).cuda()                  # float32 [frames][m]
-    dec = B.Decomposition(B.make_config(m, frames, C.PROX_GRAPH_LINF, rows, cols))
-    dec.set_graph_windows(None)
     stream = torch.cuda.current_stream()
-    res = {}
+    if world > 1:
+        # pixel-column shards; the prox runs on whole frames after an all-to-all (dist.ShardedLSD._prox_on_frames), so the dominant
+        # cost of this mode splits by frames.  Same choreography as scripts/check_sharded_graph.py (verified on 2 B200s).
+        import torch.distributed as dist
+        from background_subtraction_b200 import dist as bdist
+        c0, c1 = bdist.shard_columns(cols, world, rank)
+        cl = c1 - c0
+        full = synth.preprocess_u8(video)
+        D = torch.from_numpy(np.ascontiguousarray(full.reshape(frames, cols, rows)[:, c0:c1, :].reshape(frames, rows * cl))).cuda()
+        solver = bdist.CudaStepSolver(rows, cl, frames, m, graph_cols=cols)
+        dec = solver.dec
+        driver = bdist.ShardedLSD(solver, bdist.TorchComm())
 
-    def one():
-        dec.load(D)
-        dec.run()
-        C.check(dec.lib.bsub_finalize(dec.h, dec.stream()))
-        mask = torch.empty((frames, m), dtype=torch.uint8, device="cuda")
-        C.check(dec.lib.bsub_mask_stats_local(dec.h, 0, dec.stream()))
-        C.check(dec.lib.bsub_mask_stats_local(dec.h, 1, dec.stream()))
-        C.check(dec.lib.bsub_mask_dev(dec.h, 2.0, ctypes.c_void_p(mask.data_ptr()), dec.stream()))
-        return mask
+        def one():
+            solver.load(D)
+            driver.solve()
+            return driver.finish(2.0, want_mask=True)
+    else:
+        D = torch.from_numpy(synth.preprocess_u8(video)).cuda()              # float32 [frames][m]
+        dec = B.Decomposition(B.make_config(m, frames, C.PROX_GRAPH_LINF, rows, cols))
+        dec.set_graph_windows(None)
+
+        def one():
+            dec.load(D)
+            dec.run()
+            C.check(dec.lib.bsub_finalize(dec.h, dec.stream()))
+            mask = torch.empty((frames, m), dtype=torch.uint8, device="cuda")
+            C.check(dec.lib.bsub_mask_stats_local(dec.h, 0, dec.stream()))
+            C.check(dec.lib.bsub_mask_stats_local(dec.h, 1, dec.stream()))
+            C.check(dec.lib.bsub_mask_dev(dec.h, 2.0, ctypes.c_void_p(mask.data_ptr()), dec.stream()))
+            return mask
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 0)):          # --warmup 0 is allowed here: a 1080p x 300 graph solve takes minutes
         mask = one()
-    torch.cuda.synchronize()
-    sampler = sampler_cls(0)
-    sampler.start()
+    barrier()
+    sampler = sampler_cls(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     e0.record(stream)
     for _ in range(args.steps):
         mask = one()
     e1.record(stream)
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1) / args.steps
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    frac = torch.tensor([float(mask.float().sum().item()), float(mask.numel())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(frac)
+    ms = float(tmax.item()) / args.steps
+    if rank != 0:
+        return None
     st = dec.status()
     log = dec.log()
     cfg = {"workload": label, "rows": rows, "cols": cols, "frames": frames,
            "prox": "overlapping 3x3 windows at every pixel, l_inf (the reference's default LSD() graph mode)", "delta": 10,
+           "sharding": "one GPU" if world == 1 else "pixel columns over %d GPUs, frames around the prox (all-to-all)" % world,
            "timing": "CUDA events on the launching stream around whole decompositions; device-resident float32 D"}
     return _line(args, world, frames / (ms * 1e-3), ms, cfg,
                  {"data": "reference fixture (WaterSurface)" if label.startswith("watersurface") else "synthetic",
                   "alm_iters": int(st.iter), "converged": bool(st.converged), "rank_L": int(st.svp), "err": float(st.err),
-                  "rank_sequence": [int(l["svp"]) for l in log], "mask_fraction": float(mask.float().mean().item()),
+                  "rank_sequence": [int(l["svp"]) for l in log], "mask_fraction": float(frac[0].item() / frac[1].item()),
                   "ms_per_alm_iteration": ms / max(int(st.iter), 1), "clocks": clocks, "roofline": None, "cpu_baseline": None,
                   "e2e": {"value": None, "unit": "frames/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                           "what": "not measured for this workload"}, "gpu_launches": None})
